@@ -1,0 +1,327 @@
+"""Generate `tests/golden/*.npz` by EXECUTING THE UNMODIFIED REFERENCE in this container.
+
+Run here (the GPU box has no /root/reference):   python -m oracle.make_golden
+
+What is pinned (all from reference code, never from the oracle):
+  gae.npz        GAE.call               drl/algos/common/credit_assignment.py:195-214
+  standardize.npz standardize           drl/utils/stats.py:4-17
+  losses.npz     ppo_* loss functions   drl/algos/ppo.py:310-417 (+ composite, ppo.py:195-200)
+  ppo_2rank.npz  annotate + credit_assignment + PPO.optimize run as TWO gloo ranks with
+                 DDP(Agent(NatureCNN)) and torch.optim.Adam — the reference's deployment shape
+                 (script.py:112-116, launch.py:310) — on SURVEY §8(d) synthetic inputs.
+  normalizer.npz Normalizer.update/forward  drl/envs/wrappers/stateful/normalize.py:105-162
+  rnd.npz        RND teacher/student forward, predictor loss + grads
+                 drl/envs/wrappers/stateful/intrinsic/random_network_distillation.py:22-87,225-233
+Large tensors are stored as (sum, l2, strided sample) summaries to keep fixtures small.
+"""
+import os
+import sys
+
+import numpy as np
+import torch as tc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader, ppo_oracle as po  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+F32 = np.float32
+
+
+def summary(x: np.ndarray, n: int = 2048) -> np.ndarray:
+    """[sum, l2, sample...] of a big tensor (float64 accumulators)."""
+    f = np.asarray(x, np.float64).ravel()
+    stride = max(1, f.size // n)
+    return np.concatenate([[f.sum(), np.sqrt((f * f).sum())], f[::stride][:n]])
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_gae():
+    from drl.algos.common.credit_assignment import GAE
+    out = {}
+    cases = [(2, 0.99, 0.95, True), (16, 0.99, 0.95, True), (128, 0.99, 0.95, True),
+             (128, 0.999, 0.95, True), (128, 0.99, 0.95, False), (256, 0.99, 0.95, True),
+             (37, 0.9, 0.5, True)]
+    rs = np.random.RandomState(1234)
+    for i, (T, g, l, ud) in enumerate(cases):
+        r = rs.randint(-1, 2, size=(T,)).astype(F32) + (rs.standard_normal(T) * 0.1).astype(F32)
+        v = rs.standard_normal(T + 1).astype(F32)
+        d = (rs.uniform(size=T) < 0.05).astype(F32)
+        op = GAE(gamma=g, use_dones=ud, lambda_=l)
+        adv = op(rollout_len=T, extra_steps=0, rewards=tc.from_numpy(r), vpreds=tc.from_numpy(v),
+                 dones=tc.from_numpy(d)).numpy()
+        out.update({f'c{i}_meta': np.array([T, g, l, float(ud)]), f'c{i}_r': r, f'c{i}_v': v,
+                    f'c{i}_d': d, f'c{i}_adv': adv})
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'gae.npz'), **out)
+
+
+def gen_standardize():
+    from drl.utils.stats import standardize
+    rs = np.random.RandomState(7)
+    out = {}
+    for i, T in enumerate([10, 128, 256, 1000]):
+        x = (rs.standard_normal(T) * 3 + 1.5).astype(F32)
+        out[f'x{i}'] = x
+        out[f'y{i}'] = standardize(tc.from_numpy(x)).numpy()
+    out['n'] = np.array(4)
+    np.savez_compressed(os.path.join(GOLD, 'standardize.npz'), **out)
+
+
+def gen_losses():
+    from drl.algos.ppo import (ppo_policy_entropy_bonus, ppo_policy_surrogate_objective,
+                               ppo_vf_loss)
+    from drl.algos.common.losses import get_loss
+    rs = np.random.RandomState(99)
+    out = {}
+    cases = [(32, ['extrinsic'], {'extrinsic': 1.0}, 0.2, 0.01, 1.0, False, True, 'MSELoss'),
+             (64, ['extrinsic'], {'extrinsic': 1.0}, 0.1, 0.01, 0.5, True, True, 'MSELoss'),
+             (32, ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
+              0.1, 0.001, 0.5, False, True, 'MSELoss'),
+             (32, ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
+              0.1, 0.001, 0.5, True, False, 'MSELoss'),
+             (48, ['extrinsic'], {'extrinsic': 1.0}, 0.2, 0.0, 1.0, True, True, 'SmoothL1Loss')]
+    for i, (B, rk, rw, clip, entc, vfc, vclip, simple, crit) in enumerate(cases):
+        lp_old = np.log(rs.uniform(0.05, 0.5, B)).astype(F32)
+        lp_new = (lp_old + rs.standard_normal(B) * 0.2).astype(F32)
+        ent = rs.uniform(0.1, 1.7, B).astype(F32)
+        adv = {k: rs.standard_normal(B).astype(F32) for k in rk}
+        v_old = {k: rs.standard_normal(B).astype(F32) for k in rk}
+        v_new = {k: (v_old[k] + rs.standard_normal(B) * 0.3).astype(F32) for k in rk}
+        vt = {k: rs.standard_normal(B).astype(F32) for k in rk}
+        t = lambda a: tc.from_numpy(a)  # noqa: E731
+        e = ppo_policy_entropy_bonus(entropies=t(ent), ent_coef=entc)
+        p = ppo_policy_surrogate_objective(
+            logprobs_new=t(lp_new), logprobs_old=t(lp_old),
+            advantages={k: t(adv[k]) for k in rk}, clip_param=clip, reward_weights=rw)
+        vv = ppo_vf_loss(
+            vpreds_new={k: t(v_new[k]) for k in rk}, vpreds_old={k: t(v_old[k]) for k in rk},
+            vtargs={k: t(vt[k]) for k in rk}, clip_param=clip, vf_loss_criterion=get_loss(crit),
+            vf_loss_clipping=vclip, vf_simple_weighting=simple, reward_weights=rw)
+        policy_loss = -(p['policy_surrogate_objective'] + e['policy_entropy_bonus'])
+        composite = policy_loss + vfc * vv['vf_loss']
+        out[f'c{i}_hyper'] = np.array([clip, entc, vfc, float(vclip), float(simple),
+                                       float(crit == 'SmoothL1Loss')])
+        out[f'c{i}_keys'] = np.array(rk)
+        out[f'c{i}_weights'] = np.array([rw[k] for k in rk], F32)
+        out[f'c{i}_lp_old'], out[f'c{i}_lp_new'], out[f'c{i}_ent'] = lp_old, lp_new, ent
+        for k in rk:
+            out[f'c{i}_adv_{k}'], out[f'c{i}_vold_{k}'] = adv[k], v_old[k]
+            out[f'c{i}_vnew_{k}'], out[f'c{i}_vt_{k}'] = v_new[k], vt[k]
+        out[f'c{i}_out'] = np.array([float(policy_loss), float(vv['vf_loss']), float(composite),
+                                     float(e['state_averaged_entropy']), float(p['clipfrac'])], F32)
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'losses.npz'), **out)
+
+
+# ---------------------------------------------------------------------------------------------
+PPO2 = dict(T=16, B=8, A=6, epochs=2, seed=0, world=2, clip=0.2, ent=0.01, vf=1.0,
+            lr=1e-3, betas=(0.9, 0.999), eps=1e-5, gamma=0.99, lam=0.95, param_seed=11)
+
+
+def _ppo_rank(rank, world, port, cfg, rkeys, rweights, vclip, tag, retq):
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader as rl, ppo_oracle as po2
+    rl.load()
+    import gym
+    from drl.envs.wrappers.stateless.abstract import RewardSpec
+    from drl.agents.integration.agent import Agent
+    from drl.agents.preprocessing import ToChannelMajor
+    from drl.agents.architectures import NatureCNN, Linear
+    from drl.agents.heads import CategoricalPolicyHead, SimpleValueHead
+    from drl.algos.common.credit_assignment import GAE
+    from drl.algos.ppo import PPO
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    tc.distributed.init_process_group('gloo', rank=rank, world_size=world)
+    tc.set_num_threads(2)
+    T, B, A = cfg['T'], cfg['B'], cfg['A']
+
+    class SynthEnv(gym.core.Env):
+        def __init__(self):
+            self.observation_space = gym.spaces.Box(0., 1., (84, 84, 4), np.float32)
+            self.action_space = gym.spaces.Discrete(A)
+            self._rs = np.random.RandomState(5)
+
+        @property
+        def reward_spec(self):
+            return RewardSpec(keys=['extrinsic_raw'] + list(rkeys))
+
+        def reset(self):
+            return self._rs.uniform(size=(84, 84, 4)).astype(np.float32)
+
+        def step(self, a):
+            r = {k: 0.0 for k in ['extrinsic_raw'] + list(rkeys)}
+            return self.reset(), r, False, {}
+
+    preds = {'policy': CategoricalPolicyHead(512, A, Linear, {}, None, None)}
+    for k in rkeys:
+        preds[f'value_{k}'] = SimpleValueHead(512, Linear, {}, None, None)
+    agent = Agent([ToChannelMajor()], NatureCNN(4, None, None), preds)
+    init = po2.init_params(A, rkeys, seed=cfg['param_seed'])
+    sd = {k: tc.from_numpy(v.copy()) for k, v in init.items()}
+    agent.load_state_dict(sd, strict=True)
+    assert list(dict(agent.named_parameters()).keys()) == po2.param_keys(rkeys)
+    net = DDP(agent)
+    opt = tc.optim.Adam(net.parameters(), lr=cfg['lr'], betas=cfg['betas'], eps=cfg['eps'])
+    np.random.seed(10000 * rank + cfg['seed'])        # launch.py:33-45 seeding rule
+    tc.manual_seed(10000 * rank + cfg['seed'])
+    credit = {k: GAE(gamma=(cfg['gamma'] if k == 'extrinsic' else 0.99), use_dones=(k == 'extrinsic'),
+                     lambda_=cfg['lam']) for k in rkeys}
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    algo = PPO(rank=rank, world_size=world, rollout_len=T, extra_steps=0,
+               credit_assignment_ops=credit, stats_window_len=100, non_learning_steps=0,
+               max_steps=10 ** 9, checkpoint_frequency=10 ** 9, checkpoint_dir=tmp, log_dir=tmp,
+               media_dir=tmp, global_step=1, env=SynthEnv(), policy_net=net, policy_optimizer=opt,
+               policy_scheduler=None, value_net=None, value_optimizer=None, value_scheduler=None,
+               standardize_adv=True, opt_epochs=cfg['epochs'], learner_batch_size=B,
+               clip_param_init=cfg['clip'], clip_param_final=cfg['clip'],
+               ent_coef_init=cfg['ent'], ent_coef_final=cfg['ent'], vf_loss_cls='MSELoss',
+               vf_loss_coef=cfg['vf'], vf_loss_clipping=vclip, vf_simple_weighting=True,
+               use_pcgrad=False, reward_weights=(rweights if len(rkeys) > 1 else None))
+
+    raw = po2.make_synthetic_env_rollout(rank, cfg['seed'], T, A, rkeys)
+    rollout = dict(
+        observations=po2.scale_obs(tc.from_numpy(raw['observations'])),   # float32 NHWC, F4
+        actions=tc.from_numpy(raw['actions']),
+        rewards={k: tc.from_numpy(raw['rewards'][k]) for k in rkeys},
+        dones=tc.from_numpy(raw['dones']))
+    rollout = algo.annotate(rollout, no_grad=True)
+    rollout = algo.credit_assignment(rollout)
+
+    rec = {}
+    for k in rkeys:
+        rec[f'adv_{k}'] = rollout['advantages'][k].numpy().copy()
+        rec[f'vtarg_{k}'] = rollout['vtargs'][k].numpy().copy()
+        rec[f'vpred_{k}'] = rollout['vpreds'][k].numpy().copy()
+    rec['logp'] = rollout['logprobs'].numpy().copy()
+    rec['ent'] = rollout['entropies'].numpy().copy()
+
+    # record the permutations the sampler draws, the DDP-averaged grads of the first step, and
+    # the per-epoch global metrics
+    perms = []
+    orig_perm = np.random.permutation
+
+    def rec_perm(n):
+        p = orig_perm(n)
+        perms.append(np.asarray(p).copy())
+        return p
+    np.random.permutation = rec_perm
+    steps = []
+    orig_step = opt.step
+
+    def rec_step(*a, **k):
+        if len(steps) < 2:
+            steps.append({n: p.grad.detach().numpy().copy() for n, p in agent.named_parameters()})
+        return orig_step(*a, **k)
+    opt.step = rec_step
+    scalars = []
+    if rank == 0:
+        algo._writer.add_scalar = lambda tag, scalar_value, global_step: scalars.append((tag, float(scalar_value)))
+    import io
+    import contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        algo.optimize(rollout)
+    np.random.permutation = orig_perm
+
+    rec['perms'] = np.stack(perms)                      # [epochs, T]
+    for si, g in enumerate(steps):
+        for n, v in g.items():
+            rec[f'grad{si}::{n}'] = v if v.size <= 4096 else summary(v)
+    for n, p in agent.named_parameters():
+        v = p.detach().numpy()
+        rec[f'final::{n}'] = v.copy() if v.size <= 4096 else summary(v)
+    if rank == 0:
+        names = ['policy_loss', 'value_loss', 'composite_loss', 'meanent', 'clipfrac']
+        em = np.zeros((cfg['epochs'], 5), np.float64)
+        for stag, val in scalars:
+            ep, nm = stag.split('/')
+            em[int(ep.split('_')[1]), names.index(nm)] = val
+        rec['epoch_metrics'] = em
+    np.savez_compressed(os.path.join(GOLD, f'_{tag}_rank{rank}.npz'), **rec)
+    tc.distributed.destroy_process_group()
+
+
+def gen_ppo(tag, rkeys, rweights, vclip, port):
+    import torch.multiprocessing as mp
+    cfg = dict(PPO2)
+    mp.spawn(_ppo_rank, args=(cfg['world'], port, cfg, rkeys, rweights, vclip, tag, None),
+             nprocs=cfg['world'], join=True)
+    out = {'cfg_T': cfg['T'], 'cfg_B': cfg['B'], 'cfg_A': cfg['A'], 'cfg_epochs': cfg['epochs'],
+           'cfg_seed': cfg['seed'], 'cfg_world': cfg['world'], 'cfg_param_seed': cfg['param_seed'],
+           'cfg_hyper': np.array([cfg['clip'], cfg['ent'], cfg['vf'], cfg['lr'], cfg['betas'][0],
+                                  cfg['betas'][1], cfg['eps'], cfg['gamma'], cfg['lam'], float(vclip)]),
+           'cfg_rkeys': np.array(list(rkeys)),
+           'cfg_rweights': np.array([rweights[k] for k in rkeys], np.float64)}
+    for r in range(cfg['world']):
+        f = os.path.join(GOLD, f'_{tag}_rank{r}.npz')
+        d = np.load(f)
+        for k in d.files:
+            out[f'r{r}::{k}'] = d[k]
+        os.remove(f)
+    np.savez_compressed(os.path.join(GOLD, f'{tag}.npz'), **out)
+
+
+# ---------------------------------------------------------------------------------------------
+def gen_normalizer():
+    from drl.envs.wrappers.stateful.normalize import Normalizer
+    from oracle import rnd_oracle as ro
+    items, x = ro.normalizer_fixture_inputs()
+    nz = Normalizer([84, 84, 1], -5, 5)
+    for it in items:
+        nz.update(tc.from_numpy(it))
+    y = nz(tc.from_numpy(x)).numpy()
+    np.savez_compressed(os.path.join(GOLD, 'normalizer.npz'), y=summary(y),
+                        steps=np.array(float(nz.steps)), m1=summary(nz.moment1.numpy()),
+                        m2=summary(nz.moment2.numpy()))
+
+
+def gen_rnd():
+    from drl.envs.wrappers.stateful.intrinsic.random_network_distillation import (
+        _TeacherNetwork, _StudentNetwork)
+    from drl.envs.wrappers.stateful.normalize import Normalizer
+    from oracle import rnd_oracle as ro
+    teacher, student = _TeacherNetwork([84, 84, 1]), _StudentNetwork([84, 84, 1], 1)
+    # LAPACK-dependent orthogonal init replaced by the seeded numpy init the tests can rebuild
+    tinit, sinit = ro.init_net(False, 100), ro.init_net(True, 200)
+    assert [n for n, _ in teacher.named_parameters()] == ro.TEACHER_KEYS
+    assert [n for n, _ in student.named_parameters()] == ro.STUDENT_KEYS
+    teacher.load_state_dict({k: tc.from_numpy(v.copy()) for k, v in tinit.items()})
+    student.load_state_dict({k: tc.from_numpy(v.copy()) for k, v in sinit.items()})
+    items, obs_u8 = ro.rnd_fixture_inputs()
+    nz = Normalizer([84, 84, 1], -5, 5)
+    for it in items:
+        nz.update(tc.from_numpy(it))
+    obs = po.scale_obs(tc.from_numpy(obs_u8))[:, :, :, -1:]
+    normalized = nz(obs)
+    y, yh = teacher(normalized), student(normalized)
+    per = tc.square(y - yh).mean(dim=-1)
+    loss = per.mean(dim=0)
+    loss.backward()
+    out = dict(y=summary(y.detach().numpy()), yh=summary(yh.detach().numpy()),
+               per=per.detach().numpy(), loss=np.array(float(loss)))
+    for n, p in student.named_parameters():
+        g = p.grad.numpy()
+        out[f'sgrad::{n}'] = g if g.size <= 1024 else summary(g, 512)
+    np.savez_compressed(os.path.join(GOLD, 'rnd.npz'), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref_loader.load()
+    gen_gae()
+    gen_standardize()
+    gen_losses()
+    gen_normalizer()
+    gen_rnd()
+    gen_ppo('ppo_2rank', ['extrinsic'], {'extrinsic': 1.0}, False, 29611)
+    gen_ppo('ppo_2rank_rnd', ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
+            True, 29612)
+    print('golden vectors written to', GOLD)
+
+
+if __name__ == '__main__':
+    main()
