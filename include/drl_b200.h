@@ -1,0 +1,260 @@
+/*
+ * drl_b200.h — C-ABI of the B200-native learner hot path of lucaslingle/pytorch_drl.
+ *
+ * The reference has no FFI of its own: the path sits behind Python classes selected by name
+ * from YAML.  This header is the boundary a replacement exports underneath
+ * those classes: plain pointers and sizes, caller-owned device buffers, an explicit CUDA stream
+ * (passed as void*), int status codes, never a throw/abort across the boundary.  The Python
+ * shims in `pytorch_drl_b200/` bind it with ctypes and map status codes to ValueError /
+ * RuntimeError the way the reference raises them.  INTEGRATION.md shows the binding.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root).  All pointers are DEVICE pointers unless the name ends in `_host`.
+ * All calls are asynchronous with respect to the host and ordered on `stream`.
+ * A handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef DRL_B200_H_
+#define DRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRL_B200_ABI_VERSION 1
+
+/* ---- status codes (Python shim: 1,2,3 -> ValueError; others -> RuntimeError) ---------------- */
+enum {
+  DRL_OK = 0,
+  DRL_ERR_BAD_SHAPE = 1,    /* e.g. T % B != 0 (drl/algos/common/samplers.py:51), N<=0, A out of range */
+  DRL_ERR_BAD_ARG = 2,      /* null pointer, unknown enum value (drl/algos/common/credit_assignment.py:25) */
+  DRL_ERR_MISALIGNED = 3,   /* a pointer violates the stated alignment */
+  DRL_ERR_CUDA = 4,         /* a CUDA runtime/driver call failed; see drl_last_cuda_error() */
+  DRL_ERR_NO_DEVICE = 5,    /* no sm_100 device: there is NO CPU fallback */
+  DRL_ERR_UNSUPPORTED = 6,  /* valid request this build does not implement */
+  DRL_ERR_NCCL = 7
+};
+
+/* DRL_API: every symbol declared in this header is exported (default visibility). */
+int drl_abi_version(void);
+const char* drl_status_string(int status);
+/* cudaGetErrorString of the last CUDA failure seen by this library on this thread ("" if none). */
+const char* drl_last_cuda_error(void);
+/* 0 iff device `device` exists and is compute capability 10.x. */
+int drl_check_device(int device);
+
+/* =============================================================================================
+ * Credit assignment — replaces GAE.call (drl/algos/common/credit_assignment.py:195-214), the
+ * vtarg/standardize tail of ActorCriticAlgo.credit_assignment (drl/algos/abstract.py:427-439)
+ * and standardize (drl/utils/stats.py:4-17), for n_envs independent trajectories at once.
+ *
+ *   rewards [n_envs, ld_r]  first T entries used      vpreds [n_envs, ld_v]  first T+1 used
+ *   dones   [n_envs, ld_r]  (float 0/1)               adv/vtarg [n_envs, ld_o] first T written
+ *   nt = use_dones ? 1-d_t : 1;  delta_t = -V_t + r_t + nt*gamma*V_{t+1};
+ *   A_t = delta_t + nt*gamma*lambda*A_{t+1};  vtarg = A + V[:T];  if standardize:
+ *   A = (A-mean(A))/std_unbiased(A) per env (the reference's ranks are envs).
+ * One warp per env, reverse affine scan, float4 loads when T%4==0 and rows are 16B aligned.
+ * ============================================================================================= */
+int drl_gae_f32(const float* rewards, const float* vpreds, const float* dones,
+                int n_envs, int T, int ld_r, int ld_v, int ld_o,
+                float gamma, float lambda, int use_dones, int standardize,
+                float* adv_out, float* vtarg_out, void* stream);
+
+/* standardize alone (drl/utils/stats.py:4-17) on n_rows rows of length T. */
+int drl_standardize_f32(const float* x, int n_rows, int T, int ld, float* y, void* stream);
+
+/* =============================================================================================
+ * Fused PPO losses — replaces Categorical.log_prob/entropy (drl/algos/abstract.py:401-402),
+ * ppo_policy_entropy_bonus / ppo_policy_surrogate_objective / ppo_vf_loss
+ * (drl/algos/ppo.py:310-417), the composite (ppo.py:195-200) and their autograd backward
+ * w.r.t. logits and values, in one reduction kernel (warp shuffles + one atomic per block).
+ * ============================================================================================= */
+#define DRL_MAX_REWARD_STREAMS 4
+#define DRL_MAX_ACTIONS 32
+
+typedef struct {
+  int num_actions;                              /* A */
+  int num_streams;                              /* K reward streams, ordered like reward_weights */
+  float reward_weights[DRL_MAX_REWARD_STREAMS]; /* ppo.py:358-359 */
+  float clip_param;                             /* LinearSchedule value, schedules.py:18-29 */
+  float ent_coef;
+  float vf_coef;                                /* ppo.py:198 */
+  int vf_loss_clipping;                         /* ppo.py:403-409 */
+  int vf_simple_weighting;                      /* ppo.py:413-416 */
+  int vf_loss_kind;                             /* 0 MSELoss, 1 SmoothL1Loss (losses.py:6-18) */
+} drl_ppo_hyper_t;
+
+/* Per-sample tensors indexed through row_idx (NULL = identity): sample i of the minibatch reads
+ * row r = row_idx[i] of actions/logp_old/adv/v_old/vtarg — the gather of slice_nested_tensor
+ * (drl/utils/nested.py:6-12) folded into the kernel.  logits [nb, A] and values [nb, K] are the
+ * NEW predictions (dense, not indexed).  adv/v_old/vtarg: K device pointers passed by value.
+ * losses_out[5] (device) = policy_loss, value_loss, composite_loss, meanent, clipfrac
+ * (ppo.py:201-207); it is zeroed by the call.  dlogits [nb, A] / dvalues [nb, K] may be NULL
+ * (metrics pass, ppo.py:265-266); they hold d composite / d(.) with the 1/nb of the means. */
+typedef struct {
+  const int64_t* actions;
+  const float* logp_old;
+  const float* adv[DRL_MAX_REWARD_STREAMS];
+  const float* v_old[DRL_MAX_REWARD_STREAMS];
+  const float* vtarg[DRL_MAX_REWARD_STREAMS];
+} drl_ppo_batch_t;
+
+int drl_ppo_loss_fwd_bwd(const float* logits, const float* values, const int64_t* row_idx, int nb,
+                         const drl_ppo_batch_t* batch, const drl_ppo_hyper_t* hyper,
+                         float* losses_out, float* logp_out, float* entropy_out,
+                         float* dlogits, float* dvalues, void* stream);
+
+/* =============================================================================================
+ * NatureCNN agent — replaces Agent.forward (drl/agents/integration/agent.py:53-75) with
+ * ToChannelMajor (preprocessing/vision.py:4-9), NatureCNN (architectures/stateless/
+ * nature_cnn.py:27-36), CategoricalPolicyHead logits (heads/policy_heads.py:107) and
+ * SimpleValueHead (heads/value_heads.py:64), plus the autograd backward and the minibatch step
+ * of PPO._optimize_losses (drl/algos/ppo.py:225-240).
+ *
+ * Parameters live in ONE caller-owned flat fp32 buffer in the reference's own order and layouts
+ * (Agent.parameters(): conv OIHW weights, fc [512, c*49+h*7+w], heads [A,512],[1,512]; see
+ * drl_net_param_count / drl_net_param_offsets), so torch views of it are state_dict compatible
+ * (drl/utils/checkpointing.py:64).  Gradients are written to a second buffer of the same layout.
+ * Observations are uint8 NHWC [rows, 84, 84, 4] as the env emits them before ScaleObservations
+ * (scale_observations.py:35): the x*(1/255) is fused into conv1.
+ * ============================================================================================= */
+typedef struct drl_net drl_net_t;
+
+enum { DRL_PRECISION_FP32 = 0,   /* CUDA-core fp32 implicit GEMM: the strict-parity mode          */
+       DRL_PRECISION_BF16 = 1 }; /* tcgen05 bf16 implicit GEMM, fp32 accumulate: throughput mode */
+
+int drl_net_create(drl_net_t** out, int device, int max_batch, int num_actions, int num_values,
+                   int precision);
+int drl_net_destroy(drl_net_t* net);
+/* number of fp32 parameters (1 687 719 for A=6,K=1) and the 2*(5+K) tensor offsets in order. */
+int64_t drl_net_param_count(int num_actions, int num_values);
+int drl_net_param_offsets(int num_actions, int num_values, int64_t* offsets_host, int max_entries);
+
+/* (Re)bind the flat parameter buffer; in bf16 mode also refreshes the packed bf16 operand copies.
+ * Must be called after the caller changed parameters by other means than drl_net_adam_step. */
+int drl_net_set_params(drl_net_t* net, const float* params, void* stream);
+
+/* No-grad forward (annotate, drl/algos/abstract.py:383-411; actor, rollout.py:284-287):
+ * logits [nb, A], values [nb, K]; logp/entropy of `actions` (indexed by row_idx) if non-NULL. */
+int drl_net_forward(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb,
+                    float* logits, float* values, const int64_t* actions, float* logp_out,
+                    float* entropy_out, void* stream);
+
+/* One learner step without the optimiser: forward, fused losses, backward.  grads (flat, same
+ * layout as params) is OVERWRITTEN with d composite / d params, where composite is the mean over
+ * the nb samples (== mean over ranks of per-rank means for equal shards).
+ * losses_out[5] as in drl_ppo_loss_fwd_bwd. */
+int drl_net_ppo_step(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb,
+                     const drl_ppo_batch_t* batch, const drl_ppo_hyper_t* hyper,
+                     float* grads, float* losses_out, void* stream);
+
+/* Full-rollout metrics pass (ppo.py:265-266): forward + losses, no backward. */
+int drl_net_ppo_metrics(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb,
+                        const drl_ppo_batch_t* batch, const drl_ppo_hyper_t* hyper,
+                        float* losses_out, void* stream);
+
+/* debug / parity access to the last step's intermediate activations (device pointers owned by
+ * the handle; layout NHWC; dtype fp32 in FP32 mode, bf16 in BF16 mode). which: 1..3 conv
+ * activations, 4 features [nb,512] (always fp32). */
+int drl_net_activation(drl_net_t* net, int which, const void** ptr, int64_t* elems, int* dtype_bytes);
+/* device-to-device copy on `stream` (lets a binding read handle-owned buffers). */
+int drl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+
+/* =============================================================================================
+ * Optimiser — replaces torch.optim.Adam.step as configured by drl/utils/optimization.py:9-35
+ * (models_dir/atari_ppo/config.yaml:76-78: betas, eps=1e-5; no amsgrad, no weight decay) on a
+ * flat buffer.  grad_scale multiplies the gradient first (1/world after a SUM allreduce).
+ * `step` is the 1-based update count.  One vectorised pass: 28 B/param of HBM traffic.
+ * ============================================================================================= */
+int drl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                  void* stream);
+/* Adam on the handle's parameters, also refreshing the packed operand copies (BF16 mode). */
+int drl_net_adam_step(drl_net_t* net, float* params, const float* grads, float* exp_avg,
+                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                      int64_t step, float grad_scale, void* stream);
+
+/* =============================================================================================
+ * Observation normaliser — replaces Normalizer.forward / update
+ * (drl/envs/wrappers/stateful/normalize.py:129-162, 105-127).
+ * ============================================================================================= */
+/* y[i, j] = clip((x[i, j] - m1[j]) * rsqrt(m2[j] - m1[j]^2 + eps), lo, hi); x is n x d */
+int drl_normalizer_apply_f32(const float* x, const float* m1, const float* m2, int64_t n, int64_t d,
+                             float eps, float clip_lo, float clip_hi, float* y, void* stream);
+/* Running-moment update with `count` items x[count, d] applied in order; steps_before is the
+ * normaliser's step count before the first item. */
+int drl_normalizer_update_f32(float* m1, float* m2, const float* x, int64_t count, int64_t d,
+                              double steps_before, void* stream);
+
+/* =============================================================================================
+ * RND predictor — replaces the arithmetic of RandomNetworkDistillationWrapper.learn and .step
+ * (drl/envs/wrappers/stateful/intrinsic/random_network_distillation.py:209-235, 186-201) with
+ * _TeacherNetwork / _StudentNetwork (same file :22-87).  Flat parameter buffers in
+ * `named_parameters()` order, reference layouts.
+ * ============================================================================================= */
+typedef struct drl_rnd drl_rnd_t;
+int drl_rnd_create(drl_rnd_t** out, int device, int max_batch, int widening, int precision);
+int drl_rnd_destroy(drl_rnd_t* rnd);
+int64_t drl_rnd_param_count(int student, int widening);
+int drl_rnd_set_params(drl_rnd_t* rnd, const float* teacher_params, const float* student_params,
+                       void* stream);
+/* Intrinsic reward (step, :193-196): err[i] = mean_d (teacher - student)^2 of the normalised,
+ * clipped LAST channel of uint8 frame row_idx[i]; no gradient. */
+int drl_rnd_reward(drl_rnd_t* rnd, const uint8_t* obs, const int64_t* row_idx, int nb,
+                   const float* m1, const float* m2, float* err_out, void* stream);
+/* Predictor loss and student gradients (learn, :225-232): loss_out[0] = mean_b mean_d (y-yh)^2;
+ * student_grads (flat) overwritten. */
+int drl_rnd_learn(drl_rnd_t* rnd, const uint8_t* obs, const int64_t* row_idx, int nb,
+                  const float* m1, const float* m2, float* student_grads, float* loss_out,
+                  void* stream);
+
+/* =============================================================================================
+ * Prioritized-replay sum-tree.  NO REFERENCE IMPLEMENTATION EXISTS (the reference only
+ * cites Schaul et al. 2015 at README.md:15): parity is against oracle/sumtree.c, "parity unpinned".
+ * Layout: implicit binary heap in one fp32 array tree[2*cap] (cap a power of two): node 1 is
+ * the root, leaves are tree[cap + i]; parent = fp32(left + right), recomputed (never delta
+ * updated) so results are bit-reproducible.
+ * ============================================================================================= */
+/* Set leaf idx[j] = prio[j] for j in [0,n) (last writer wins on duplicates: the highest j), then
+ * recompute every affected ancestor level by level. idx int64 in [0,cap). */
+int drl_sumtree_update(float* tree, int64_t cap, const int64_t* idx, const float* prio, int64_t n,
+                       void* stream);
+/* Rebuild all internal nodes from the leaves. */
+int drl_sumtree_rebuild(float* tree, int64_t cap, void* stream);
+/* Prefix-sum descent for n query masses u[j] in [0, total): at each node go left if u < left
+ * else subtract left and go right.  idx_out[j] = leaf index, prio_out[j] = its priority. */
+int drl_sumtree_sample(const float* tree, int64_t cap, const float* u, int64_t n,
+                       int64_t* idx_out, float* prio_out, void* stream);
+/* Stratified masses (Schaul et al. 2015 §3.3): u[j] = (j + uniform01[j]) * total / n, computed
+ * on device in fp32 from caller-supplied uniforms so the host RNG stays the seed authority. */
+int drl_sumtree_stratified_u(const float* tree, const float* uniform01, int64_t n, float* u_out,
+                             void* stream);
+
+/* =============================================================================================
+ * Gradient exchange — replaces the DistributedDataParallel wrapper (drl/utils/launch.py:310;
+ * allreduce inside backward, drl/algos/ppo.py:233) and global_mean
+ * (drl/algos/common/metrics.py:8-26).  One process per GPU; the communicator is created from
+ * an NCCL unique id the caller broadcasts (e.g. through torch.distributed).
+ * ============================================================================================= */
+typedef struct drl_comm drl_comm_t;
+#define DRL_NCCL_UNIQUE_ID_BYTES 128
+int drl_comm_unique_id(uint8_t* id_host /* [128] */);
+int drl_comm_create(drl_comm_t** out, const uint8_t* id_host, int rank, int world, int device);
+int drl_comm_destroy(drl_comm_t* comm);
+/* In-place SUM allreduce of a flat fp32 buffer in `n_buckets` buckets given by bucket_offsets
+ * [n_buckets+1] (host, elements), issued in order on `stream`. */
+int drl_grad_allreduce_bucketed(drl_comm_t* comm, float* flat, const int64_t* bucket_offsets_host,
+                                int n_buckets, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* DRL_B200_H_ */

@@ -1,0 +1,59 @@
+"""`Communicator`: the data-parallel plumbing that replaces the reference's
+DistributedDataParallel wrapper (drl/utils/launch.py:310) and `global_mean`
+(drl/algos/common/metrics.py:8-26).  One process per GPU; the NCCL communicator lives in the
+C-ABI library and is bootstrapped with a unique id broadcast through torch.distributed."""
+import ctypes
+from typing import List, Optional
+
+import torch as tc
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+
+class Communicator:
+    def __init__(self, rank: int, world_size: int, device_index: int):
+        self.rank, self.world = rank, world_size
+        L = _lib.lib()
+        ident = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)()
+        if rank == 0:
+            check(L.drl_comm_unique_id(ident), 'comm_unique_id')
+        t = tc.tensor(list(ident), dtype=tc.uint8)
+        if world_size > 1:
+            if not dist.is_initialized():
+                raise RuntimeError('torch.distributed must be initialised to bootstrap the communicator')
+            if dist.get_backend() == 'nccl':
+                t = t.cuda(device_index)
+            dist.broadcast(t, src=0)
+        ident = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)(*t.cpu().tolist())
+        h = ctypes.c_void_p()
+        check(L.drl_comm_create(ctypes.byref(h), ident, rank, world_size, device_index), 'comm_create')
+        self._h, self._L = h, L
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h:
+            self._L.drl_comm_destroy(h)
+
+    @staticmethod
+    def grad_buckets(offsets: List[int]) -> List[int]:
+        """Two buckets in reverse-backward order of availability: trunk convs
+        [0, fc.weight) and fc + heads [fc.weight, end)."""
+        return [0, offsets[6], offsets[-1]]
+
+    def allreduce_(self, flat: tc.Tensor, bucket_offsets: Optional[List[int]] = None) -> tc.Tensor:
+        offs = bucket_offsets or [0, flat.numel()]
+        arr = (ctypes.c_int64 * len(offs))(*offs)
+        check(self._L.drl_grad_allreduce_bucketed(self._h, ptr(flat), arr, len(offs) - 1, current_stream()),
+              'grad_allreduce')
+        return flat
+
+    def allreduce_grads(self, engine) -> None:
+        self.allreduce_(engine.grads, self.grad_buckets(engine.offsets))
+
+    def mean_(self, vec: tc.Tensor) -> tc.Tensor:
+        """global_mean of a small fp32 CUDA vector (metrics.py:8-26), one collective."""
+        v = vec.contiguous()
+        self.allreduce_(v)
+        return v / self.world

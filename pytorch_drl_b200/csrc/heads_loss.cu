@@ -1,0 +1,248 @@
+// Fused policy/value heads + PPO losses + their backward (K5 + K6 + K8 + head part of K9).
+//
+// Replaces, for one minibatch: CategoricalPolicyHead logits (drl/agents/heads/policy_heads.py:107),
+// SimpleValueHead (drl/agents/heads/value_heads.py:64), Categorical.log_prob/entropy
+// (drl/algos/abstract.py:401-402), the three ppo_* loss functions and the composite
+// (drl/algos/ppo.py:310-417, 195-200), and autograd's backward through all of them down to the
+// pre-ReLU gradient of the 512 features (nature_cnn.py:35-36) plus the head weight/bias grads.
+//
+// One warp per sample: the 512 features are read once (coalesced), the A+K dot products are
+// reduced with shuffles, every lane evaluates the scalar loss math, d(feat) is written once.
+// Head weight gradients are accumulated in registers by the whole CTA over tiles of 8 samples
+// (no shared-memory atomics) and flushed with one global atomicAdd per element per CTA.
+#include "ppo_math.cuh"
+#include "net.cuh"
+
+namespace drl {
+
+constexpr int kFeat = 512;
+constexpr int kWarps = 8;
+
+
+template <typename T> __device__ __forceinline__ void store_act(T* p, float v);
+template <> __device__ __forceinline__ void store_act<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store_act<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// MODE 0: forward only (logits/values/logp/entropy);  MODE 1: + losses;  MODE 2: + backward.
+template <int MAXA, int MODE, typename TD>
+__global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
+    const float* __restrict__ feat, HeadParams hp_ptrs, const int64_t* __restrict__ row_idx, int nb,
+    drl_ppo_batch_t batch, drl_ppo_hyper_t hp, float inv_nb, float* __restrict__ losses_out,
+    float* __restrict__ logits_out, float* __restrict__ values_out, float* __restrict__ logp_out,
+    float* __restrict__ ent_out, TD* __restrict__ dpre) {
+  constexpr int MAXO = MAXA + DRL_MAX_REWARD_STREAMS;
+  extern __shared__ float smem[];
+  const int A = hp.num_actions, K = hp.num_streams, O = A + K;
+  float* Ws = smem;                              // [O][512]
+  float* bs = Ws + (size_t)O * kFeat;            // [O]
+  float* sf = bs + MAXO;                         // [kWarps][512]  features of the tile
+  float* sd = sf + kWarps * kFeat;               // [kWarps][MAXO] d(out) of the tile
+  float* red = sd + kWarps * MAXO;               // [128]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int e = threadIdx.x; e < O * kFeat; e += blockDim.x) {
+    const int o = e / kFeat, c = e % kFeat;
+    Ws[e] = o < A ? hp_ptrs.wp[o * kFeat + c] : hp_ptrs.wv[o - A][c];
+  }
+  if (threadIdx.x < O) bs[threadIdx.x] = threadIdx.x < A ? hp_ptrs.bp[threadIdx.x] : hp_ptrs.bv[threadIdx.x - A][0];
+  __syncthreads();
+
+  float gw[MAXO][2];
+  float gb = 0.f;
+  if (MODE == 2) {
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) { gw[o][0] = 0.f; gw[o][1] = 0.f; }
+  }
+  PpoSums acc{0.f, 0.f, 0.f, 0.f};
+  const int ntiles = (nb + kWarps - 1) / kWarps;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i = tile * kWarps + warp;
+    const bool live = i < nb;
+    float f[16];
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) f[q] = feat[(size_t)i * kFeat + lane + 32 * q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) f[q] = 0.f;
+    }
+    float out[MAXO];
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < O) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s = fmaf(f[q], Ws[o * kFeat + lane + 32 * q], s);
+        out[o] = warp_sum(s) + bs[o];
+      } else {
+        out[o] = 0.f;
+      }
+    }
+    float logit[MAXA], dlogit[MAXA], v_new[DRL_MAX_REWARD_STREAMS], dv[DRL_MAX_REWARD_STREAMS];
+#pragma unroll
+    for (int j = 0; j < MAXA; ++j) logit[j] = j < A ? out[j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) {
+      // out[A + k] with a compile-time-unrollable select
+      float v = 0.f;
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o) if (o == A + k) v = out[o];
+      v_new[k] = v;
+      dv[k] = 0.f;
+    }
+    if (live) {
+      if (logits_out && lane < A) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) if (j == lane) v = logit[j];
+        logits_out[(size_t)i * A + lane] = v;
+      }
+      if (values_out && lane < K) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) if (k == lane) v = v_new[k];
+        values_out[(size_t)i * K + lane] = v;
+      }
+    }
+    if (MODE == 0) {
+      if (live && (logp_out || ent_out)) {
+        PpoSampleIn in{};
+        in.action = batch.actions ? (int)batch.actions[row_idx ? row_idx[i] : (int64_t)i] : 0;
+        PpoSums s;
+        float logp, ent;
+        drl_ppo_hyper_t h2 = hp;
+        h2.num_streams = 0;
+        ppo_sample<MAXA>(logit, v_new, in, h2, 0.f, false, dlogit, dv, s, logp, ent);
+        if (lane == 0) {
+          if (logp_out) logp_out[i] = logp;
+          if (ent_out) ent_out[i] = ent;
+        }
+      }
+      continue;
+    }
+    if (live) {
+      PpoSampleIn in;
+      load_sample(batch, K, row_idx ? row_idx[i] : (int64_t)i, in);
+      PpoSums s;
+      float logp, ent;
+      ppo_sample<MAXA>(logit, v_new, in, hp, inv_nb, MODE == 2, dlogit, dv, s, logp, ent);
+      if (lane == 0) {
+        acc.surr += s.surr; acc.ent += s.ent; acc.clip += s.clip; acc.vf += s.vf;
+        if (logp_out) logp_out[i] = logp;
+        if (ent_out) ent_out[i] = ent;
+      }
+    }
+    if (MODE == 2) {
+      // d(out) of this sample -> smem; features -> smem (for the CTA-wide head wgrad)
+      float dout[MAXO];
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o) {
+        float v = 0.f;
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j) if (j == o && o < A) v = dlogit[j];
+#pragma unroll
+          for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) if (o == A + k && k < K) v = dv[k];
+        }
+        dout[o] = v;
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) sd[warp * MAXO + o] = dout[o];
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) sf[warp * kFeat + lane + 32 * q] = f[q];
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float d = 0.f;
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) if (o < O) d = fmaf(dout[o], Ws[o * kFeat + lane + 32 * q], d);
+          d = f[q] > 0.f ? d : 0.f;                       // ReLU of the fc layer (nature_cnn.py:36)
+          store_act<TD>(dpre + (size_t)i * kFeat + lane + 32 * q, d);
+        }
+      }
+      __syncthreads();
+      const int c0 = threadIdx.x, c1 = threadIdx.x + kWarps * 32;
+#pragma unroll
+      for (int s = 0; s < kWarps; ++s) {
+        const float f0 = sf[s * kFeat + c0], f1 = sf[s * kFeat + c1];
+#pragma unroll
+        for (int o = 0; o < MAXO; ++o) {
+          if (o < O) {
+            const float d = sd[s * MAXO + o];
+            gw[o][0] = fmaf(d, f0, gw[o][0]);
+            gw[o][1] = fmaf(d, f1, gw[o][1]);
+          }
+        }
+        if (threadIdx.x < O) gb += sd[s * MAXO + threadIdx.x];
+      }
+      __syncthreads();
+    }
+  }
+  if (MODE >= 1) {
+    PpoSums tot = block_reduce_sums(acc, red);
+    if (threadIdx.x == 0) ppo_accumulate_losses(tot, hp, inv_nb, losses_out);
+  }
+  if (MODE == 2) {
+    const int c0 = threadIdx.x, c1 = threadIdx.x + kWarps * 32;
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < O) {
+        float* g = o < A ? hp_ptrs.gwp + o * kFeat : hp_ptrs.gwv[o - A];
+        atomicAdd(g + c0, gw[o][0]);
+        atomicAdd(g + c1, gw[o][1]);
+      }
+    }
+    if (threadIdx.x < O) {
+      float* g = threadIdx.x < A ? hp_ptrs.gbp + threadIdx.x : hp_ptrs.gbv[threadIdx.x - A];
+      atomicAdd(g, gb);
+    }
+  }
+}
+
+template <int MAXA, int MODE, typename TD>
+static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t* row_idx, int nb,
+                        const drl_ppo_batch_t& batch, const drl_ppo_hyper_t& hp, float* losses_out,
+                        float* logits_out, float* values_out, float* logp_out, float* ent_out,
+                        TD* dpre, cudaStream_t st) {
+  constexpr int MAXO = MAXA + DRL_MAX_REWARD_STREAMS;
+  const int O = hp.num_actions + hp.num_streams;
+  const size_t smem = sizeof(float) * ((size_t)O * kFeat + MAXO + kWarps * kFeat + kWarps * MAXO + 128);
+  auto kern = heads_loss_kernel<MAXA, MODE, TD>;
+  DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ntiles = (nb + kWarps - 1) / kWarps;
+  int blocks = ntiles < sm_count() * 2 ? ntiles : sm_count() * 2;
+  kern<<<blocks, kWarps * 32, smem, st>>>(feat, hpp, row_idx, nb, batch, hp, 1.0f / (float)nb,
+                                          losses_out, logits_out, values_out, logp_out, ent_out, dpre);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+// mode: 0 forward, 1 losses, 2 losses + backward.  dpre_is_bf16 selects the d(feat) dtype.
+int heads_loss_dispatch(int mode, bool dpre_is_bf16, const float* feat, const HeadParams& hpp,
+                        const int64_t* row_idx, int nb, const drl_ppo_batch_t& batch,
+                        const drl_ppo_hyper_t& hp, float* losses_out, float* logits_out,
+                        float* values_out, float* logp_out, float* ent_out, void* dpre,
+                        cudaStream_t st) {
+  const int A = hp.num_actions;
+#define GO(MAXA, MODE, TD) \
+  return launch_heads<MAXA, MODE, TD>(feat, hpp, row_idx, nb, batch, hp, losses_out, logits_out, \
+                                      values_out, logp_out, ent_out, (TD*)dpre, st)
+#define BY_MODE(MAXA)                                              \
+  do {                                                             \
+    if (mode == 0) GO(MAXA, 0, float);                             \
+    if (mode == 1) GO(MAXA, 1, float);                             \
+    if (dpre_is_bf16) GO(MAXA, 2, __nv_bfloat16);                  \
+    GO(MAXA, 2, float);                                            \
+  } while (0)
+  if (A <= 8) BY_MODE(8);
+  if (A <= 18) BY_MODE(18);
+  BY_MODE(32);
+#undef BY_MODE
+#undef GO
+}
+
+}  // namespace drl

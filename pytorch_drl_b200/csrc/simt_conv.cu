@@ -1,0 +1,226 @@
+// FP32 CUDA-core implicit-GEMM convolution engine: the strict-parity mode of the NatureCNN trunk
+// (DRL_PRECISION_FP32).  Forward, data-gradient and weight-gradient of every trunk layer
+// (nature_cnn.py:27-36; the fc layer is a 7x7 "conv" over the 7x7x64 map so that the NCHW flatten
+// order c*49+h*7+w of nature_cnn.py:34 is honoured) run through ONE tiled SIMT GEMM whose
+// operands are fetched by gather functors, directly on the reference's parameter layouts (OIHW).
+// Activations are NHWC fp32.  conv1 reads uint8 frames and applies x*(1/255) exactly like
+// scale_observations.py:35, with the minibatch gather (nested.py:6-12) folded into the row index.
+#include "common.cuh"
+#include "simt_conv.cuh"
+
+namespace drl {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <bool A_M_FAST, class AF, class BF, class EF>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int k_per_split, AF af,
+                                                        BF bf, EF ef) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // M tiles on x: up to 2^31-1 blocks
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + 256 * i;
+      const int kk = A_M_FAST ? e / BM : e % BK;
+      const int mm = A_M_FAST ? e % BM : e / BK;
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < kend) ? af(m, k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + 256 * i;
+      const int kk = e / BN, nn = e % BN;
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < kend) ? bf(k, n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) ef(m, n, acc[i][j]);
+    }
+  }
+}
+
+// ---- gather functors ----------------------------------------------------------------------------
+template <typename TIn> __device__ __forceinline__ float load_in(const TIn* p, size_t i);
+template <> __device__ __forceinline__ float load_in<float>(const float* p, size_t i) { return __ldg(p + i); }
+template <> __device__ __forceinline__ float load_in<uint8_t>(const uint8_t* p, size_t i) {
+  return __fmul_rn((float)__ldg(p + i), __uint_as_float(0x3b808081u));   // float32(1/255)
+}
+
+// im2col element: row r = (b, oy, ox) of the output grid, column c = (ky, kx, ci)
+template <typename TIn>
+struct PatchGather {
+  const TIn* in; const int64_t* row_idx; ConvGeom g;
+  __device__ __forceinline__ float operator()(int r, int c) const {
+    const int pos = g.OH * g.OW;
+    const int b = r / pos, rem = r - b * pos;
+    const int oy = rem / g.OW, ox = rem - oy * g.OW;
+    const int kc = g.KW * g.Cin;
+    const int ky = c / kc, r2 = c - ky * kc;
+    const int kx = r2 / g.Cin, ci = r2 - kx * g.Cin;
+    const size_t row = row_idx ? (size_t)row_idx[b] : (size_t)b;
+    return load_in<TIn>(in, ((row * g.H + (oy * g.S + ky)) * g.W + (ox * g.S + kx)) * g.Cin + ci);
+  }
+};
+
+struct WeightFwd {            // B(k=(ky,kx,ci), n=co) = W[co, ci, ky, kx]
+  const float* w; ConvGeom g;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    const int kc = g.KW * g.Cin;
+    const int ky = k / kc, r2 = k - ky * kc;
+    const int kx = r2 / g.Cin, ci = r2 - kx * g.Cin;
+    return __ldg(w + ((size_t)(n * g.Cin + ci) * g.KH + ky) * g.KW + kx);
+  }
+};
+
+template <typename TOut>
+struct EpiBiasRelu {
+  const float* bias; TOut* out; int N;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    out[(size_t)m * N + n] = fmaxf(acc + __ldg(bias + n), 0.f);
+  }
+};
+
+// dgrad: A(m=(b,iy,ix), k=(ky,kx,co)) = dY[b,(iy-ky)/S,(ix-kx)/S,co] when that lands on the grid
+struct DyGather {
+  const float* dy; ConvGeom g;
+  __device__ __forceinline__ float operator()(int m, int k) const {
+    const int pos = g.H * g.W;
+    const int b = m / pos, rem = m - b * pos;
+    const int iy = rem / g.W, ix = rem - iy * g.W;
+    const int kc = g.KW * g.Cout;
+    const int ky = k / kc, r2 = k - ky * kc;
+    const int kx = r2 / g.Cout, co = r2 - kx * g.Cout;
+    const int ty = iy - ky, tx = ix - kx;
+    if (ty < 0 || tx < 0) return 0.f;
+    const int oy = ty / g.S, ox = tx / g.S;
+    if (oy * g.S != ty || ox * g.S != tx || oy >= g.OH || ox >= g.OW) return 0.f;
+    return __ldg(dy + (((size_t)b * g.OH + oy) * g.OW + ox) * g.Cout + co);
+  }
+};
+
+struct WeightDgrad {          // B(k=(ky,kx,co), n=ci) = W[co, ci, ky, kx]
+  const float* w; ConvGeom g;
+  __device__ __forceinline__ float operator()(int k, int n) const {
+    const int kc = g.KW * g.Cout;
+    const int ky = k / kc, r2 = k - ky * kc;
+    const int kx = r2 / g.Cout, co = r2 - kx * g.Cout;
+    return __ldg(w + ((size_t)(co * g.Cin + n) * g.KH + ky) * g.KW + kx);
+  }
+};
+
+struct EpiReluMask {          // dX = acc * (X > 0): ReLU of the producing layer
+  const float* x_act; float* dx; int N;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    const size_t i = (size_t)m * N + n;
+    dx[i] = __ldg(x_act + i) > 0.f ? acc : 0.f;
+  }
+};
+
+struct DyT {                  // wgrad A'(m=co, k=r) = dY[r, co]
+  const float* dy; int Cout;
+  __device__ __forceinline__ float operator()(int m, int k) const { return __ldg(dy + (size_t)k * Cout + m); }
+};
+
+template <typename TIn>
+struct PatchGatherT {         // wgrad B'(k=r, n=(ky,kx,ci)) plus a ones column (n == Kp) for the bias
+  PatchGather<TIn> pg; int Kp;
+  __device__ __forceinline__ float operator()(int k, int n) const { return n < Kp ? pg(k, n) : 1.f; }
+};
+
+struct EpiWgrad {             // scatter-add into the OIHW gradient (+ bias gradient)
+  float* gw; float* gb; ConvGeom g; int Kp;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    if (n < Kp) {
+      const int kc = g.KW * g.Cin;
+      const int ky = n / kc, r2 = n - ky * kc;
+      const int kx = r2 / g.Cin, ci = r2 - kx * g.Cin;
+      atomicAdd(gw + ((size_t)(m * g.Cin + ci) * g.KH + ky) * g.KW + kx, acc);
+    } else {
+      atomicAdd(gb + m, acc);
+    }
+  }
+};
+
+static inline dim3 tiles(int M, int N, int z = 1) { return dim3((M + BM - 1) / BM, (N + BN - 1) / BN, z); }
+
+template <typename TIn>
+int simt_conv_forward(const TIn* in, const int64_t* row_idx, int nb, const ConvGeom& g, const float* w,
+                      const float* bias, float* out, cudaStream_t st) {
+  const int M = nb * g.OH * g.OW, N = g.Cout, K = g.KH * g.KW * g.Cin;
+  PatchGather<TIn> af{in, row_idx, g};
+  WeightFwd bf{w, g};
+  EpiBiasRelu<float> ef{bias, out, N};
+  simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+template int simt_conv_forward<float>(const float*, const int64_t*, int, const ConvGeom&, const float*,
+                                      const float*, float*, cudaStream_t);
+template int simt_conv_forward<uint8_t>(const uint8_t*, const int64_t*, int, const ConvGeom&,
+                                        const float*, const float*, float*, cudaStream_t);
+
+int simt_conv_dgrad(const float* dy, int nb, const ConvGeom& g, const float* w, const float* x_act,
+                    float* dx, cudaStream_t st) {
+  const int M = nb * g.H * g.W, N = g.Cin, K = g.KH * g.KW * g.Cout;
+  DyGather af{dy, g};
+  WeightDgrad bf{w, g};
+  EpiReluMask ef{x_act, dx, N};
+  simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+template <typename TIn>
+int simt_conv_wgrad(const float* dy, const TIn* in, const int64_t* row_idx, int nb, const ConvGeom& g,
+                    float* gw, float* gb, cudaStream_t st) {
+  const int Kp = g.KH * g.KW * g.Cin;
+  const int M = g.Cout, N = Kp + 1, K = nb * g.OH * g.OW;
+  // split the (long) reduction over the rows so that the grid fills the machine
+  const int base = tiles(M, N).x * tiles(M, N).y;
+  int splits = (sm_count() * 4 + base - 1) / base;
+  int k_per = (K + splits - 1) / splits;
+  k_per = ((k_per + BK - 1) / BK) * BK;
+  splits = (K + k_per - 1) / k_per;
+  DyT af{dy, g.Cout};
+  PatchGatherT<TIn> bf{PatchGather<TIn>{in, row_idx, g}, Kp};
+  EpiWgrad ef{gw, gb, g, Kp};
+  simt_gemm_kernel<true><<<tiles(M, N, splits), 256, 0, st>>>(M, N, K, k_per, af, bf, ef);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+template int simt_conv_wgrad<float>(const float*, const float*, const int64_t*, int, const ConvGeom&,
+                                    float*, float*, cudaStream_t);
+template int simt_conv_wgrad<uint8_t>(const float*, const uint8_t*, const int64_t*, int,
+                                      const ConvGeom&, float*, float*, cudaStream_t);
+
+}  // namespace drl

@@ -1,0 +1,113 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header
+declares, the ctypes prototypes cover the header, the host-side drop-in logic (samplers,
+schedules, reward bookkeeping, Agent construction / state_dict names) behaves like the
+reference's, and the product path fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch as tc
+
+import pytorch_drl_b200 as pkg
+from pytorch_drl_b200 import _lib, agents, algos
+from pytorch_drl_b200.engine import param_names
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'drl_b200.h')
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(drl_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_header_symbol():
+    assert os.path.exists(_lib.LIB_PATH), 'build with python -m pytorch_drl_b200.build'
+    out = subprocess.check_output(['nm', '-D', '--defined-only', _lib.LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if ' T ' in l}
+    syms = header_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if s not in exported]
+    assert not missing, missing
+
+
+def test_ctypes_prototypes_cover_header():
+    assert sorted(_lib.PROTOTYPES.keys()) == header_symbols()
+    L = _lib.lib()
+    assert L.drl_abi_version() == 1
+    assert L.drl_status_string(1) == b'bad shape'
+
+
+def test_param_layout_matches_reference_agent():
+    L = _lib.lib()
+    assert L.drl_net_param_count(6, 1) == 1687719
+    assert L.drl_net_param_count(18, 2) == 1693875 + 513
+    import ctypes
+    offs = (ctypes.c_int64 * 13)()
+    assert L.drl_net_param_offsets(6, 1, offs, 13) == 0
+    assert list(offs)[:9] == [0, 8192, 8224, 40992, 41056, 77920, 77984, 1683616, 1684128]
+    assert L.drl_net_param_offsets(6, 1, offs, 3) == 1     # bad shape -> ValueError in the shim
+    with pytest.raises(ValueError):
+        _lib.check(1, 'x')
+    with pytest.raises(RuntimeError):
+        _lib.check(5, 'x')
+
+
+def test_no_device_means_loud_failure_not_fallback():
+    if tc.cuda.is_available():
+        pytest.skip('GPU present')
+    assert _lib.lib().drl_check_device(0) == 5
+    with pytest.raises(RuntimeError):
+        _lib.require_device(0)
+    ag = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4),
+                      {'policy': agents.CategoricalPolicyHead(512, 6), 'value_extrinsic': agents.SimpleValueHead(512)})
+    with pytest.raises(RuntimeError):
+        ag.fuse(8)
+    with pytest.raises(RuntimeError):
+        ag(tc.zeros(1, 84, 84, 4, dtype=tc.uint8), ['policy'])
+    from pytorch_drl_b200 import ops
+    with pytest.raises(ValueError):
+        ops.standardize(tc.arange(10.0))               # CPU tensor is rejected, never computed
+
+
+def test_agent_state_dict_names_match_reference_layout():
+    ag = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4),
+                      {'policy': agents.CategoricalPolicyHead(512, 6),
+                       'value_extrinsic': agents.SimpleValueHead(512),
+                       'value_intrinsic_rnd': agents.SimpleValueHead(512)})
+    assert [n for n, _ in ag.named_parameters()] == param_names(['value_extrinsic', 'value_intrinsic_rnd'])
+    with pytest.raises(ValueError):
+        agents.Agent([], agents.NatureCNN(4), {'policy': agents.CategoricalPolicyHead(512, 6),
+                                                 'bogus': agents.SimpleValueHead(512)})
+
+
+def test_sampler_disjoint_cover_and_seed_stream():
+    """drl/algos/common/test_samplers.py: blocks are disjoint and cover range(T); the stream
+    equals np.random.permutation under the reference's seeding rule."""
+    rs = np.random.RandomState(10000 * 3 + 0)
+    s = algos.IndependentSampler(128, 32, rs)
+    s.resample()
+    blocks = list(iter(s))
+    assert len(blocks) == 4 and all(b.shape == (32,) for b in blocks)
+    assert sorted(np.concatenate(blocks).tolist()) == list(range(128))
+    ref = np.random.RandomState(10000 * 3 + 0)
+    ref.permutation(128)
+    np.testing.assert_array_equal(np.concatenate(blocks), ref.permutation(128))
+    with pytest.raises(AssertionError):
+        algos.IndependentSampler(100, 32)              # samplers.py:51
+
+
+def test_linear_schedule():
+    s = algos.LinearSchedule(0.2, 0.0, 100)             # schedules.py:18-29
+    assert s.value(0) == 0.2 and s.value(100) == 0.0 and abs(s.value(50) - 0.1) < 1e-12
+    assert s.value(1000) == 0.0
+
+
+def test_credit_op_registry():
+    op = algos.get_credit_assignment_op('GAE', dict(gamma=0.99, lambda_=0.95, use_dones=True))
+    assert isinstance(op, algos.GAE)
+    with pytest.raises(ValueError):
+        algos.get_credit_assignment_op('Nope', {})     # credit_assignment.py:25

@@ -1,0 +1,368 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs,
+the committed golden vectors, and size-independent properties at BASELINE sizes.
+All tests need a B200:  python -m pytest tests -m gpu
+Tolerances are stated per test; integer/index work is bit-exact."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch as tc
+
+from oracle import ppo_oracle as po, rnd_oracle as ro, sumtree_oracle as so
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def dev():
+    return tc.device('cuda', 0)
+
+
+def cu(a):
+    return tc.as_tensor(np.ascontiguousarray(a)).to(dev())
+
+
+# ---- GAE / standardize -------------------------------------------------------------------------------
+def test_gae_vs_reference_golden(golden_dir):
+    from pytorch_drl_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'gae.npz'))
+    for i in range(int(g['ncases'])):
+        T, gamma, lam, ud = g[f'c{i}_meta']
+        T = int(T)
+        adv, vt = ops.gae(cu(g[f'c{i}_r'][None]), cu(g[f'c{i}_v'][None]), cu(g[f'c{i}_d'][None]),
+                          float(gamma), float(lam), bool(ud), False, T)
+        ref = g[f'c{i}_adv']
+        # warp-parallel affine scan re-associates the recurrence: fp32 tolerance, not bit-exact
+        np.testing.assert_allclose(adv.cpu().numpy()[0], ref, rtol=2e-5, atol=2e-6, err_msg=f'case {i}')
+        np.testing.assert_allclose(vt.cpu().numpy()[0], ref + g[f'c{i}_v'][:T], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize('N,T,use_dones,std', [(1024, 128, True, True), (64, 256, True, True),
+                                               (33, 128, False, True), (7, 37, True, False), (5, 1000, True, True)])
+def test_gae_batched_vs_oracle(N, T, use_dones, std):
+    from pytorch_drl_b200 import ops
+    rs = np.random.RandomState(N + T)
+    ld = (T + 1 + 3) // 4 * 4
+    r = np.zeros((N, ld), F32); v = np.zeros((N, ld), F32); d = np.zeros((N, ld), F32)
+    r[:, :T] = rs.randint(-1, 2, size=(N, T)); v[:, :T + 1] = rs.standard_normal((N, T + 1))
+    d[:, :T] = rs.uniform(size=(N, T)) < 0.01
+    adv, vt = ops.gae(cu(r), cu(v), cu(d), 0.99, 0.95, use_dones, std, T)
+    adv, vt = adv.cpu().numpy(), vt.cpu().numpy()
+    for e in list(range(min(N, 6))) + [N - 1]:
+        a_ref, vt_ref = po.credit_assignment(T, 0, r[e, :T], v[e, :T + 1], d[e, :T], 0.99, 0.95, use_dones, std)
+        np.testing.assert_allclose(adv[e], a_ref, rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(vt[e], vt_ref, rtol=2e-5, atol=2e-5)
+    if std:   # property at full size: per-env zero mean / unit unbiased std
+        np.testing.assert_allclose(adv.mean(1), 0, atol=1e-5)
+        np.testing.assert_allclose(adv.std(1, ddof=1), 1, rtol=1e-4)
+
+
+def test_standardize_golden(golden_dir):
+    from pytorch_drl_b200.utils import standardize
+    g = np.load(os.path.join(golden_dir, 'standardize.npz'))
+    for i in range(int(g['n'])):
+        np.testing.assert_allclose(standardize(cu(g[f'x{i}'])).cpu().numpy(), g[f'y{i}'], rtol=1e-5, atol=1e-6)
+
+
+def test_gae_dropin_signature():
+    from pytorch_drl_b200.algos import GAE
+    op = GAE(gamma=0.99, use_dones=True, lambda_=0.95)        # test_credit_assignment.py:7-61
+    adv = op(rollout_len=2, extra_steps=0, rewards=cu(np.array([0., 0.], F32)),
+             vpreds=cu(np.array([0., 0., 1.], F32)), dones=cu(np.array([1., 0.], F32)))
+    np.testing.assert_allclose(adv.cpu().numpy(), [0.0, 0.99], rtol=1.3e-6, atol=1e-5)
+
+
+# ---- fused losses -------------------------------------------------------------------------------------
+def _random_loss_case(rs, B, A, rk, rw, clip, entc, vfc, vclip, simple, crit='MSELoss'):
+    logits = (rs.standard_normal((B, A)) * 1.5).astype(F32)
+    actions = rs.randint(0, A, size=B).astype(np.int64)
+    values = {k: rs.standard_normal(B).astype(F32) for k in rk}
+    lt = tc.from_numpy(logits)
+    logp_new, _ = po.categorical_logprob_entropy(lt, tc.from_numpy(actions))
+    lp_old = (logp_new.numpy() + rs.standard_normal(B) * 0.3).astype(F32)
+    adv = {k: rs.standard_normal(B).astype(F32) for k in rk}
+    v_old = {k: (values[k] + rs.standard_normal(B) * 0.3).astype(F32) for k in rk}
+    vt = {k: rs.standard_normal(B).astype(F32) for k in rk}
+    return dict(logits=logits, actions=actions, values=values, lp_old=lp_old, adv=adv, v_old=v_old, vt=vt)
+
+
+def _oracle_loss(c, rk, rw, clip, entc, vfc, vclip, simple, crit):
+    logits = tc.from_numpy(c['logits']).requires_grad_(True)
+    vals = {k: tc.from_numpy(c['values'][k]).requires_grad_(True) for k in rk}
+    logp, ent = po.categorical_logprob_entropy(logits, tc.from_numpy(c['actions']))
+    out = po.ppo_losses(logp, ent, vals, tc.from_numpy(c['lp_old']), {k: tc.from_numpy(c['adv'][k]) for k in rk},
+                        {k: tc.from_numpy(c['v_old'][k]) for k in rk}, {k: tc.from_numpy(c['vt'][k]) for k in rk},
+                        rw, clip, entc, vfc, vclip, simple, crit)
+    out['composite_loss'].backward()
+    return ({k: float(v) for k, v in out.items()}, logits.grad.numpy(),
+            np.stack([vals[k].grad.numpy() for k in rk], 1), logp.detach().numpy(), ent.detach().numpy())
+
+
+@pytest.mark.parametrize('B,A,rk,rw,clip,entc,vfc,vclip,simple,crit', [
+    (32, 6, ['extrinsic'], {'extrinsic': 1.0}, 0.2, 0.01, 1.0, False, True, 'MSELoss'),
+    (4096, 6, ['extrinsic'], {'extrinsic': 1.0}, 0.1, 0.01, 0.5, True, True, 'MSELoss'),
+    (1000, 18, ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0}, 0.1, 0.001, 0.5, True, False, 'MSELoss'),
+    (257, 18, ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0}, 0.1, 0.001, 0.5, False, True, 'SmoothL1Loss'),
+    (64, 32, ['extrinsic'], {'extrinsic': 1.0}, 0.2, 0.0, 1.0, True, True, 'SmoothL1Loss')])
+def test_fused_loss_kernel_vs_oracle(B, A, rk, rw, clip, entc, vfc, vclip, simple, crit):
+    from pytorch_drl_b200 import ops
+    rs = np.random.RandomState(B + A)
+    c = _random_loss_case(rs, B, A, rk, rw, clip, entc, vfc, vclip, simple, crit)
+    ref, dl_ref, dv_ref, logp_ref, ent_ref = _oracle_loss(c, rk, rw, clip, entc, vfc, vclip, simple, crit)
+    hyper = ops.make_hyper(A, [rw[k] for k in rk], clip, entc, vfc, vclip, simple, crit)
+    keep = [cu(c['actions']), cu(c['lp_old'])] + [cu(c['adv'][k]) for k in rk] + [cu(c['v_old'][k]) for k in rk] + [cu(c['vt'][k]) for k in rk]
+    K = len(rk)
+    batch = ops.make_batch(keep[0], keep[1], keep[2:2 + K], keep[2 + K:2 + 2 * K], keep[2 + 2 * K:])
+    losses, logp, ent, dl, dv = ops.ppo_loss(cu(c['logits']), cu(np.stack([c['values'][k] for k in rk], 1)), batch, hyper)
+    got = dict(zip(ops.LOSS_NAMES, losses.cpu().tolist()))
+    for n in ('policy_loss', 'value_loss', 'composite_loss', 'meanent'):
+        np.testing.assert_allclose(got[n], ref[n], rtol=2e-5, atol=2e-6, err_msg=n)
+    assert abs(got['clipfrac'] - ref['clipfrac']) <= 1.0 / B + 1e-6
+    np.testing.assert_allclose(logp.cpu().numpy(), logp_ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ent.cpu().numpy(), ent_ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dl.cpu().numpy(), dl_ref, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(dv.cpu().numpy(), dv_ref, rtol=1e-4, atol=1e-7)
+
+
+def test_fused_loss_reference_known_answers():
+    """drl/algos/test_ppo.py:17-41 and :44-88 through the kernel (logits chosen so that
+    log-softmax reproduces the test's probabilities)."""
+    from pytorch_drl_b200 import ops
+    p_new = np.array([0.105, 0.08, 0.24, 0.095, 0.12, 0.16])
+    logits = np.log(np.stack([p_new, 1 - p_new], 1)).astype(F32)
+    lp_old = np.log(np.array([0.10, 0.10, 0.20, 0.10, 0.10, 0.20])).astype(F32)
+    adv = np.array([1, 1, 1, -1, -1, -1], F32)
+    v_new = np.array([1.05, 2.4, 1.2, -1.05, -2.4, -1.2], F32)
+    v_old = np.array([1.0, 2.0, 1.0, -1.0, -2.0, -1.0], F32)
+    vt = np.array([1.5, 1.5, 1.5, -1.5, -1.5, -1.5], F32)
+    keep = [cu(np.zeros(6, np.int64)), cu(lp_old), cu(adv), cu(v_old), cu(vt)]
+    batch = ops.make_batch(keep[0], keep[1], [keep[2]], [keep[3]], [keep[4]])
+    for vclip, exp_v in ((False, [1.05, 2.4, 1.2, -1.05, -2.4, -1.2]), (True, [1.05, 2.4, 1.1, -1.05, -2.4, -1.1])):
+        hyper = ops.make_hyper(2, [1.0], 0.10, 0.0, 1.0, vclip, True)
+        losses, *_ = ops.ppo_loss(cu(logits), cu(v_new[:, None]), batch, hyper, want_grad=False)
+        got = losses.cpu().numpy()
+        np.testing.assert_allclose(-got[0], np.mean([1.05, 0.80, 1.10, -0.95, -1.20, -0.90]), rtol=2e-6, atol=1e-5)
+        np.testing.assert_allclose(got[1], np.mean([(a - b) ** 2 for a, b in zip(exp_v, [1.5] * 3 + [-1.5] * 3)]), rtol=2e-6, atol=1e-5)
+
+
+# ---- Adam ---------------------------------------------------------------------------------------------
+def test_adam_vs_torch_semantics():
+    from pytorch_drl_b200 import ops
+    rs = np.random.RandomState(5)
+    n = 1687719
+    p = rs.standard_normal(n).astype(F32); m = np.zeros(n, F32); v = np.zeros(n, F32)
+    P, M, V = cu(p), cu(m), cu(v)
+    for step in range(1, 4):
+        g = (rs.standard_normal(n) * 0.01).astype(F32)
+        po.adam_step(p, g, m, v, step, 1e-3, 0.9, 0.999, 1e-5)
+        ops.adam_step(P, cu(g), M, V, step, 1e-3, (0.9, 0.999), 1e-5)
+    np.testing.assert_allclose(P.cpu().numpy(), p, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(M.cpu().numpy(), m, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(V.cpu().numpy(), v, rtol=1e-6, atol=1e-12)
+
+
+# ---- sum-tree: bit-exact vs the C oracle -----------------------------------------------------------------
+@pytest.mark.parametrize('cap,batch', [(64, 20), (1 << 20, 512), (1 << 20, 3000)])
+def test_sumtree_bit_exact(cap, batch):
+    from pytorch_drl_b200.replay import SumTree
+    rs = np.random.RandomState(cap % 1000 + batch)
+    ref = so.SumTree(cap)
+    gpu = SumTree(cap)
+    init = rs.uniform(0, 1, size=cap).astype(F32)
+    ref.tree[cap:] = init
+    ref.rebuild()
+    gpu.set_leaves(cu(init))
+    assert np.array_equal(gpu.tree.cpu().numpy().view(np.uint32), ref.tree.view(np.uint32))
+    for it in range(3):
+        idx = rs.randint(0, cap, size=batch).astype(np.int64)
+        if it == 1:
+            idx[: batch // 4] = idx[0]                 # collisions: the highest j wins
+        pr = rs.uniform(0.001, 5.0, size=batch).astype(F32)
+        ref.update(idx, pr)
+        gpu.update(cu(idx), cu(pr))
+        assert np.array_equal(gpu.tree.cpu().numpy().view(np.uint32), ref.tree.view(np.uint32)), f'update {it}'
+        uni = rs.uniform(size=batch).astype(F32)
+        u_ref = ref.stratified_u(uni)
+        u_gpu = gpu.stratified_u(cu(uni))
+        assert np.array_equal(u_gpu.cpu().numpy().view(np.uint32), u_ref.view(np.uint32))
+        i_ref, p_ref = ref.sample(u_ref)
+        i_gpu, p_gpu = gpu.sample(u_gpu)
+        assert np.array_equal(i_gpu.cpu().numpy(), i_ref)           # sampled transitions: bit-exact
+        assert np.array_equal(p_gpu.cpu().numpy().view(np.uint32), p_ref.view(np.uint32))
+
+
+def test_sumtree_edge_cases():
+    from pytorch_drl_b200.replay import SumTree
+    t = SumTree(8)
+    t.update(cu(np.zeros(0, np.int64)), cu(np.zeros(0, F32)))        # empty batch
+    t.update(cu(np.array([3], np.int64)), cu(np.array([2.0], F32)))
+    idx, pr = t.sample(cu(np.array([0.0, 1.999, 5.0], F32)))            # u >= total falls on the last massive leaf
+    assert idx.cpu().tolist() == [3, 3, 3] and pr.cpu().tolist() == [2.0, 2.0, 2.0]
+    with pytest.raises(ValueError):
+        SumTree(12)
+
+
+# ---- normaliser ----------------------------------------------------------------------------------------
+def test_normalizer_vs_reference_golden(golden_dir):
+    from pytorch_drl_b200 import ops
+    from tests.test_oracle_golden import close_to_summary
+    g = np.load(os.path.join(golden_dir, 'normalizer.npz'))
+    items, x = ro.normalizer_fixture_inputs()
+    m1 = tc.zeros(84 * 84, device=dev()); m2 = tc.zeros(84 * 84, device=dev())
+    steps = ops.normalizer_update(m1, m2, cu(items), 0.0)
+    assert steps == float(g['steps'])
+    close_to_summary(m1.cpu().numpy(), g['m1'], rtol=1e-6, always=True)
+    close_to_summary(m2.cpu().numpy(), g['m2'], rtol=1e-6, always=True)
+    y = ops.normalizer_apply(cu(x), m1, m2)
+    close_to_summary(y.cpu().numpy(), g['y'], rtol=1e-5, always=True)
+
+
+# ---- NatureCNN + PPO step -------------------------------------------------------------------------------
+def _build(precision, A, rk, max_batch, param_seed=11):
+    from pytorch_drl_b200.engine import LearnerEngine
+    eng = LearnerEngine(A, [f'value_{k}' for k in rk], max_batch, precision)
+    params = po.init_params(A, rk, seed=param_seed)
+    eng.load_named({k: tc.from_numpy(v) for k, v in params.items()})
+    return eng, params
+
+
+TOL = {   # (rtol on the relative L2 error of a tensor, abs tol on losses)
+    'fp32': dict(act=2e-5, grad=2e-4, loss=2e-5),
+    'bf16': dict(act=1.5e-2, grad=4e-2, loss=3e-3),
+}
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _precisions():
+    return ['fp32', 'bf16']
+
+
+@pytest.mark.parametrize('precision', _precisions())
+def test_forward_vs_oracle(precision):
+    A, rk, nb = 6, ['extrinsic'], 37
+    eng, params = _build(precision, A, rk, 64)
+    rs = np.random.RandomState(3)
+    obs = rs.randint(0, 256, size=(50, 84, 84, 4), dtype=np.uint8)
+    rows = rs.permutation(50)[:nb].astype(np.int64)
+    actions = rs.randint(0, A, size=50).astype(np.int64)
+    logits, values, logp, ent = eng.forward(cu(obs), cu(rows), actions=cu(actions))
+    keep = {}
+    p = {k: tc.from_numpy(v) for k, v in params.items()}
+    with tc.no_grad():
+        feat = po.trunk_forward(p, po.scale_obs(tc.from_numpy(obs[rows])), keep)
+        l_ref, v_ref = po.heads_forward(p, feat, rk)
+        lp_ref, e_ref = po.categorical_logprob_entropy(l_ref, tc.from_numpy(actions[rows]))
+    t = TOL[precision]
+    for i, name in enumerate(['act1', 'act2', 'act3']):
+        got = eng.activation(i + 1, nb).float().cpu().numpy().reshape((nb,) + tuple(keep[name].shape[2:]) + (keep[name].shape[1],))
+        ref = keep[name].permute(0, 2, 3, 1).numpy()
+        assert rel_l2(got, ref) < t['act'], (name, rel_l2(got, ref))
+    assert rel_l2(eng.activation(4, nb).cpu().numpy().reshape(nb, 512), keep['feat'].numpy()) < t['act']
+    assert rel_l2(logits.cpu().numpy(), l_ref.numpy()) < t['act']
+    assert rel_l2(values.cpu().numpy()[:, 0], v_ref['extrinsic'].numpy()) < t['act']
+    np.testing.assert_allclose(logp.cpu().numpy(), lp_ref.numpy(), rtol=0, atol=t['loss'])
+    np.testing.assert_allclose(ent.cpu().numpy(), e_ref.numpy(), rtol=0, atol=t['loss'])
+
+
+def _ppo_case(A, rk, n_envs, T, B, seed=0):
+    params = po.init_params(A, rk, seed=11)
+    credit = {k: dict(gamma=0.99, lambda_=0.95, use_dones=(k == 'extrinsic')) for k in rk}
+    raws = [po.make_synthetic_env_rollout(r, seed, T, A, rk) for r in range(n_envs)]
+    rollouts = [po.collect_from_raw(params, raw, T, credit, True) for raw in raws]
+    return params, raws, rollouts, credit
+
+
+@pytest.mark.parametrize('precision', _precisions())
+@pytest.mark.parametrize('A,rk,rw,vclip', [(6, ['extrinsic'], {'extrinsic': 1.0}, False),
+                                           (18, ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0}, True)])
+def test_ppo_step_losses_and_grads_vs_oracle(precision, A, rk, rw, vclip):
+    from pytorch_drl_b200 import ops
+    from pytorch_drl_b200.algos import RolloutStorage
+    n_envs, T, B = 3, 16, 8
+    params, raws, rollouts, credit = _ppo_case(A, rk, n_envs, T, B)
+    eng, _ = _build(precision, A, rk, n_envs * B)
+    st = RolloutStorage(n_envs, T, rk, dev())
+    d = st.as_dict()
+    for e in range(n_envs):
+        st.load_env(e, raws[e]['observations'], raws[e]['actions'], raws[e]['rewards'], raws[e]['dones'])
+        d['logprobs'][e, :T] = cu(rollouts[e]['logprobs'])
+        for k in rk:
+            d['advantages'][k][e, :T] = cu(rollouts[e]['advantages'][k])
+            d['vpreds'][k][e, :T] = cu(rollouts[e]['vpreds'][k])
+            d['vtargs'][k][e, :T] = cu(rollouts[e]['vtargs'][k])
+    rs = np.random.RandomState(9)
+    blocks = [rs.permutation(T)[:B] for _ in range(n_envs)]
+    rows = np.concatenate([b + e * st.Tp for e, b in enumerate(blocks)]).astype(np.int64)
+    hp = po.Hyper(rw, 0.1, 0.01, 0.5, vclip, True)
+    ref_m, ref_g = po.minibatch_losses_and_grads(params, [po.slice_env(rollouts[e], blocks[e]) for e in range(n_envs)], hp)
+    hyper = ops.make_hyper(A, [rw[k] for k in rk], 0.1, 0.01, 0.5, vclip, True)
+    batch = ops.make_batch(d['actions'], d['logprobs'], [d['advantages'][k] for k in rk],
+                           [d['vpreds'][k] for k in rk], [d['vtargs'][k] for k in rk])
+    losses = eng.ppo_step(d['observations'], cu(rows), batch, hyper).cpu().numpy()
+    t = TOL[precision]
+    got = dict(zip(ops.LOSS_NAMES, losses))
+    for n in ('policy_loss', 'value_loss', 'composite_loss', 'meanent'):
+        np.testing.assert_allclose(got[n], ref_m[n], rtol=t['loss'], atol=t['loss'], err_msg=n)
+    assert abs(got['clipfrac'] - ref_m['clipfrac']) <= 2.0 / (n_envs * B) + 1e-6
+    gv = eng.named_views(eng.grads)
+    worst = {}
+    for k in po.param_keys(rk):
+        worst[k] = rel_l2(gv[k].cpu().numpy(), ref_g[k])
+    bad = {k: v for k, v in worst.items() if not v < t['grad']}
+    assert not bad, bad
+    # metrics-only pass agrees with the step's losses
+    m2 = eng.ppo_step(d['observations'], cu(rows), batch, hyper, grads=False).cpu().numpy()
+    np.testing.assert_allclose(m2, losses, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('precision', ['fp32'])
+@pytest.mark.parametrize('tag', ['ppo_2rank', 'ppo_2rank_rnd'])
+def test_ppo_optimize_vs_reference_2rank_golden(golden_dir, precision, tag):
+    """The drop-in PPO.optimize on one GPU with envs_per_rank=2 against the UNMODIFIED reference run
+    as 2 gloo ranks (tests/golden/ppo_2rank*.npz): final parameters, first-step grads, epoch metrics."""
+    from pytorch_drl_b200 import agents, algos
+    from tests.test_oracle_golden import close_to_summary
+    g = np.load(os.path.join(golden_dir, f'{tag}.npz'))
+    T, B, A, epochs = int(g['cfg_T']), int(g['cfg_B']), int(g['cfg_A']), int(g['cfg_epochs'])
+    seed, world = int(g['cfg_seed']), int(g['cfg_world'])
+    clip, ent, vf, lr, b1, b2, eps, gamma, lam, vclip = [float(x) for x in g['cfg_hyper']]
+    rk = [str(k) for k in g['cfg_rkeys']]
+    rw = {k: float(w) for k, w in zip(rk, g['cfg_rweights'])}
+    preds = {'policy': agents.CategoricalPolicyHead(512, A)}
+    for k in rk:
+        preds[f'value_{k}'] = agents.SimpleValueHead(512)
+    agent = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4), preds)
+    agent.load_state_dict({k: tc.from_numpy(v) for k, v in po.init_params(A, rk, int(g['cfg_param_seed'])).items()})
+    agent.fuse(max_batch=world * (T + 1), precision=precision)
+    opt = tc.optim.Adam(agent.parameters(), lr=lr, betas=(b1, b2), eps=eps)
+    credit = {k: algos.GAE(gamma=(gamma if k == 'extrinsic' else 0.99), use_dones=(k == 'extrinsic'), lambda_=lam) for k in rk}
+    algo = algos.PPO(rank=0, world_size=1, rollout_len=T, extra_steps=0, credit_assignment_ops=credit,
+                     global_step=1, max_steps=10 ** 9, policy_net=agent, policy_optimizer=opt,
+                     standardize_adv=True, opt_epochs=epochs, learner_batch_size=B, clip_param_init=clip,
+                     clip_param_final=clip, ent_coef_init=ent, ent_coef_final=ent, vf_loss_coef=vf,
+                     vf_loss_clipping=bool(vclip), reward_weights=(rw if len(rk) > 1 else None),
+                     envs_per_rank=world, sampler_seed=seed)
+    st = algos.RolloutStorage(world, T, rk, dev())
+    for r in range(world):
+        raw = po.make_synthetic_env_rollout(r, seed, T, A, rk)
+        st.load_env(r, raw['observations'], raw['actions'], raw['rewards'], raw['dones'])
+    rollout = algo.credit_assignment(algo.annotate(st.as_dict()))
+    for r in range(world):
+        np.testing.assert_allclose(rollout['logprobs'][r, :T].cpu().numpy(), g[f'r{r}::logp'], rtol=1e-4, atol=1e-5)
+        for k in rk:
+            np.testing.assert_allclose(rollout['advantages'][k][r, :T].cpu().numpy(), g[f'r{r}::adv_{k}'], rtol=2e-3, atol=2e-4)
+            np.testing.assert_allclose(rollout['vtargs'][k][r, :T].cpu().numpy(), g[f'r{r}::vtarg_{k}'], rtol=1e-4, atol=1e-5)
+    algo.optimize(rollout)
+    final = {k: v.detach().cpu().numpy() for k, v in agent.state_dict().items()}
+    for k in po.param_keys(rk):
+        close_to_summary(final[k], g[f'r0::final::{k}'], rtol=2e-3, atol=5e-5)
+    em = g['r0::epoch_metrics']
+    for ep in range(epochs):
+        got = np.array([algo.last_epoch_metrics[ep][n] for n in algos.ppo.METRIC_NAMES])
+        np.testing.assert_allclose(got[:4], em[ep][:4], rtol=5e-3, atol=5e-5)
+        assert abs(got[4] - em[ep][4]) <= 2.0 / T + 1e-6
