@@ -47,6 +47,13 @@ const char* drl_status_string(int status);
 const char* drl_last_cuda_error(void);
 /* 0 iff device `device` exists and is compute capability 10.x. */
 int drl_check_device(int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long drl_launch_count(void);
+/* Per-launch-site CUDA-event timing on the launching stream.  drl_profile_read synchronises the
+ * device, returns for each site seen since the last read its name (48-char slots), summed
+ * milliseconds and launch count, and clears the records. */
+int drl_profile_enable(int on);
+int drl_profile_read(int max_sites, char* names_out, float* total_ms, int* counts, int* n_sites);
 
 /* =============================================================================================
  * Credit assignment — replaces GAE.call (drl/algos/common/credit_assignment.py:195-214), the
@@ -170,13 +177,14 @@ int drl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
  * (models_dir/atari_ppo/config.yaml:76-78: betas, eps=1e-5; no amsgrad, no weight decay) on a
  * flat buffer.  grad_scale multiplies the gradient first (1/world after a SUM allreduce).
  * `step` is the 1-based update count.  One vectorised pass: 28 B/param of HBM traffic.
+ * Hyper-parameters are doubles because torch forms 1-beta and lr/bias_correction in double.
  * ============================================================================================= */
 int drl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                  float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                  double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale,
                   void* stream);
 /* Adam on the handle's parameters, also refreshing the packed operand copies (BF16 mode). */
 int drl_net_adam_step(drl_net_t* net, float* params, const float* grads, float* exp_avg,
-                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                      float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
                       int64_t step, float grad_scale, void* stream);
 
 /* =============================================================================================

@@ -37,6 +37,9 @@ PROTOTYPES = {
     'drl_status_string': (c_char_p, [c_int]),
     'drl_last_cuda_error': (c_char_p, []),
     'drl_check_device': (c_int, [c_int]),
+    'drl_launch_count': (ctypes.c_longlong, []),
+    'drl_profile_enable': (c_int, [c_int]),
+    'drl_profile_read': (c_int, [c_int, ctypes.c_char_p, POINTER(c_float), POINTER(c_int), POINTER(c_int)]),
     'drl_gae_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                             c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'drl_standardize_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -56,10 +59,10 @@ PROTOTYPES = {
                                     POINTER(PpoHyper), c_void_p, c_void_p]),
     'drl_net_activation': (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]),
     'drl_memcpy_d2d': (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
-    'drl_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
-                              c_float, c_float, c_int64, c_float, c_void_p]),
-    'drl_net_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
-                                  c_float, c_float, c_int64, c_float, c_void_p]),
+    'drl_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
+                              c_double, c_double, c_int64, c_float, c_void_p]),
+    'drl_net_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
+                                  c_double, c_double, c_int64, c_float, c_void_p]),
     'drl_normalizer_apply_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float,
                                          c_float, c_float, c_void_p, c_void_p]),
     'drl_normalizer_update_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double,

@@ -6,12 +6,12 @@
 
 namespace drl {
 
-struct AdamCoef { float lr_bc1, inv_sqrt_bc2, beta1, beta2, eps, gscale; };
+struct AdamCoef { float lr_bc1, inv_sqrt_bc2, beta1, beta2, omb1, omb2, eps, gscale; };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamCoef& c) {
   g *= c.gscale;
-  m = m + (g - m) * (1.f - c.beta1);                 // exp_avg.lerp_(grad, 1-beta1)
-  v = v * c.beta2 + (1.f - c.beta2) * g * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+  m = m + (g - m) * c.omb1;                 // exp_avg.lerp_(grad, 1-beta1)
+  v = v * c.beta2 + c.omb2 * g * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
   const float denom = sqrtf(v) * c.inv_sqrt_bc2 + c.eps;
   p = p - c.lr_bc1 * (m / denom);
 }
@@ -39,14 +39,16 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 int adam_launch(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale,
                 cudaStream_t st) {
   if (!params || !grads || !exp_avg || !exp_avg_sq) return DRL_ERR_BAD_ARG;
   if (n < 0 || step < 1) return DRL_ERR_BAD_SHAPE;
   if (n == 0) return DRL_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  AdamCoef c{(float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps, grad_scale};
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  // 1-beta is formed in double like torch's python scalars (value=1-beta2), then rounded once
+  AdamCoef c{(float)(lr / bc1), (float)(1.0 / sqrt(bc2)), (float)beta1, (float)beta2,
+             (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, grad_scale};
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const int vec_ok = al(params) && al(grads) && al(exp_avg) && al(exp_avg_sq);
   const int threads = 256;
@@ -60,7 +62,7 @@ int adam_launch(float* params, const float* grads, float* exp_avg, float* exp_av
 }  // namespace drl
 
 extern "C" int drl_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
-                             int64_t n, float lr, float beta1, float beta2, float eps,
+                             int64_t n, double lr, double beta1, double beta2, double eps,
                              int64_t step, float grad_scale, void* stream) {
   return drl::adam_launch(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
                           grad_scale, drl::as_stream(stream));

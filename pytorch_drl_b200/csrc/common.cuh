@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include "../../include/drl_b200.h"
+#include "profile.cuh"
 
 namespace drl {
 
@@ -22,6 +23,7 @@ inline int cuda_fail(cudaError_t e) {
 
 #define DRL_LAUNCH_CHECK()                               \
   do {                                                   \
+    ::drl::count_launch();                               \
     cudaError_t _e = cudaGetLastError();                 \
     if (_e != cudaSuccess) return ::drl::cuda_fail(_e);  \
   } while (0)

@@ -170,8 +170,11 @@ static int ppo_common(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx
   DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
   HeadParams hpp;
   head_params(net, net->params, grads, hpp);
+  {
+  ProfileScope prof("heads_loss", st);
   DRL_TRY(heads_loss_dispatch(grads ? 2 : 1, bf16, net->feat, hpp, row_idx, nb, *batch, *hyper, losses_out,
                               nullptr, nullptr, nullptr, nullptr, net->dpre, st));
+  }
   if (grads)
     DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, st)
                  : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
@@ -201,11 +204,14 @@ extern "C" int drl_net_activation(drl_net_t* net, int which, const void** ptr, i
 }
 
 extern "C" int drl_net_adam_step(drl_net_t* net, float* params, const float* grads, float* exp_avg,
-                                 float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                 float* exp_avg_sq, double lr, double beta1, double beta2, double eps,
                                  int64_t step, float grad_scale, void* stream) {
   if (!net) return DRL_ERR_BAD_ARG;
+  {
+  ProfileScope prof("adam", as_stream(stream));
   DRL_TRY(adam_launch(params, grads, exp_avg, exp_avg_sq, net->nparams, lr, beta1, beta2, eps, step,
                       grad_scale, as_stream(stream)));
+  }
   net->params = params;
   if (net->precision == DRL_PRECISION_BF16) return bf16_pack_params(net, as_stream(stream));
   return DRL_OK;

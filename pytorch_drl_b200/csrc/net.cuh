@@ -40,7 +40,7 @@ int heads_loss_dispatch(int mode, bool dpre_is_bf16, const float* feat, const He
                         float* values_out, float* logp_out, float* ent_out, void* dpre,
                         cudaStream_t st);
 int adam_launch(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale,
                 cudaStream_t st);
 
 // tcgen05 bf16 engine (umma_net.cu)

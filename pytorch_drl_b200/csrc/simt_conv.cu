@@ -180,6 +180,7 @@ int simt_conv_forward(const TIn* in, const int64_t* row_idx, int nb, const ConvG
   PatchGather<TIn> af{in, row_idx, g};
   WeightFwd bf{w, g};
   EpiBiasRelu<float> ef{bias, out, N};
+  ProfileScope prof("simt_fwd", st);
   simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
@@ -195,6 +196,7 @@ int simt_conv_dgrad(const float* dy, int nb, const ConvGeom& g, const float* w, 
   DyGather af{dy, g};
   WeightDgrad bf{w, g};
   EpiReluMask ef{x_act, dx, N};
+  ProfileScope prof("simt_dgrad", st);
   simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
@@ -214,6 +216,7 @@ int simt_conv_wgrad(const float* dy, const TIn* in, const int64_t* row_idx, int 
   DyT af{dy, g.Cout};
   PatchGatherT<TIn> bf{PatchGather<TIn>{in, row_idx, g}, Kp};
   EpiWgrad ef{gw, gb, g, Kp};
+  ProfileScope prof("simt_wgrad", st);
   simt_gemm_kernel<true><<<tiles(M, N, splits), 256, 0, st>>>(M, N, K, k_per, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;

@@ -1,9 +1,324 @@
-// tcgen05 bf16 engine of the NatureCNN trunk — placeholder until the kernels land.
+// tcgen05 bf16 engine of the NatureCNN trunk (DRL_PRECISION_BF16): weight packing into swizzled
+// tile images, launch geometry of the forward / data-gradient / weight-gradient implicit GEMMs
+// (umma_gemm.cuh), and the bias-gradient column sums.
+//
+// Layers (nature_cnn.py:27-36): conv1 8x8/4 (uint8 -> fp16 operands, 1/255 in the epilogue),
+// conv2 4x4/2, conv3 3x3/1, fc 3136->512 (a 7x7 "conv" so that the NCHW flatten order
+// c*49+h*7+w of nature_cnn.py:34 is honoured).  Activations are bf16 NHWC; features, logits,
+// losses, gradients and Adam state are fp32.
 #include "net.cuh"
+#include <string.h>
+#include <new>
+#include "umma_gemm.cuh"
+
 namespace drl {
-int bf16_alloc(drl_net*) { return DRL_ERR_UNSUPPORTED; }
-void bf16_free(drl_net*) {}
-int bf16_pack_params(drl_net*, cudaStream_t) { return DRL_ERR_UNSUPPORTED; }
-int bf16_trunk_forward(drl_net*, const uint8_t*, const int64_t*, int, cudaStream_t) { return DRL_ERR_UNSUPPORTED; }
-int bf16_trunk_backward(drl_net*, const uint8_t*, const int64_t*, int, float*, cudaStream_t) { return DRL_ERR_UNSUPPORTED; }
+
+static const float kInv255 = [] { const uint32_t u = 0x3b808081u; float f; memcpy(&f, &u, 4); return f; }();   // float32(1/255)
+
+struct Bf16Engine {
+  // packed B operands (tile images)
+  void* w1f = nullptr;   // conv1 fwd   fp16 [4][32x64]
+  void* w2f = nullptr;   // conv2 fwd   bf16 [8][64x64]
+  void* w3f = nullptr;   // conv3 fwd   bf16 [9][64x64]
+  void* wff = nullptr;   // fc fwd      bf16 [4 n-tiles][49][128x64]
+  void* wfd = nullptr;   // fc dgrad    bf16 [49 n-tiles][8][64x64]
+  void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
+  void* w2d = nullptr;   // conv2 dgrad bf16 [4 classes][4][32x64]
+};
+
+// ---- packing -----------------------------------------------------------------------------------------
+enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4 };
+
+struct PackArgs {
+  const float* w;      // reference-layout fp32 weights of the layer
+  void* out;
+  int mode, fp16;
+  int variants, KB, N; // tile grid: [variants][KB][N rows x 64]
+  int Cin, KH, KW, Cout;
+};
+
+__device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n, int k) {
+  switch (a.mode) {
+    case PK_CONV_FWD: {            // B[n=co][k=(ky,kx,ci)] = W[co,ci,ky,kx]
+      const int kc = a.KW * a.Cin;
+      const int ky = k / kc, r2 = k - ky * kc, kx = r2 / a.Cin, ci = r2 - kx * a.Cin;
+      return a.w[((size_t)(n * a.Cin + ci) * a.KH + ky) * a.KW + kx];
+    }
+    case PK_FC_FWD: {              // B[n=variant*128+n][k=(hw,c)] = Wfc[n, c*49+hw]
+      const int hw = k / 64, c = k - hw * 64;
+      return a.w[(size_t)(variant * a.N + n) * 3136 + c * 49 + hw];
+    }
+    case PK_FC_DGRAD: {            // B[row = kfc = variant*64+n, (hw,c) order][k = n_fc] = Wfc[n_fc, c*49+hw]
+      const int kfc = variant * 64 + n;
+      const int hw = kfc / 64, c = kfc - hw * 64;
+      return a.w[(size_t)k * 3136 + c * 49 + hw];
+    }
+    case PK_CONV3_DGRAD: {         // B[n=ci][k=(ty,tx,co)] = W3[co,ci,2-ty,2-tx]
+      const int t = k / 64, co = k - t * 64, ty = t / 3, tx = t - ty * 3;
+      return a.w[((size_t)(co * 64 + n) * 3 + (2 - ty)) * 3 + (2 - tx)];
+    }
+    default: {                     // PK_CONV2_DGRAD: class (py,px); B[n=ci][k=(ty,tx,co)] = W2[co,ci,py+2(1-ty),px+2(1-tx)]
+      const int py = variant >> 1, px = variant & 1;
+      const int t = k / 64, co = k - t * 64, ty = t >> 1, tx = t & 1;
+      return a.w[((size_t)(co * 32 + n) * 4 + (py + 2 * (1 - ty))) * 4 + (px + 2 * (1 - tx))];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const PackArgs a) {
+  const int64_t total = (int64_t)a.variants * a.KB * a.N * 64;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(e & 63);
+    const int n = (int)((e >> 6) % a.N);
+    const int64_t t = (e >> 6) / a.N;
+    const int kb = (int)(t % a.KB), variant = (int)(t / a.KB);
+    const float v = pack_src(a, variant, n, kb * 64 + kk);
+    const int64_t tile_bytes = (int64_t)a.N * 128;
+    const int64_t off = t * tile_bytes + umma::swz_off<128>((uint32_t)n, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
+    if (a.fp16) *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(a.out) + off) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(a.out) + off) = __float2bfloat16_rn(v);
+  }
+}
+
+static int pack_one(const float* w, void* out, int mode, int fp16, int variants, int KB, int N, int Cin, int KH,
+                    int KW, int Cout, cudaStream_t st) {
+  PackArgs a{w, out, mode, fp16, variants, KB, N, Cin, KH, KW, Cout};
+  const int64_t total = (int64_t)variants * KB * N * 64;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  pack_tiles_kernel<<<blocks, 256, 0, st>>>(a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+// ---- bias gradients: column sums of a bf16 [R, C] matrix, C in {32, 64, 512} -----------------------------
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t R, int C,
+                                                          float* __restrict__ out) {
+  __shared__ float red[256 * 8];
+  const int tpr = C / 8;                       // threads per row (each handles 8 columns = 16 B)
+  const int rl = threadIdx.x / tpr, cg = threadIdx.x % tpr, rows_per_pass = 256 / tpr;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_pass + rl; r < R; r += (int64_t)gridDim.x * rows_per_pass) {
+    const uint4 v = umma::ldg_v4(x + r * C + cg * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += __uint_as_float(w[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int cgi = threadIdx.x / 8, j = threadIdx.x % 8;
+    float s = 0.f;
+    for (int q = 0; q < rows_per_pass; ++q) s += red[(q * tpr + cgi) * 8 + j];
+    atomicAdd(out + threadIdx.x, s);
+  }
+}
+
+static int colsum(const void* x, int64_t R, int C, float* out, cudaStream_t st) {   // C in {32, 64}
+  ProfileScope prof("bias_grad", st);
+  const int tpr = C / 8;
+  const int rows_per_pass = 256 / tpr;
+  int blocks = (int)((R + rows_per_pass - 1) / rows_per_pass);
+  if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+  colsum_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), R, C, out);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+// fc bias (512 columns): each thread owns 2 columns of a row pass
+__global__ void __launch_bounds__(256) colsum512_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t R,
+                                                             float* __restrict__ out) {
+  float a0 = 0.f, a1 = 0.f;
+  for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(x + r * 512 + threadIdx.x * 2);
+    a0 += __uint_as_float(w << 16);
+    a1 += __uint_as_float(w & 0xffff0000u);
+  }
+  atomicAdd(out + threadIdx.x * 2, a0);
+  atomicAdd(out + threadIdx.x * 2 + 1, a1);
+}
+
+// ---- engine ---------------------------------------------------------------------------------------------
+int bf16_alloc(drl_net* n) {
+  Bf16Engine* e = new (std::nothrow) Bf16Engine();
+  if (!e) return DRL_ERR_CUDA;
+  n->bf16 = e;
+  const size_t nb = (size_t)n->max_batch;
+  DRL_CUDA(cudaMalloc(&n->act[0], nb * 12800 * 2));
+  DRL_CUDA(cudaMalloc(&n->act[1], nb * 5184 * 2));
+  DRL_CUDA(cudaMalloc(&n->act[2], nb * 3136 * 2));
+  DRL_CUDA(cudaMalloc(&n->dact[0], nb * 12800 * 2));
+  DRL_CUDA(cudaMalloc(&n->dact[1], nb * 5184 * 2));
+  DRL_CUDA(cudaMalloc(&n->dact[2], nb * 3136 * 2));
+  DRL_CUDA(cudaMalloc(&n->feat, nb * 512 * 4));
+  DRL_CUDA(cudaMalloc(&n->dpre, nb * 512 * 2));
+  DRL_CUDA(cudaMalloc(&e->w1f, 4 * 32 * 128));
+  DRL_CUDA(cudaMalloc(&e->w2f, 8 * 64 * 128));
+  DRL_CUDA(cudaMalloc(&e->w3f, 9 * 64 * 128));
+  DRL_CUDA(cudaMalloc(&e->wff, (size_t)4 * 49 * 128 * 128));
+  DRL_CUDA(cudaMalloc(&e->wfd, (size_t)49 * 8 * 64 * 128));
+  DRL_CUDA(cudaMalloc(&e->w3d, 9 * 64 * 128));
+  DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
+  return DRL_OK;
+}
+
+void bf16_free(drl_net* n) {
+  Bf16Engine* e = n->bf16;
+  if (!e) return;
+  cudaFree(e->w1f); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d);
+  delete e;
+  n->bf16 = nullptr;
+}
+
+int bf16_pack_params(drl_net* n, cudaStream_t st) {
+  ProfileScope prof("pack_weights", st);
+  Bf16Engine* e = n->bf16;
+  const float* p = n->params;
+  const int64_t* o = n->off;
+  DRL_TRY(pack_one(p + o[0], e->w1f, PK_CONV_FWD, 1, 1, 4, 32, 4, 8, 8, 32, st));
+  DRL_TRY(pack_one(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64, st));
+  DRL_TRY(pack_one(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64, st));
+  DRL_TRY(pack_one(p + o[6], e->wff, PK_FC_FWD, 0, 4, 49, 128, 64, 7, 7, 512, st));
+  DRL_TRY(pack_one(p + o[6], e->wfd, PK_FC_DGRAD, 0, 49, 8, 64, 64, 7, 7, 512, st));
+  DRL_TRY(pack_one(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64, st));
+  DRL_TRY(pack_one(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 4, 4, 32, 32, 4, 4, 64, st));
+  return DRL_OK;
+}
+
+template <int N, int SRC, int EPI>
+static int launch_rowgather(const char* site, const RowGatherArgs& a, int grid_y, cudaStream_t st) {
+  ProfileScope prof(site, st);
+  auto kern = rowgather_gemm_kernel<N, SRC, EPI>;
+  constexpr int smem = RowGatherSmem<N>::kTotal;
+  static bool configured = false;
+  if (!configured) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = (a.M + 127) / 128;
+  int gx = sm_count() / grid_y;
+  if (gx < 1) gx = 1;
+  if (gx > tiles) gx = tiles;
+  kern<<<dim3(gx, grid_y), 288, smem, st>>>(a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+template <int NT, int SRC, int MB>
+static int launch_wgrad(const char* site, const WgradArgs& a, int grid_x, int grid_y, cudaStream_t st) {
+  ProfileScope prof(site, st);
+  auto kern = wgrad_gemm_kernel<NT, SRC, MB>;
+  constexpr int smem = 2 * (2 * MB * 8192 + WgradCfg<NT>::kDyBytes) + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<dim3(grid_x, grid_y), 288, smem, st>>>(a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+static RowGatherArgs fwd_args(int nb, const void* src, const int64_t* row_idx, int P, int OW, int H, int W, int C,
+                              int stride, int KB, int KBX, const void* bpack, void* out, const float* bias,
+                              float scale, int Ntotal) {
+  RowGatherArgs a{};
+  a.M = nb * P; a.KB = KB; a.src = src; a.row_idx = row_idx; a.P = P; a.OW = OW; a.H = H; a.W = W; a.C = C;
+  a.stride = stride; a.pad = 0; a.KBX = KBX; a.bpack = bpack; a.b_variant_stride = 0; a.out = out; a.bias = bias;
+  a.scale = scale; a.mask_src = nullptr; a.out_sample_pitch = (int64_t)P * Ntotal; a.out_row_pitch = OW * Ntotal;
+  a.out_C = Ntotal; a.osy = 1; a.osx = 1; a.n_variant_stride = 0; a.classes = 0;
+  return a;
+}
+
+int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, cudaStream_t st) {
+  Bf16Engine* e = n->bf16;
+  const float* p = n->params;
+  const int64_t* o = n->off;
+  // conv1: uint8 frames -> fp16 operands; y = relu(acc * (1/255) + b)   (scale_observations.py:35 fused)
+  RowGatherArgs a1 = fwd_args(nb, obs, row_idx, 400, 20, 84, 84, 4, 4, 4, 1, e->w1f, n->act[0], p + o[1],
+                              kInv255, 32);
+  DRL_TRY((launch_rowgather<32, SRC_U8, EPI_BIAS_RELU_BF16>("conv1_fwd", a1, 1, st)));
+  RowGatherArgs a2 = fwd_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 8, 2, e->w2f, n->act[1], p + o[3], 1.f, 64);
+  DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
+  RowGatherArgs a3 = fwd_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 9, 3, e->w3f, n->act[2], p + o[5], 1.f, 64);
+  DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
+  RowGatherArgs a4 = fwd_args(nb, n->act[2], nullptr, 1, 1, 7, 7, 64, 1, 49, 7, e->wff, n->feat, p + o[7], 1.f, 512);
+  a4.b_variant_stride = (int64_t)49 * 128 * 128;
+  a4.n_variant_stride = 128;
+  DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_BIAS_RELU_F32>("fc_fwd", a4, 4, st)));
+  return DRL_OK;
+}
+
+static WgradArgs wgrad_args(int nb, const void* src, const int64_t* row_idx, int P, int OW, int H, int W, int C,
+                            int stride, int KBX, int atoms, const void* dy, int dy_ld, int mb_per_cta, int n_tiles,
+                            float* gw, int Cin, int KH, int KW) {
+  WgradArgs a{};
+  a.M = nb * P; a.src = src; a.row_idx = row_idx; a.P = P; a.OW = OW; a.H = H; a.W = W; a.C = C; a.stride = stride;
+  a.KBX = KBX; a.n_atoms_valid = atoms; a.dy = reinterpret_cast<const __nv_bfloat16*>(dy); a.dy_ld = dy_ld;
+  a.mb_per_cta = mb_per_cta; a.n_tiles = n_tiles; a.gw = gw; a.Cin = Cin; a.KH = KH; a.KW = KW; a.scale = 1.f;
+  return a;
+}
+
+int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, float* g, cudaStream_t st) {
+  Bf16Engine* e = n->bf16;
+  const int64_t* o = n->off;
+  const int sms = sm_count();
+  auto splits = [&](int M, int gy) { int s = (M + 63) / 64; int gx = (sms + gy - 1) / gy; return s < gx ? s : gx; };
+
+  // ---- fc: bias, weight gradient (3136 x 512, split over the batch), data gradient (masked by act3 > 0)
+  {
+    ProfileScope prof("bias_grad", st);
+    colsum512_bf16_kernel<<<sms * 2 < nb ? sms * 2 : nb, 256, 0, st>>>((const __nv_bfloat16*)n->dpre, nb, g + o[7]);
+    DRL_LAUNCH_CHECK();
+  }
+  WgradArgs wf = wgrad_args(nb, n->act[2], nullptr, 1, 1, 7, 7, 64, 1, 7, 49, n->dpre, 512, 1, 2, g + o[6], 64, 7, 7);
+  DRL_TRY((launch_wgrad<256, SRC_BF16, 1>("fc_wgrad", wf, splits(nb, 50), 50, st)));
+  {
+    RowGatherArgs a{};
+    a.M = nb; a.KB = 8; a.src = n->dpre; a.row_idx = nullptr; a.P = 1; a.OW = 1; a.H = 1; a.W = 1; a.C = 512;
+    a.stride = 1; a.pad = 0; a.KBX = 8; a.bpack = e->wfd; a.b_variant_stride = (int64_t)8 * 64 * 128;
+    a.out = n->dact[2]; a.mask_src = (const __nv_bfloat16*)n->act[2]; a.scale = 1.f; a.bias = nullptr;
+    a.out_sample_pitch = 3136; a.out_row_pitch = 3136; a.out_C = 3136; a.osy = 1; a.osx = 1;
+    a.n_variant_stride = 64; a.classes = 0;
+    DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("fc_dgrad", a, 49, st)));
+  }
+  // ---- conv3
+  DRL_TRY(colsum(n->dact[2], (int64_t)nb * 49, 64, g + o[5], st));
+  WgradArgs w3 = wgrad_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 3, 9, n->dact[2], 64, 5, 1, g + o[4], 64, 3, 3);
+  DRL_TRY((launch_wgrad<64, SRC_BF16, 5>("conv3_wgrad", w3, splits(nb * 49, 1), 1, st)));
+  {
+    RowGatherArgs a{};
+    a.M = nb * 81; a.KB = 9; a.src = n->dact[2]; a.row_idx = nullptr; a.P = 81; a.OW = 9; a.H = 7; a.W = 7; a.C = 64;
+    a.stride = 1; a.pad = 2; a.KBX = 1; a.bpack = e->w3d; a.b_variant_stride = 0;
+    a.out = n->dact[1]; a.mask_src = (const __nv_bfloat16*)n->act[1]; a.scale = 1.f; a.bias = nullptr;
+    a.out_sample_pitch = 5184; a.out_row_pitch = 9 * 64; a.out_C = 64; a.osy = 1; a.osx = 1;
+    a.n_variant_stride = 0; a.classes = 0;
+    DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
+  }
+  // ---- conv2
+  DRL_TRY(colsum(n->dact[1], (int64_t)nb * 81, 64, g + o[3], st));
+  WgradArgs w2 = wgrad_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 2, 8, n->dact[1], 64, 4, 1, g + o[2], 32, 4, 4);
+  DRL_TRY((launch_wgrad<64, SRC_BF16, 4>("conv2_wgrad", w2, splits(nb * 81, 1), 1, st)));
+  {
+    // four parity classes of the stride-2 transposed convolution: a 2x2-tap gather over dY2 each
+    RowGatherArgs a{};
+    a.M = nb * 100; a.KB = 4; a.src = n->dact[1]; a.row_idx = nullptr; a.P = 100; a.OW = 10; a.H = 9; a.W = 9; a.C = 64;
+    a.stride = 1; a.pad = 1; a.KBX = 1; a.bpack = e->w2d; a.b_variant_stride = (int64_t)4 * 32 * 128;
+    a.out = n->dact[0]; a.mask_src = (const __nv_bfloat16*)n->act[0]; a.scale = 1.f; a.bias = nullptr;
+    a.out_sample_pitch = 12800; a.out_row_pitch = 20 * 32; a.out_C = 32; a.osy = 2; a.osx = 2;
+    a.n_variant_stride = 0; a.classes = 1;
+    DRL_TRY((launch_rowgather<32, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 4, st)));
+  }
+  // ---- conv1 (no data gradient: observations need none, agent.py:66-67)
+  DRL_TRY(colsum(n->dact[0], (int64_t)nb * 400, 32, g + o[1], st));
+  WgradArgs w1 = wgrad_args(nb, obs, row_idx, 400, 20, 84, 84, 4, 4, 1, 4, n->dact[0], 32, 2, 1, g + o[0], 4, 8, 8);
+  w1.scale = kInv255;
+  DRL_TRY((launch_wgrad<32, SRC_U8, 2>("conv1_wgrad", w1, splits(nb * 400, 1), 1, st)));
+  return DRL_OK;
+}
+
 }  // namespace drl

@@ -33,18 +33,19 @@ def gae(rewards: tc.Tensor, vpreds: tc.Tensor, dones: tc.Tensor, gamma: float, l
     n = r.shape[0]
     if v.shape[0] != n or d.shape[0] != n or v.shape[1] < T + 1 or r.shape[1] < T or d.shape[1] < T:
         raise ValueError('inconsistent shapes for GAE')
-    if r.stride(1) != 1 or v.stride(1) != 1 or d.stride(1) != 1 or d.stride(0) != r.stride(0):
+    ld = lambda t: t.stride(0) if t.shape[0] > 1 else t.shape[1]     # size-1 dims carry arbitrary strides
+    if r.stride(1) != 1 or v.stride(1) != 1 or d.stride(1) != 1 or ld(d) != ld(r):
         raise ValueError('GAE inputs must be row-contiguous with equal reward/done row strides')
     if adv_out is not None:
         adv, vt = _cuda(adv_out, tc.float32, 'adv_out'), _cuda(vtarg_out, tc.float32, 'vtarg_out')
-        if adv.shape[0] != n or adv.shape[1] < T or adv.stride() != vt.stride() or adv.stride(1) != 1:
+        if adv.shape[0] != n or adv.shape[1] < T or ld(adv) != ld(vt) or adv.stride(1) != 1:
             raise ValueError('adv_out/vtarg_out must be [n_envs, >=T] with equal strides')
-        ld_o = adv.stride(0)
+        ld_o = ld(adv)
     else:
         ld_o = (T + 3) // 4 * 4
         adv = tc.empty((n, ld_o), dtype=tc.float32, device=r.device)
         vt = tc.empty((n, ld_o), dtype=tc.float32, device=r.device)
-    check(_lib.lib().drl_gae_f32(ptr(r), ptr(v), ptr(d), n, T, r.stride(0), v.stride(0), ld_o,
+    check(_lib.lib().drl_gae_f32(ptr(r), ptr(v), ptr(d), n, T, ld(r), ld(v), ld_o,
                                  gamma, lambda_, int(use_dones), int(standardize), ptr(adv), ptr(vt),
                                  current_stream()), 'gae')
     return adv[:, :T], vt[:, :T]
@@ -56,7 +57,7 @@ def standardize(x: tc.Tensor) -> tc.Tensor:
     x2 = x.reshape(1, -1) if x.dim() == 1 else x
     x2 = x2.contiguous()
     y = tc.empty_like(x2)
-    check(_lib.lib().drl_standardize_f32(ptr(x2), x2.shape[0], x2.shape[1], x2.stride(0), ptr(y),
+    check(_lib.lib().drl_standardize_f32(ptr(x2), x2.shape[0], x2.shape[1], x2.shape[1], ptr(y),
                                          current_stream()), 'standardize')
     return y.reshape(x.shape)
 

@@ -206,7 +206,7 @@ def test_sumtree_edge_cases():
 # ---- normaliser ----------------------------------------------------------------------------------------
 def test_normalizer_vs_reference_golden(golden_dir):
     from pytorch_drl_b200 import ops
-    from tests.test_oracle_golden import close_to_summary
+    from _util import close_to_summary
     g = np.load(os.path.join(golden_dir, 'normalizer.npz'))
     items, x = ro.normalizer_fixture_inputs()
     m1 = tc.zeros(84 * 84, device=dev()); m2 = tc.zeros(84 * 84, device=dev())
@@ -326,7 +326,7 @@ def test_ppo_optimize_vs_reference_2rank_golden(golden_dir, precision, tag):
     """The drop-in PPO.optimize on one GPU with envs_per_rank=2 against the UNMODIFIED reference run
     as 2 gloo ranks (tests/golden/ppo_2rank*.npz): final parameters, first-step grads, epoch metrics."""
     from pytorch_drl_b200 import agents, algos
-    from tests.test_oracle_golden import close_to_summary
+    from _util import close_to_summary
     g = np.load(os.path.join(golden_dir, f'{tag}.npz'))
     T, B, A, epochs = int(g['cfg_T']), int(g['cfg_B']), int(g['cfg_A']), int(g['cfg_epochs'])
     seed, world = int(g['cfg_seed']), int(g['cfg_world'])

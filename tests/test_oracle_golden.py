@@ -13,18 +13,7 @@ from oracle import ppo_oracle as po, rnd_oracle as ro
 F32 = np.float32
 
 
-def summary(x, n=2048):
-    f = np.asarray(x, np.float64).ravel()
-    stride = max(1, f.size // n)
-    return np.concatenate([[f.sum(), np.sqrt((f * f).sum())], f[::stride][:n]])
-
-
-def close_to_summary(x, gold, n=2048, rtol=2e-4, atol=2e-6, always=False):
-    big = np.asarray(x).size > (4096 if n == 2048 else 1024)
-    s = summary(x, n) if (big or always) else np.asarray(x, np.float64)
-    assert s.shape == gold.shape, (s.shape, gold.shape)
-    scale = np.abs(gold[2:]).max() if s.ndim == 1 and s.size > 2 else 1.0
-    np.testing.assert_allclose(s, gold, rtol=rtol, atol=atol + 1e-5 * scale)
+from _util import summary, close_to_summary  # noqa: E402,F401
 
 
 # ---- GAE ------------------------------------------------------------------------------------
