@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — PPO update samples/sec on synthetic 84x84x4 rollouts (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one learner step of PPO.optimize (drl/algos/ppo.py:246-257): gather a minibatch of
+B samples from each env of the GPU, NatureCNN forward, fused losses, backward, gradient
+all-reduce across GPUs, Adam.  Workload at N=1: BASELINE config[1] — 1024 envs x 128 steps per
+GPU, B=32 per env => 32 768 samples per step per GPU (weak scaling: every GPU owns 1024 envs).
+Rank 0 prints ONE JSON line (see the keys in `main`).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch as tc  # noqa: E402
+
+A, T, B = 6, 128, 32
+REWARD_KEYS = ['extrinsic']
+MACS = {  # algorithmic multiply-accumulates per sample
+    'conv1_fwd': 3276800, 'conv2_fwd': 2654208, 'conv3_fwd': 1806336, 'fc_fwd': 1605632,
+    'conv1_wgrad': 3276800, 'conv2_wgrad': 2654208, 'conv3_wgrad': 1806336, 'fc_wgrad': 1605632,
+    'conv2_dgrad': 2654208, 'conv3_dgrad': 1806336, 'fc_dgrad': 1605632,
+}
+STEP_FLOPS_PER_SAMPLE = 49525760          # fwd 18.69 + bwd 30.83 MFLOP (A=6, K=1), SURVEY §8d
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0))),
+                    hbm=float(d.get('hbm_gbs', 6650.0)), src='measured (MEASURED_PEAKS.json, sustained bf16)')
+    return dict(tflops=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc = [], None
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace('.', '', 1).isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_steps: int = 200, steps=None):
+    """Times the CPU restatement of the reference's learner step (oracle port: torch-CPU fp32 autograd
+    through the same conv/linear/Adam ops the reference calls, all host threads) on a bounded sample:
+    `n_envs` ranks x B samples per step.  Returns (samples/s, steps, threads)."""
+    from oracle import ppo_oracle as po
+    rs = np.random.RandomState(0)
+    params = po.init_params(A, REWARD_KEYS, seed=11)
+    hp = po.Hyper({'extrinsic': 1.0}, 0.2, 0.01, 1.0, False, True)
+    mbs = []
+    for e in range(n_envs):
+        mbs.append(dict(observations=rs.randint(0, 256, size=(B, 84, 84, 4), dtype=np.uint8),
+                        actions=rs.randint(0, A, size=B).astype(np.int64),
+                        logprobs=np.full(B, -np.log(A), np.float32),
+                        advantages={'extrinsic': rs.standard_normal(B).astype(np.float32)},
+                        vpreds={'extrinsic': np.zeros(B, np.float32)},
+                        vtargs={'extrinsic': rs.standard_normal(B).astype(np.float32)}))
+    keys = list(params.keys())
+    m = {k: np.zeros_like(params[k]) for k in keys}
+    v = {k: np.zeros_like(params[k]) for k in keys}
+
+    def one(step):
+        _, grads = po.minibatch_losses_and_grads(params, mbs, hp)
+        for k in keys:
+            po.adam_step(params[k], grads[k], m[k], v[k], step, 1e-3, 0.9, 0.999, 1e-5)
+
+    for i in range(warmup):
+        one(i + 1)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one(warmup + n + 1)
+        n += 1
+        el = time.perf_counter() - t0
+        if steps is not None:
+            if n >= steps:
+                break
+        elif el >= seconds or n >= max_steps:
+            break
+    return n * n_envs * B / el, n, tc.get_num_threads(), el
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path is pure PyTorch-CPU
+    Python that cannot travel to the GPU box (/root/reference is absent there and gym/moviepy are not
+    installable), so the arm times the oracle port — pinned to the reference by tests/golden — on all
+    host threads.  One step = one learner step over a bounded sample (8 ranks x 32 samples, the
+    reference's own CPU-runnable shape)."""
+    if rank != 0:
+        return
+    n_envs = 8
+    rate, n, threads, el = cpu_reference_step_rate(n_envs, 0.0, warmup=max(1, args.warmup), steps=args.steps)
+    line = {
+        'impl': 'reference', 'metric': 'PPO update samples/sec (84x84x4 frames)', 'value': rate, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': n, 'warmup': max(1, args.warmup), 'ms_per_step': 1e3 * el / n,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'PPO NatureCNN synthetic 84x84x4 rollout, 1024 envs x 128 steps, B=32 per env',
+                   'sample': f'{n_envs} envs x {B} samples per step on the host CPU'},
+        'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+                         'sample': f'{n} learner steps of {n_envs} envs x {B} samples (oracle port, torch-CPU fp32)'},
+        'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=1024, help='envs per GPU')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    assert args.warmup >= 3 or args.steps <= 2, 'timing rule: W >= 3'
+
+    import torch.distributed as dist
+    from pytorch_drl_b200 import _lib, agents, algos
+    from pytorch_drl_b200.comm import Communicator
+    from pytorch_drl_b200.utils.nested import MinibatchView
+    tc.cuda.set_device(local_rank)
+    dev = tc.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    L = _lib.lib()
+    n_envs = args.envs
+    nb = n_envs * B
+
+    # ---- model + algo through the public drop-in API ----
+    tc.manual_seed(0)
+    agent = agents.Agent(
+        [agents.ToChannelMajor()],
+        agents.NatureCNN(4, lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5), tc.nn.init.zeros_),
+        {'policy': agents.CategoricalPolicyHead(512, A, w_init=lambda w: tc.nn.init.orthogonal_(w, gain=0.01), b_init=tc.nn.init.zeros_),
+         'value_extrinsic': agents.SimpleValueHead(512, w_init=lambda w: tc.nn.init.orthogonal_(w, gain=0.01), b_init=tc.nn.init.zeros_)})
+    agent.fuse(max_batch=nb, precision=args.precision, device=dev)
+    opt = tc.optim.Adam(agent.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5)
+    comm = Communicator(rank, world, local_rank) if world > 1 else None
+    algo = algos.PPO(rank=rank, world_size=world, rollout_len=T, extra_steps=0,
+                     credit_assignment_ops={'extrinsic': algos.GAE(gamma=0.99, use_dones=True, lambda_=0.95)},
+                     global_step=1, max_steps=10 ** 7, policy_net=agent, policy_optimizer=opt, standardize_adv=True,
+                     opt_epochs=3, learner_batch_size=B, clip_param_init=0.2, clip_param_final=0.0,
+                     ent_coef_init=0.01, ent_coef_final=0.01, vf_loss_coef=1.0, envs_per_rank=n_envs, comm=comm,
+                     sampler_seed=0)
+
+    # ---- synthetic rollout, generated on the device; annotate + GAE through the API ----
+    st = algos.RolloutStorage(n_envs, T, REWARD_KEYS, dev)
+    d = st.as_dict()
+    g = tc.Generator(device=dev)
+    g.manual_seed(10000 * rank)
+    chunk = 64
+    for e0 in range(0, n_envs, chunk):
+        e1 = min(n_envs, e0 + chunk)
+        d['observations'][e0:e1] = tc.randint(0, 256, (e1 - e0, st.Tp, 84, 84, 4), device=dev, dtype=tc.uint8, generator=g)
+    d['actions'][:] = tc.randint(0, A, (n_envs, st.Tp), device=dev, generator=g)
+    d['rewards']['extrinsic'][:] = tc.randint(-1, 2, (n_envs, st.Tp), device=dev, generator=g).float()
+    d['dones'][:] = (tc.rand((n_envs, st.Tp), device=dev, generator=g) < 0.01).float()
+    rollout = algo.credit_assignment(algo.annotate(d))
+    tc.cuda.synchronize()
+
+    rs = np.random.RandomState(1234 + rank)
+
+    def step_rows():
+        blocks = [rs.permutation(T)[:B] for _ in range(n_envs)]
+        return algo._minibatch_rows(rollout, blocks)
+
+    total_steps = args.warmup + args.steps
+    rows_list = [step_rows() for _ in range(total_steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        tc.cuda.synchronize()
+
+    # ---- device-resident timing (value) ----
+    for i in range(args.warmup):
+        algo.learner_step(MinibatchView(rollout, rows_list[i]))
+    barrier()
+    L.drl_profile_enable(1)
+    names = (b'\0' * (48 * 64))
+    import ctypes
+    nbuf = ctypes.create_string_buffer(48 * 64)
+    ms = (ctypes.c_float * 64)()
+    cnt = (ctypes.c_int * 64)()
+    ns = ctypes.c_int()
+    L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))       # clear
+    launches0 = L.drl_launch_count()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        algo.learner_step(MinibatchView(rollout, rows_list[args.warmup + i]))
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = L.drl_launch_count() - launches0
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))
+    L.drl_profile_enable(0)
+    sites = {}
+    for i in range(ns.value):
+        nm = nbuf.raw[48 * i:48 * i + 48].split(b'\0')[0].decode()
+        sites[nm] = (ms[i] / max(1, cnt[i]), cnt[i])
+    if world > 1:
+        t = tc.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = nb * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end: host minibatches -> H2D -> learner step -> D2H loss read, every step ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(algo, agent, rollout, st, n_envs, dev, world, args, rows_list)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    # dominant kernel of the step and its roofline
+    dom = max((k for k in sites if k in MACS), key=lambda k: sites[k][0] * 1.0, default=None)
+    roof = None
+    per_kernel = {k: round(v[0], 4) for k, v in sites.items()}
+    if dom:
+        flops = 2.0 * MACS[dom] * nb
+        ach = flops / (sites[dom][0] * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
+                'frac': ach / pk['tflops'], 'traffic': None, 'peak_source': pk['src'],
+                'avg_launch_ms': sites[dom][0], 'kernel_share_of_step': sites[dom][0] / ms_per_step,
+                'step_achieved': STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12,
+                'step_frac': STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12 / pk['tflops'],
+                'per_kernel_ms': per_kernel}
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rate, n, threads, el = cpu_reference_step_rate(8, args.cpu_seconds)
+        cpu = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
+               'sample': f'{n} learner steps of 8 envs x {B} samples in {el:.1f} s (oracle port of the reference CPU path, torch-CPU fp32, os.cpu_count={os.cpu_count()})'}
+    line = {
+        'metric': 'PPO update samples/sec (84x84x4 frames)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+        'config': {'workload': f'PPO NatureCNN synthetic 84x84x4 rollout, {n_envs} envs x {T} steps per GPU, '
+                               f'learner step = {B} samples x {n_envs} envs = {nb} samples/GPU, A={A}, K=1',
+                   'parallelism': f'dp{world}', 'l2_policy': 'inputs larger than L2 (3.8 GB uint8 rollout per GPU, '
+                                                             'a different random minibatch every step)'},
+        'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(algo, agent, rollout, st, n_envs, dev, world, args, rows_list):
+    """Same metric through the public API with HOST minibatches: every step copies that step's
+    minibatch (frames + per-sample scalars, pinned host memory) to the device, runs
+    PPO.learner_step on it and reads the losses back to the host.  Copies are double-buffered on a
+    side stream so that step s+1's upload overlaps step s's compute; everything is inside the timed
+    region."""
+    import torch.distributed as dist
+    from pytorch_drl_b200.utils.nested import MinibatchView
+    nb = n_envs * B
+    nbuf = 2
+    host, devb = [], []
+    names = ['observations', 'actions', 'logprobs']
+    for b in range(nbuf):
+        rows = rows_list[b]
+        h = {
+            'observations': rollout['observations'].view(-1, 84, 84, 4)[rows].cpu().pin_memory(),
+            'actions': rollout['actions'].view(-1)[rows].cpu().pin_memory(),
+            'logprobs': rollout['logprobs'].view(-1)[rows].cpu().pin_memory(),
+            'advantages': rollout['advantages']['extrinsic'].reshape(-1)[rows].cpu().pin_memory(),
+            'vpreds': rollout['vpreds']['extrinsic'].reshape(-1)[rows].cpu().pin_memory(),
+            'vtargs': rollout['vtargs']['extrinsic'].reshape(-1)[rows].cpu().pin_memory(),
+        }
+        host.append(h)
+        devb.append({k: tc.empty(v.shape, dtype=v.dtype, device=dev) for k, v in h.items()})
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    ident = tc.arange(nb, device=dev, dtype=tc.int64)
+    loss_host = tc.empty((args.steps + args.warmup, 5), dtype=tc.float32).pin_memory()
+    copy_stream = tc.cuda.Stream(device=dev)
+    main = tc.cuda.current_stream()
+    ready = [tc.cuda.Event() for _ in range(nbuf)]
+    freed = [tc.cuda.Event() for _ in range(nbuf)]
+
+    def upload(i):
+        b = i % nbuf
+        with tc.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            for k in host[b]:
+                devb[b][k].copy_(host[b][k], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def view(b):
+        dd = devb[b]
+        return MinibatchView({'observations': dd['observations'].view(1, nb, 84, 84, 4), 'actions': dd['actions'].view(1, nb),
+                              'logprobs': dd['logprobs'].view(1, nb), 'advantages': {'extrinsic': dd['advantages'].view(1, nb)},
+                              'vpreds': {'extrinsic': dd['vpreds'].view(1, nb)}, 'vtargs': {'extrinsic': dd['vtargs'].view(1, nb)}},
+                             ident)
+
+    def run(n, offset):
+        upload(0)
+        for i in range(n):
+            b = i % nbuf
+            if i + 1 < n:
+                upload(i + 1)
+            main.wait_event(ready[b])
+            losses = algo.learner_step(view(b))
+            freed[b].record(main)
+            loss_host[offset + i].copy_(losses, non_blocking=True)
+        tc.cuda.synchronize()
+
+    for b in range(nbuf):
+        freed[b].record(main)
+    run(max(3, min(args.warmup, 5)), 0)
+    if world > 1:
+        dist.barrier()
+    tc.cuda.synchronize()
+    ev0, ev1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+    ev0.record()
+    run(args.steps, args.warmup)
+    ev1.record()
+    tc.cuda.synchronize()
+    el = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = tc.tensor([el], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    assert bool(tc.isfinite(loss_host[args.warmup:args.warmup + args.steps]).all())
+    return {'value': nb * world / (el / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d),
+            'd2h_bytes_per_step': 20, 'ms_per_step': el / args.steps,
+            'api': 'PPO.learner_step(MinibatchView) on pinned-host minibatches, double-buffered uploads'}
+
+
+if __name__ == '__main__':
+    main()

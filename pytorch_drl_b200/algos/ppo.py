@@ -224,12 +224,26 @@ class PPO:
         idx = np.stack([b.astype(np.int64) + e * Tp for e, b in enumerate(blocks_per_env)]).reshape(-1)
         return tc.as_tensor(idx, device=self._engine.device)
 
+    def learner_step(self, minibatch) -> tc.Tensor:
+        """One learner step on a minibatch (ppo.py:250-257): forward, fused losses, backward,
+        gradient all-reduce across GPUs (the DDP mean, launch.py:310), Adam.  Returns the device
+        tensor losses[5] (policy_loss, value_loss, composite_loss, meanent, clipfrac)."""
+        eng = self._engine
+        rows = minibatch.row_idx
+        if rows.numel() > eng.max_batch:
+            raise ValueError('minibatch larger than the engine max_batch')
+        losses = eng.ppo_step(minibatch['observations'], rows, self._batch(minibatch), self._hyper(), grads=True)
+        world = self._world_size if self._comm is not None else 1
+        if self._comm is not None:
+            self._comm.allreduce_grads(eng)
+        lr, betas, eps = self._optimizer_hparams()
+        eng.adam_step(lr, betas, eps, grad_scale=1.0 / world)
+        return losses
+
     def optimize(self, rollout: Dict[str, Any]) -> None:
         """ppo.py:242-281: opt_epochs x T/B learner steps (+ the per-epoch full-rollout metrics pass
         and the scheduler step).  One learner step = B samples of each env of every GPU."""
-        eng = self._engine
         self.last_epoch_metrics = []
-        world = self._world_size if self._comm is not None else 1
         for opt_epoch in range(self._opt_epochs):
             for s in self._samplers:
                 s.resample()
@@ -240,11 +254,7 @@ class PPO:
                 self._update_trainable_wrappers(minibatch)
                 if self._global_step <= self._non_learning_steps:
                     continue
-                self.compute_losses_and_metrics(minibatch, no_grad=False)
-                if self._comm is not None:
-                    self._comm.allreduce_grads(eng)
-                lr, betas, eps = self._optimizer_hparams()
-                eng.adam_step(lr, betas, eps, grad_scale=1.0 / world)
+                self.learner_step(minibatch)
             metrics = self.compute_losses_and_metrics(rollout, no_grad=True)
             vec = tc.stack([metrics[n] for n in METRIC_NAMES])
             if self._comm is not None:

@@ -293,7 +293,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   {
     RowGatherArgs a{};
     a.M = nb * 81; a.KB = 9; a.src = n->dact[2]; a.row_idx = nullptr; a.P = 81; a.OW = 9; a.H = 7; a.W = 7; a.C = 64;
-    a.stride = 1; a.pad = 2; a.KBX = 1; a.bpack = e->w3d; a.b_variant_stride = 0;
+    a.stride = 1; a.pad = 2; a.KBX = 3; a.bpack = e->w3d; a.b_variant_stride = 0;
     a.out = n->dact[1]; a.mask_src = (const __nv_bfloat16*)n->act[1]; a.scale = 1.f; a.bias = nullptr;
     a.out_sample_pitch = 5184; a.out_row_pitch = 9 * 64; a.out_C = 64; a.osy = 1; a.osx = 1;
     a.n_variant_stride = 0; a.classes = 0;
@@ -307,7 +307,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     // four parity classes of the stride-2 transposed convolution: a 2x2-tap gather over dY2 each
     RowGatherArgs a{};
     a.M = nb * 100; a.KB = 4; a.src = n->dact[1]; a.row_idx = nullptr; a.P = 100; a.OW = 10; a.H = 9; a.W = 9; a.C = 64;
-    a.stride = 1; a.pad = 1; a.KBX = 1; a.bpack = e->w2d; a.b_variant_stride = (int64_t)4 * 32 * 128;
+    a.stride = 1; a.pad = 1; a.KBX = 2; a.bpack = e->w2d; a.b_variant_stride = (int64_t)4 * 32 * 128;
     a.out = n->dact[0]; a.mask_src = (const __nv_bfloat16*)n->act[0]; a.scale = 1.f; a.bias = nullptr;
     a.out_sample_pitch = 12800; a.out_row_pitch = 20 * 32; a.out_C = 32; a.osy = 2; a.osx = 2;
     a.n_variant_stride = 0; a.classes = 1;
