@@ -144,6 +144,15 @@ __device__ __forceinline__ uint2 ldg_v2(const void* p) {
   return v;
 }
 
+// ---- Ampere-style async copies (LDGSTS): 16 B global -> shared without register staging ---------------
+// src_bytes = 0 zero-fills the destination (padding taps / rows past the end).
+__device__ __forceinline__ void cp_async_16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // 8 uint8 (two 32-bit words) -> 8 fp16, exact: byte b becomes the half 0x6400|b = 1024+b, then -1024.
 __device__ __forceinline__ uint4 u8x8_to_f16x8(uint2 w) {
   const uint32_t magic = 0x64006400u;

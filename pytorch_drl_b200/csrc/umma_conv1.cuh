@@ -1,0 +1,386 @@
+// conv1 of NatureCNN (8x8 stride 4 over uint8 84x84x4 frames -> 20x20x32) as tcgen05 kernels that read
+// the uint8 frames DIRECTLY: the frame rows a tile needs are contiguous in memory (NHWC rows of
+// 336 B), so they are staged into shared memory by 1-D TMA bulk copies (gathered through the
+// minibatch row index), converted u8 -> fp16/bf16 on the way into the swizzled operand tiles by the
+// producer warps, and the x*(1/255) of scale_observations.py:35 is applied to the accumulator.
+//
+//   conv1_fwd_kernel   D[128 positions x 32] = im2col(frame)[128 x 256] * W1[32 x 256]^T
+//   conv1_wgrad_kernel dW1^T[256 x 32] += im2col(frame)[m x 256]^T * dY1[m x 32]
+//
+// A tile is 128 consecutive rows of the flattened (sample, oy, ox) grid; it touches at most two
+// samples ("segments"), each needing input rows [4*oy_a, 4*oy_b + 8) = at most 36 rows = 12 096 B.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace drl {
+
+struct Conv1Args {
+  const uint8_t* obs;        // [rows, 84, 84, 4]
+  const int64_t* row_idx;    // [nb] or nullptr
+  int nb;
+  const void* bpack;         // fwd: fp16 [4][32 x 64] swizzled tile images (16 KB)
+  const float* bias;         // fwd: [32]
+  float scale;               // float32(1/255)
+  __nv_bfloat16* out;        // fwd: act1 [nb*400, 32]
+  const __nv_bfloat16* dy;   // wgrad: dY1 [nb*400, 32]
+  float* gw;                 // wgrad: fp32 [32][4][8][8]
+};
+
+constexpr int kC1SegBytes = 12288;
+constexpr int kC1FrameBytes = 84 * 84 * 4;
+constexpr int kC1RowBytes = 84 * 4;
+
+struct C1Seg { int rows_begin; int oy_a; uint32_t bytes; int64_t src_off; bool valid; };
+
+// Segment s (0/1) of the tile starting at flattened position p0.
+__device__ __forceinline__ void c1_segment(int p0, int s, int nb, const int64_t* row_idx, C1Seg& g) {
+  const int b0 = p0 / 400, r0 = p0 - b0 * 400;
+  int b, ra, rb;
+  if (s == 0) { b = b0; ra = r0; rb = min(399, r0 + 127); }
+  else { b = b0 + 1; ra = 0; rb = r0 + 127 - 400; }
+  g.valid = b < nb && rb >= ra;
+  if (!g.valid) { g.bytes = 0; g.oy_a = 0; g.src_off = 0; g.rows_begin = 0; return; }
+  const int oy_a = ra / 20, oy_b = rb / 20;
+  g.oy_a = oy_a;
+  g.bytes = (uint32_t)(((oy_b - oy_a) * 4 + 8) * kC1RowBytes);
+  const int64_t srow = row_idx ? row_idx[b] : (int64_t)b;
+  g.src_off = srow * kC1FrameBytes + (int64_t)oy_a * 4 * kC1RowBytes;
+}
+
+// smem byte offset (inside the raw staging buffer pair of one tile) of the tap-(0,0) pixel of tile
+// row r, or -1 if the row lies past the end of the batch.
+__device__ __forceinline__ int c1_row_base(int p0, int r, int nb) {
+  const int p = p0 + r;
+  const int b0 = p0 / 400;
+  const int b = p / 400;
+  if (b >= nb) return -1;
+  const int rem = p - b * 400;
+  const int oy = rem / 20, ox = rem - oy * 20;
+  int oy_a;
+  if (b == b0) oy_a = (p0 - b0 * 400) / 20; else oy_a = 0;
+  return (b - b0) * kC1SegBytes + (oy - oy_a) * 4 * kC1RowBytes + ox * 16;
+}
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+  return v;
+}
+
+// 8 uint8 -> 8 bf16 (exact: 0..255 fit the 8-bit significand): fp32 magic number then truncation.
+__device__ __forceinline__ uint4 u8x8_to_bf16x8(uint2 w) {
+  const uint32_t magic = 0x4B000000u;                 // 2^23
+  float f[8];
+  f[0] = __uint_as_float(__byte_perm(w.x, magic, 0x7440)) - 8388608.f;   // {b0,0,0,0x4B}
+  f[1] = __uint_as_float(__byte_perm(w.x, magic, 0x7441)) - 8388608.f;
+  f[2] = __uint_as_float(__byte_perm(w.x, magic, 0x7442)) - 8388608.f;
+  f[3] = __uint_as_float(__byte_perm(w.x, magic, 0x7443)) - 8388608.f;
+  f[4] = __uint_as_float(__byte_perm(w.y, magic, 0x7440)) - 8388608.f;
+  f[5] = __uint_as_float(__byte_perm(w.y, magic, 0x7441)) - 8388608.f;
+  f[6] = __uint_as_float(__byte_perm(w.y, magic, 0x7442)) - 8388608.f;
+  f[7] = __uint_as_float(__byte_perm(w.y, magic, 0x7443)) - 8388608.f;
+  uint4 o;   // bf16x2 = high halves of the two floats
+  o.x = __byte_perm(__float_as_uint(f[0]), __float_as_uint(f[1]), 0x7632);
+  o.y = __byte_perm(__float_as_uint(f[2]), __float_as_uint(f[3]), 0x7632);
+  o.z = __byte_perm(__float_as_uint(f[4]), __float_as_uint(f[5]), 0x7632);
+  o.w = __byte_perm(__float_as_uint(f[6]), __float_as_uint(f[7]), 0x7632);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kC1ProdWarps = 8;
+constexpr int kC1Threads = 32 * (5 + kC1ProdWarps);
+constexpr int kC1FwdSmem = 16384 /*B*/ + 4 * 16384 /*A*/ + 2 * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
+
+__global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Args args) {
+  using namespace umma;
+  constexpr int NP = 32 * kC1ProdWarps;          // producer threads
+  constexpr int RPT = 128 / (NP / 8);            // tile rows per producer thread
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + 16384;
+  uint8_t* sRaw = smem + 16384 + 4 * 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + 2 * 2 * kC1SegBytes);
+  uint64_t* full = bars;            // [4] one per k-block tile
+  uint64_t* empty = bars + 4;       // [4]
+  uint64_t* tfull = bars + 8;       // [2]
+  uint64_t* tempty = bars + 10;     // [2]
+  uint64_t* raw_full = bars + 12;   // [2]
+  uint64_t* raw_empty = bars + 14;  // [2]
+  uint64_t* b_full = bars + 16;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = args.nb * 400;
+  const int num_tiles = (M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull + a, 1); mbar_init(tempty + a, 128);
+      mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP);
+    }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 5) {
+    // ================= producers: TMA-stage the raw rows, convert u8 -> fp16 into the A tiles ===========
+    const int pt = threadIdx.x - 160;
+    const int c = pt & 7, rg = pt >> 3;
+    auto issue_raw = [&](int tile, uint32_t j) {      // thread 0 only
+      const uint32_t buf = j & 1;
+      mbar_wait(raw_empty + buf, ((j >> 1) & 1) ^ 1);
+      C1Seg s0, s1;
+      c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
+      c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
+      mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes);
+      uint8_t* dst = sRaw + buf * 2 * kC1SegBytes;
+      if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
+      if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
+    };
+    if (pt == 0) {
+      mbar_arrive_expect_tx(b_full, 16384);
+      tma_bulk_g2s(sB, args.bpack, 16384, b_full);
+      if ((int)blockIdx.x < num_tiles) issue_raw(blockIdx.x, 0);
+    }
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t buf = j & 1;
+      if (pt == 0 && tile + (int)gridDim.x < num_tiles) issue_raw(tile + gridDim.x, j + 1);
+      int rb[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) rb[q] = c1_row_base(tile * 128, q * (NP / 8) + rg, args.nb);
+      mbar_wait(raw_full + buf, (j >> 1) & 1);
+      const uint32_t raw_addr = smem_u32(sRaw + buf * 2 * kC1SegBytes);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        mbar_wait(empty + kb, (j & 1) ^ 1);
+        const uint32_t a_addr = smem_u32(sA + kb * 16384);
+        const uint32_t koff = (uint32_t)((2 * kb + (c >> 2)) * kC1RowBytes + (c & 3) * 8);
+        uint2 v[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) v[q] = rb[q] >= 0 ? lds_v2(raw_addr + rb[q] + koff) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) st_shared_v4(a_addr + swz_off<128>(q * (NP / 8) + rg, c), u8x8_to_f16x8(v[q]));
+        fence_proxy_async_smem();
+        mbar_arrive(full + kb);
+      }
+      mbar_arrive(raw_empty + buf);
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(0u, 128, 32, 0, 0);     // fp16 operands
+      mbar_wait(b_full, 0);
+      uint32_t j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t acc = j & 1;
+        mbar_wait(tempty + acc, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(full + kb, j & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sB + kb * 4096);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_f16_ss(tmem_base + acc * 32, make_smem_desc(a_addr + k * 32, 0, 1024, LAYOUT_SW128),
+                       make_smem_desc(b_addr + k * 32, 0, 1024, LAYOUT_SW128), idesc, (kb | k) != 0);
+          mma_commit(empty + kb);
+        }
+        mma_commit(tfull + acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue: acc * (1/255) + bias, ReLU, bf16, one 64-byte row per thread ===========
+    float bias[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias[i] = __ldg(args.bias + i);
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t acc = j & 1;
+      const int m = tile * 128 + threadIdx.x;
+      mbar_wait(tfull + acc, (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty + acc);
+      if (m < M) {
+        uint4* o = reinterpret_cast<uint4*>(args.out + (int64_t)m * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(__uint_as_float(r[8 * q + i]), args.scale, bias[8 * q + i]), 0.f);
+          o[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace drl
+
+namespace drl {
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient:  dW1^T[kp=256 x co=32] += P[m x 256]^T * dY1[m x 32]   (both operands MN-major)
+// Per tile of 128 positions: frames + the 8 KB of dY1 rows arrive by TMA into a raw staging buffer;
+// producers build 4 sub-stages of 32 rows: 4 patch atoms (32 x 64 kp, bf16, SW128) + the dY tile
+// (32 x 32, SW64).  The two 128x32 accumulators live in TMEM for the whole kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kC1wStage = 4 * 4096 + 2048;                 // 18 KB
+constexpr int kC1wRaw = 2 * kC1SegBytes + 8192;            // frames (2 segments) + dY rows
+constexpr int kC1WgradSmem = 4 * kC1wStage + 2 * kC1wRaw + 256 + 1024;
+
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
+__global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1Args args) {
+  using namespace umma;
+  constexpr int NP = 32 * kC1ProdWarps;          // 256 producer threads
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sSt = smem;                                   // 4 sub-stages
+  uint8_t* sRaw = smem + 4 * kC1wStage;                  // 2 raw buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + 2 * kC1wRaw);
+  uint64_t* full = bars;            // [4]
+  uint64_t* empty = bars + 4;       // [4]
+  uint64_t* raw_full = bars + 8;    // [2]
+  uint64_t* raw_empty = bars + 10;  // [2]
+  uint64_t* done = bars + 12;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = args.nb * 400;
+  const int num_tiles = (M + 127) / 128;
+  // contiguous slice of tiles per CTA
+  const int per = (num_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per, t_end = min(num_tiles, t_begin + per);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (t_begin < t_end) {
+    if (warp >= 5) {
+      const int pt = threadIdx.x - 160;
+      const int c = pt & 7, row = pt >> 3;         // one row of each 32-row sub-stage per thread
+      auto issue_raw = [&](int tile, uint32_t j) {
+        const uint32_t buf = j & 1;
+        mbar_wait(raw_empty + buf, ((j >> 1) & 1) ^ 1);
+        C1Seg s0, s1;
+        c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
+        c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
+        const uint32_t dy_bytes = (uint32_t)min(128, M - tile * 128) * 64u;
+        mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes + dy_bytes);
+        uint8_t* dst = sRaw + buf * kC1wRaw;
+        if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
+        if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
+        tma_bulk_g2s(dst + 2 * kC1SegBytes, args.dy + (int64_t)tile * 128 * 32, dy_bytes, raw_full + buf);
+      };
+      if (pt == 0) issue_raw(t_begin, 0);
+      uint32_t j = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++j) {
+        const uint32_t buf = j & 1;
+        if (pt == 0 && tile + 1 < t_end) issue_raw(tile + 1, j + 1);
+        int rb[4];
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) rb[ss] = c1_row_base(tile * 128, ss * 32 + row, args.nb);
+        mbar_wait(raw_full + buf, (j >> 1) & 1);
+        const uint32_t raw_addr = smem_u32(sRaw + buf * kC1wRaw);
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) {
+          mbar_wait(empty + ss, (j & 1) ^ 1);
+          const uint32_t st_addr = smem_u32(sSt + ss * kC1wStage);
+          uint2 v[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            v[a] = rb[ss] >= 0 ? lds_v2(raw_addr + rb[ss] + (uint32_t)((2 * a + (c >> 2)) * kC1RowBytes + (c & 3) * 8))
+                               : make_uint2(0u, 0u);
+          uint4 dyv = make_uint4(0u, 0u, 0u, 0u);
+          if (c < 4 && rb[ss] >= 0) dyv = lds_v4(raw_addr + 2 * kC1SegBytes + (ss * 32 + row) * 64 + c * 16);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) st_shared_v4(st_addr + a * 4096 + swz_off<128>(row, c), u8x8_to_bf16x8(v[a]));
+          if (c < 4) st_shared_v4(st_addr + 4 * 4096 + swz_off<64>(row, c), dyv);
+          fence_proxy_async_smem();
+          mbar_arrive(full + ss);
+        }
+        mbar_arrive(raw_empty + buf);
+      }
+    } else if (warp == 4) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_f16(1u, 128, 32, 1, 1);   // bf16, MN-major A and B
+        uint32_t j = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++j) {
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss) {
+            mbar_wait(full + ss, j & 1);
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(sSt + ss * kC1wStage), d_addr = p_addr + 4 * 4096;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                mma_f16_ss(tmem_base + mb * 32,
+                           make_smem_desc(p_addr + (2 * mb) * 4096 + k * 16 * 128, 4096, 1024, LAYOUT_SW128),
+                           make_smem_desc(d_addr + k * 16 * 64, 0, 512, LAYOUT_SW64), idesc,
+                           (j > 0 || ss > 0 || k > 0) ? 1u : 0u);
+            mma_commit(empty + ss);
+          }
+        }
+        mma_commit(done);
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(done, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int kp = mb * 128 + threadIdx.x;            // (ky, kx, ci): ky = kp/32, kx = (kp%32)/4, ci = kp%4
+        const int ky = kp >> 5, kx = (kp & 31) >> 2, ci = kp & 3;
+        float* g0 = args.gw + (ci * 8 + ky) * 8 + kx;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int co = 0; co < 32; ++co) atomicAdd(g0 + co * 256, __uint_as_float(r[co]) * args.scale);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace drl

@@ -53,21 +53,21 @@ struct RowGatherArgs {
   int out_C;                  // elements per output pixel
   int osy, osx;               // output pixel = (oy*osy + ooy, ox*osx + oox)
   int n_variant_stride;       // n0 = blockIdx.y * n_variant_stride (N tiles); 0 for parity classes
-  int classes;                // 1: blockIdx.y encodes (ooy, oox) = (y >> 1, y & 1)
+  int classes;                // 1: 32-column chunk ch of the tile goes to output pixel (oy*osy + ch/2, ox*osx + ch%2)
 };
 
 template <int N>
 struct RowGatherSmem {
-  static constexpr int kStages = 4;
+  static constexpr int kStages = N >= 128 ? 3 : 4;     // 96 KB per CTA either way: two CTAs per SM
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = N * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 256 + 1024;   // barriers + bias[N]
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // + alignment slack
 };
 
 template <int N, int SRC, int EPI>
-__global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherArgs args) {
+__global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherArgs args) {
   using namespace umma;
   using L = RowGatherSmem<N>;
   constexpr int S = L::kStages;
@@ -83,9 +83,11 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
   uint64_t* tfull = bars + 2 * S;    // [2]
   uint64_t* tempty = bars + 2 * S + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  float* sBias = reinterpret_cast<float*>(bars) + 64;   // [N] (256 B past the barriers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (args.M + 127) / 128;
+  if (EPI != EPI_MASK_BF16 && threadIdx.x < N) sBias[threadIdx.x] = args.bias[blockIdx.y * args.n_variant_stride + threadIdx.x];
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 129); mbar_init(empty + s, 1); }
@@ -100,16 +102,16 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
 
   const uint8_t* bpack = reinterpret_cast<const uint8_t*>(args.bpack) + (int64_t)blockIdx.y * args.b_variant_stride;
   const int n0 = blockIdx.y * args.n_variant_stride;
-  const int ooy = args.classes ? (blockIdx.y >> 1) : 0, oox = args.classes ? (blockIdx.y & 1) : 0;
 
   if (warp >= 5) {
     // ================= producers: im2col gather of the A tile =================
     const int pt = threadIdx.x - 160;          // 0..127
     const int c = pt & 7, rg = pt >> 3;
     constexpr int ES = SRC == SRC_U8 ? 1 : 2;  // source element bytes
-    uint32_t stage = 0, phase = 0;
+    constexpr uint32_t LAG = 2;                // async-copy k-blocks in flight behind the newest one
+    uint32_t it = 0;                           // k-block iteration counter (across tiles)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int64_t base[8];       // byte offset of the (tap 0,0) source pixel of each of my 8 rows; <0: row invalid
+      int64_t base[8];       // byte offset of the (tap 0,0) source pixel of each of my 8 rows; INT64_MIN: row invalid
       int py0[8], px0[8];    // source pixel coords of tap (0,0) (only needed when pad > 0)
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
@@ -125,14 +127,14 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
           base[p] = INT64_MIN; py0[p] = 0; px0[p] = 0;
         }
       }
-      for (int kb = 0; kb < args.KB; ++kb) {
+      for (int kb = 0; kb < args.KB; ++kb, ++it) {
+        const uint32_t stage = it % S, phase = (it / S) & 1;
         mbar_wait(empty + stage, phase ^ 1);
-        uint8_t* a_st = sA + stage * L::kABytes;
         if (pt == 0) {
           mbar_arrive_expect_tx(full + stage, L::kBBytes);
           tma_bulk_g2s(sB + stage * L::kBBytes, bpack + (int64_t)kb * L::kBBytes, L::kBBytes, full + stage);
         }
-        const uint32_t a_addr = smem_u32(a_st);
+        const uint32_t a_addr = smem_u32(sA + stage * L::kABytes);
         if (SRC == SRC_U8) {
           // k-block = 2 kernel rows x (8 px x 4 ch): chunk c -> ky = 2kb + (c>>2), 2 pixels at (c&3)*2
           const int ky = 2 * kb + (c >> 2);
@@ -143,12 +145,13 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
             v[p] = base[p] != INT64_MIN ? ldg_v2(reinterpret_cast<const uint8_t*>(args.src) + base[p] + koff) : make_uint2(0u, 0u);
 #pragma unroll
           for (int p = 0; p < 8; ++p) st_shared_v4(a_addr + swz_off<128>(p * 16 + rg, c), u8x8_to_f16x8(v[p]));
+          fence_proxy_async_smem();
+          mbar_arrive(full + stage);
         } else {
           const int ty = kb / args.KBX, kbx = kb - ty * args.KBX;
           const int eoff = kbx * 64 + c * 8;                      // element offset inside the tap row
           const int64_t koff = ((int64_t)ty * args.W * args.C + eoff) * ES;
           const int tx = eoff / args.C;                           // pixel offset (bounds check only)
-          uint4 v[8];
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
             bool ok = base[p] != INT64_MIN;
@@ -156,15 +159,22 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
               const int y = py0[p] + ty, x = px0[p] + tx;
               ok = ok && y >= 0 && y < args.H && x >= 0 && x < args.W;
             }
-            v[p] = ok ? ldg_v4(reinterpret_cast<const uint8_t*>(args.src) + base[p] + koff) : make_uint4(0u, 0u, 0u, 0u);
+            const uint8_t* g = reinterpret_cast<const uint8_t*>(args.src) + (ok ? base[p] + koff : 0);
+            cp_async_16(a_addr + swz_off<128>(p * 16 + rg, c), g, ok ? 16u : 0u);
           }
-#pragma unroll
-          for (int p = 0; p < 8; ++p) st_shared_v4(a_addr + swz_off<128>(p * 16 + rg, c), v[p]);
+          cp_async_commit();
+          if (it >= LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async_smem();
+            mbar_arrive(full + ((it - LAG) % S));
+          }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(full + stage);
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
+    }
+    if (SRC != SRC_U8) {     // drain the copies still in flight
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; ++j) mbar_arrive(full + (j % S));
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -204,8 +214,20 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
       if (m < args.M) {
         const int b = m / args.P, rem = m - b * args.P;
         const int oy = rem / args.OW, ox = rem - oy * args.OW;
-        ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(oy * args.osy + ooy) * args.out_row_pitch +
-               (int64_t)(ox * args.osx + oox) * args.out_C + n0;
+        ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(oy * args.osy) * args.out_row_pitch +
+               (int64_t)(ox * args.osx) * args.out_C + n0;
+      }
+      // chunk ch (32 columns) goes to ooff + coff(ch): consecutive columns, or — for the merged
+      // parity classes of the stride-2 transposed conv — output pixel (2u + ch/2, 2v + ch%2)
+      auto coff = [&](int ch) -> int64_t {
+        return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
+      };
+      uint4 mk[N <= 64 ? N / 8 : 1];
+      if (EPI == EPI_MASK_BF16 && N <= 64 && ooff >= 0) {      // prefetch the ReLU mask before the accumulator is ready
+#pragma unroll
+        for (int ch = 0; ch < N / 32; ++ch)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mk[ch * 4 + q] = ldg_v4(args.mask_src + ooff + coff(ch) + 8 * q);
       }
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
@@ -223,11 +245,12 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
             float* o = reinterpret_cast<float*>(args.out) + ooff + ch * 32;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
+              const float4 bb = *reinterpret_cast<const float4*>(sBias + ch * 32 + 4 * q);
               float4 v;
-              v.x = fmaxf(fmaf(__uint_as_float(r[4 * q + 0]), args.scale, __ldg(args.bias + n0 + ch * 32 + 4 * q + 0)), 0.f);
-              v.y = fmaxf(fmaf(__uint_as_float(r[4 * q + 1]), args.scale, __ldg(args.bias + n0 + ch * 32 + 4 * q + 1)), 0.f);
-              v.z = fmaxf(fmaf(__uint_as_float(r[4 * q + 2]), args.scale, __ldg(args.bias + n0 + ch * 32 + 4 * q + 2)), 0.f);
-              v.w = fmaxf(fmaf(__uint_as_float(r[4 * q + 3]), args.scale, __ldg(args.bias + n0 + ch * 32 + 4 * q + 3)), 0.f);
+              v.x = fmaxf(fmaf(__uint_as_float(r[4 * q + 0]), args.scale, bb.x), 0.f);
+              v.y = fmaxf(fmaf(__uint_as_float(r[4 * q + 1]), args.scale, bb.y), 0.f);
+              v.z = fmaxf(fmaf(__uint_as_float(r[4 * q + 2]), args.scale, bb.z), 0.f);
+              v.w = fmaxf(fmaf(__uint_as_float(r[4 * q + 3]), args.scale, bb.w), 0.f);
               reinterpret_cast<float4*>(o)[q] = v;
             }
           } else if (EPI == EPI_BIAS_RELU_BF16) {
@@ -237,16 +260,15 @@ __global__ void __launch_bounds__(288, 1) rowgather_gemm_kernel(const RowGatherA
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                f[j] = fmaxf(fmaf(__uint_as_float(r[8 * q + j]), args.scale, __ldg(args.bias + n0 + ch * 32 + 8 * q + j)), 0.f);
+                f[j] = fmaxf(fmaf(__uint_as_float(r[8 * q + j]), args.scale, sBias[ch * 32 + 8 * q + j]), 0.f);
               uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
               reinterpret_cast<uint4*>(o)[q] = pk;
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
-            const __nv_bfloat16* mk = args.mask_src + ooff + ch * 32;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 mv = ldg_v4(mk + 8 * q);
+              const uint4 mv = N <= 64 ? mk[ch * 4 + q] : ldg_v4(args.mask_src + ooff + coff(ch) + 8 * q);
               const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
               uint32_t pk[4];
 #pragma unroll
@@ -296,23 +318,28 @@ struct WgradArgs {
 
 template <int NT>
 struct WgradCfg {
+  static constexpr int kRows = 32;                                // reduction rows per smem stage
+  static constexpr int kStages = 4;
   static constexpr int kDyRowB = NT >= 64 ? 128 : 64;             // bytes per dY tile row (per atom)
   static constexpr int kDyAtoms = NT >= 64 ? NT / 64 : 1;
-  static constexpr int kDyBytes = kDyAtoms * 64 * kDyRowB;        // 64 rows per stage
-  static constexpr int kAtomBytes = 64 * 128;
+  static constexpr int kDyAtomBytes = kRows * kDyRowB;
+  static constexpr int kDyBytes = kDyAtoms * kDyAtomBytes;
+  static constexpr int kAtomBytes = kRows * 128;                  // one patch atom: 32 rows x 64 kp
 };
 
-template <int NT, int SRC, int MB>     // MB: accumulator blocks per CTA (compile-time upper bound)
+template <int NT, int SRC, int MB>     // MB: accumulator blocks (128 kp each) per CTA
 __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args) {
   using namespace umma;
   using Cf = WgradCfg<NT>;
-  constexpr int S = 2;
+  constexpr int S = Cf::kStages;
+  constexpr int ROWS = Cf::kRows;
   constexpr int NA = 2 * MB;                                    // patch atoms per stage
   constexpr int P_BYTES = NA * Cf::kAtomBytes;
   constexpr int STAGE = P_BYTES + Cf::kDyBytes;
   constexpr int ACC_COLS = MB * NT;
   constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(STAGE % 1024 == 0, "stage alignment");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * STAGE);
@@ -322,8 +349,8 @@ __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // this CTA's slice of the reduction, in stages of 64 rows
-  const int total_stages = (args.M + 63) / 64;
+  // this CTA's slice of the reduction, in stages of ROWS rows
+  const int total_stages = (args.M + ROWS - 1) / ROWS;
   const int per = (total_stages + gridDim.x - 1) / gridDim.x;
   const int st_begin = blockIdx.x * per;
   const int st_end = min(total_stages, st_begin + per);
@@ -346,17 +373,19 @@ __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args
     if (warp >= 5) {
       // ================= producers =================
       const int pt = threadIdx.x - 160;
-      const int c = pt & 7, slot = pt >> 3;      // rows slot*4 .. slot*4+3 of the stage
+      const int c = pt & 7, slot = pt >> 3;      // rows slot*2, slot*2+1 of the stage
       constexpr int ES = SRC == SRC_U8 ? 1 : 2;
-      uint32_t stage = 0, phase = 0;
-      for (int st = st_begin; st < st_end; ++st) {
+      constexpr uint32_t LAG = 2;
+      uint32_t it = 0;
+      for (int st = st_begin; st < st_end; ++st, ++it) {
+        const uint32_t stage = it & (S - 1), phase = (it / S) & 1;
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* base_s = smem + stage * STAGE;
         const uint32_t p_addr = smem_u32(base_s), d_addr = smem_u32(base_s + P_BYTES);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = slot * 4 + i;
-          const int m = st * 64 + r;
+        for (int i = 0; i < 2; ++i) {
+          const int r = slot * 2 + i;
+          const int m = st * ROWS + r;
           const bool live = m < args.M;
           int64_t base = 0;
           if (live) {
@@ -365,66 +394,73 @@ __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args
             const int64_t srow = args.row_idx ? args.row_idx[b] : (int64_t)b;
             base = ((srow * args.H + oy * args.stride) * (int64_t)args.W + ox * args.stride) * args.C * ES;
           }
-          // dY tile row
+          // dY tile row (bf16, always an async copy)
           if (NT >= 64) {
 #pragma unroll
-            for (int a = 0; a < Cf::kDyAtoms; ++a) {
-              const uint4 v = live ? ldg_v4(args.dy + (int64_t)m * args.dy_ld + n0 + a * 64 + c * 8) : make_uint4(0u, 0u, 0u, 0u);
-              st_shared_v4(d_addr + a * Cf::kAtomBytes + swz_off<128>(r, c), v);
-            }
+            for (int a = 0; a < Cf::kDyAtoms; ++a)
+              cp_async_16(d_addr + a * Cf::kDyAtomBytes + swz_off<128>(r, c),
+                          args.dy + (live ? (int64_t)m * args.dy_ld + n0 + a * 64 + c * 8 : 0), live ? 16u : 0u);
           } else if (c < 4) {
-            const uint4 v = live ? ldg_v4(args.dy + (int64_t)m * args.dy_ld + n0 + c * 8) : make_uint4(0u, 0u, 0u, 0u);
-            st_shared_v4(d_addr + swz_off<64>(r, c), v);
+            cp_async_16(d_addr + swz_off<64>(r, c), args.dy + (live ? (int64_t)m * args.dy_ld + n0 + c * 8 : 0), live ? 16u : 0u);
           }
           // patch row: atoms atom0 .. atom0+NA-1
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
             const int atom = atom0 + a;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (live && atom < args.n_atoms_valid) {
-              if (SRC == SRC_U8) {
+            const bool ok = live && atom < args.n_atoms_valid;
+            const uint32_t dst = p_addr + a * Cf::kAtomBytes + swz_off<128>(r, c);
+            if (SRC == SRC_U8) {
+              uint4 v = make_uint4(0u, 0u, 0u, 0u);
+              if (ok) {
                 const int ky = 2 * atom + (c >> 2);
                 const uint2 w = ldg_v2(reinterpret_cast<const uint8_t*>(args.src) + base + (int64_t)ky * args.W * args.C + (c & 3) * 8);
                 v.x = pack_bf16x2((float)(w.x & 0xffu), (float)((w.x >> 8) & 0xffu));
                 v.y = pack_bf16x2((float)((w.x >> 16) & 0xffu), (float)(w.x >> 24));
                 v.z = pack_bf16x2((float)(w.y & 0xffu), (float)((w.y >> 8) & 0xffu));
                 v.w = pack_bf16x2((float)((w.y >> 16) & 0xffu), (float)(w.y >> 24));
-              } else {
-                const int ty = atom / args.KBX, kbx = atom - ty * args.KBX;
-                v = ldg_v4(reinterpret_cast<const uint8_t*>(args.src) + base +
-                           ((int64_t)ty * args.W * args.C + kbx * 64 + c * 8) * ES);
               }
+              st_shared_v4(dst, v);
+            } else {
+              const int ty = atom / args.KBX, kbx = atom - ty * args.KBX;
+              const uint8_t* g = reinterpret_cast<const uint8_t*>(args.src) +
+                                 (ok ? base + ((int64_t)ty * args.W * args.C + kbx * 64 + c * 8) * ES : 0);
+              cp_async_16(dst, g, ok ? 16u : 0u);
             }
-            st_shared_v4(p_addr + a * Cf::kAtomBytes + swz_off<128>(r, c), v);
           }
         }
-        fence_proxy_async_smem();
-        mbar_arrive(full + stage);
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        cp_async_commit();
+        if (it >= LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async_smem();
+          mbar_arrive(full + ((it - LAG) & (S - 1)));
+        }
       }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; ++j) mbar_arrive(full + (j & (S - 1)));
     } else if (warp == 4) {
       // ================= MMA issuer =================
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);       // bf16, both operands MN-major
-        uint32_t stage = 0, phase = 0;
-        for (int st = st_begin; st < st_end; ++st) {
+        uint32_t it = 0;
+        for (int st = st_begin; st < st_end; ++st, ++it) {
+          const uint32_t stage = it & (S - 1), phase = (it / S) & 1;
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t p_addr = smem_u32(smem + stage * STAGE), d_addr = p_addr + P_BYTES;
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < ROWS / 16; ++k) {
               // A: 2 MN-atoms of 64 kp (LBO = atom stride), 16 reduction rows per MMA (128 B each)
               const uint64_t ad = make_smem_desc(p_addr + (2 * mb) * Cf::kAtomBytes + k * 16 * 128, Cf::kAtomBytes, 1024, LAYOUT_SW128);
               const uint64_t bd = NT >= 64
-                  ? make_smem_desc(d_addr + k * 16 * 128, Cf::kAtomBytes, 1024, LAYOUT_SW128)
+                  ? make_smem_desc(d_addr + k * 16 * 128, Cf::kDyAtomBytes, 1024, LAYOUT_SW128)
                   : make_smem_desc(d_addr + k * 16 * 64, 0, 512, LAYOUT_SW64);
-              mma_f16_ss(tmem_base + mb * NT, ad, bd, idesc, (st > st_begin || k > 0) ? 1u : 0u);
+              mma_f16_ss(tmem_base + mb * NT, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
           }
           mma_commit(empty + stage);
-          if (++stage == S) { stage = 0; phase ^= 1; }
         }
         mma_commit(done);
       }

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <new>
 #include "umma_gemm.cuh"
+#include "umma_conv1.cuh"
 
 namespace drl {
 
@@ -23,7 +24,7 @@ struct Bf16Engine {
   void* wff = nullptr;   // fc fwd      bf16 [4 n-tiles][49][128x64]
   void* wfd = nullptr;   // fc dgrad    bf16 [49 n-tiles][8][64x64]
   void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
-  void* w2d = nullptr;   // conv2 dgrad bf16 [4 classes][4][32x64]
+  void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
 };
 
 // ---- packing -----------------------------------------------------------------------------------------
@@ -57,10 +58,10 @@ __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n,
       const int t = k / 64, co = k - t * 64, ty = t / 3, tx = t - ty * 3;
       return a.w[((size_t)(co * 64 + n) * 3 + (2 - ty)) * 3 + (2 - tx)];
     }
-    default: {                     // PK_CONV2_DGRAD: class (py,px); B[n=ci][k=(ty,tx,co)] = W2[co,ci,py+2(1-ty),px+2(1-tx)]
-      const int py = variant >> 1, px = variant & 1;
+    default: {                     // PK_CONV2_DGRAD: row n = (class (py,px), ci); B[n][k=(ty,tx,co)] = W2[co,ci,py+2(1-ty),px+2(1-tx)]
+      const int cls = n >> 5, ci = n & 31, py = cls >> 1, px = cls & 1;
       const int t = k / 64, co = k - t * 64, ty = t >> 1, tx = t & 1;
-      return a.w[((size_t)(co * 32 + n) * 4 + (py + 2 * (1 - ty))) * 4 + (px + 2 * (1 - tx))];
+      return a.w[((size_t)(co * 32 + ci) * 4 + (py + 2 * (1 - ty))) * 4 + (px + 2 * (1 - tx))];
     }
   }
 }
@@ -185,7 +186,7 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   DRL_TRY(pack_one(p + o[6], e->wff, PK_FC_FWD, 0, 4, 49, 128, 64, 7, 7, 512, st));
   DRL_TRY(pack_one(p + o[6], e->wfd, PK_FC_DGRAD, 0, 49, 8, 64, 64, 7, 7, 512, st));
   DRL_TRY(pack_one(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64, st));
-  DRL_TRY(pack_one(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 4, 4, 32, 32, 4, 4, 64, st));
+  DRL_TRY(pack_one(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 1, 4, 128, 32, 4, 4, 64, st));
   return DRL_OK;
 }
 
@@ -200,7 +201,7 @@ static int launch_rowgather(const char* site, const RowGatherArgs& a, int grid_y
     configured = true;
   }
   const int tiles = (a.M + 127) / 128;
-  int gx = sm_count() / grid_y;
+  int gx = 2 * sm_count() / grid_y;        // two CTAs per SM (96 KB smem, <= 256 TMEM columns each)
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
   kern<<<dim3(gx, grid_y), 288, smem, st>>>(a);
@@ -212,7 +213,8 @@ template <int NT, int SRC, int MB>
 static int launch_wgrad(const char* site, const WgradArgs& a, int grid_x, int grid_y, cudaStream_t st) {
   ProfileScope prof(site, st);
   auto kern = wgrad_gemm_kernel<NT, SRC, MB>;
-  constexpr int smem = 2 * (2 * MB * 8192 + WgradCfg<NT>::kDyBytes) + 256 + 1024;
+  using Cf = WgradCfg<NT>;
+  constexpr int smem = Cf::kStages * (2 * MB * Cf::kAtomBytes + Cf::kDyBytes) + 256 + 1024;
   static bool configured = false;
   if (!configured) {
     DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -239,9 +241,20 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   const float* p = n->params;
   const int64_t* o = n->off;
   // conv1: uint8 frames -> fp16 operands; y = relu(acc * (1/255) + b)   (scale_observations.py:35 fused)
-  RowGatherArgs a1 = fwd_args(nb, obs, row_idx, 400, 20, 84, 84, 4, 4, 4, 1, e->w1f, n->act[0], p + o[1],
-                              kInv255, 32);
-  DRL_TRY((launch_rowgather<32, SRC_U8, EPI_BIAS_RELU_BF16>("conv1_fwd", a1, 1, st)));
+  {
+    ProfileScope prof("conv1_fwd", st);
+    Conv1Args a1{};
+    a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.bpack = e->w1f; a1.bias = p + o[1]; a1.scale = kInv255;
+    a1.out = reinterpret_cast<__nv_bfloat16*>(n->act[0]);
+    static bool configured = false;
+    if (!configured) {
+      DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1FwdSmem));
+      configured = true;
+    }
+    const int tiles = (nb * 400 + 127) / 128;
+    conv1_fwd_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdSmem, st>>>(a1);
+    DRL_LAUNCH_CHECK();
+  }
   RowGatherArgs a2 = fwd_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 8, 2, e->w2f, n->act[1], p + o[3], 1.f, 64);
   DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
   RowGatherArgs a3 = fwd_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 9, 3, e->w3f, n->act[2], p + o[5], 1.f, 64);
@@ -267,7 +280,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   Bf16Engine* e = n->bf16;
   const int64_t* o = n->off;
   const int sms = sm_count();
-  auto splits = [&](int M, int gy) { int s = (M + 63) / 64; int gx = (sms + gy - 1) / gy; return s < gx ? s : gx; };
+  auto splits = [&](int M, int gy) { int s = (M + 31) / 32; int gx = (sms + gy - 1) / gy; return s < gx ? s : gx; };
 
   // ---- fc: bias, weight gradient (3136 x 512, split over the batch), data gradient (masked by act3 > 0)
   {
@@ -304,20 +317,32 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   WgradArgs w2 = wgrad_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 2, 8, n->dact[1], 64, 4, 1, g + o[2], 32, 4, 4);
   DRL_TRY((launch_wgrad<64, SRC_BF16, 4>("conv2_wgrad", w2, splits(nb * 81, 1), 1, st)));
   {
-    // four parity classes of the stride-2 transposed convolution: a 2x2-tap gather over dY2 each
+    // the four parity classes of the stride-2 transposed convolution share their 2x2-tap gather over dY2:
+    // ONE GEMM with N = 4 classes x 32 ci; column chunk `cls` lands on output pixel (2u + cls/2, 2v + cls%2)
     RowGatherArgs a{};
     a.M = nb * 100; a.KB = 4; a.src = n->dact[1]; a.row_idx = nullptr; a.P = 100; a.OW = 10; a.H = 9; a.W = 9; a.C = 64;
-    a.stride = 1; a.pad = 1; a.KBX = 2; a.bpack = e->w2d; a.b_variant_stride = (int64_t)4 * 32 * 128;
+    a.stride = 1; a.pad = 1; a.KBX = 2; a.bpack = e->w2d; a.b_variant_stride = 0;
     a.out = n->dact[0]; a.mask_src = (const __nv_bfloat16*)n->act[0]; a.scale = 1.f; a.bias = nullptr;
     a.out_sample_pitch = 12800; a.out_row_pitch = 20 * 32; a.out_C = 32; a.osy = 2; a.osx = 2;
     a.n_variant_stride = 0; a.classes = 1;
-    DRL_TRY((launch_rowgather<32, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 4, st)));
+    DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
   }
   // ---- conv1 (no data gradient: observations need none, agent.py:66-67)
   DRL_TRY(colsum(n->dact[0], (int64_t)nb * 400, 32, g + o[1], st));
-  WgradArgs w1 = wgrad_args(nb, obs, row_idx, 400, 20, 84, 84, 4, 4, 1, 4, n->dact[0], 32, 2, 1, g + o[0], 4, 8, 8);
-  w1.scale = kInv255;
-  DRL_TRY((launch_wgrad<32, SRC_U8, 2>("conv1_wgrad", w1, splits(nb * 400, 1), 1, st)));
+  {
+    ProfileScope prof("conv1_wgrad", st);
+    Conv1Args a1{};
+    a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.scale = kInv255;
+    a1.dy = reinterpret_cast<const __nv_bfloat16*>(n->dact[0]); a1.gw = g + o[0];
+    static bool configured = false;
+    if (!configured) {
+      DRL_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1WgradSmem));
+      configured = true;
+    }
+    const int tiles = (nb * 400 + 127) / 128;
+    conv1_wgrad_kernel<<<tiles < sms ? tiles : sms, kC1Threads, kC1WgradSmem, st>>>(a1);
+    DRL_LAUNCH_CHECK();
+  }
   return DRL_OK;
 }
 
