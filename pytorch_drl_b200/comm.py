@@ -12,21 +12,37 @@ from . import _lib
 from ._lib import check, current_stream, ptr
 
 
+def shard_envs(n_envs_total: int, rank: int, world_size: int) -> range:
+    """GPU `rank` owns envs [rank*n/world, (rank+1)*n/world) — the reference's rank = env model with
+    several envs per process.  Requires an even split."""
+    if n_envs_total % world_size != 0:
+        raise ValueError('n_envs_total must be divisible by world_size')
+    per = n_envs_total // world_size
+    return range(rank * per, (rank + 1) * per)
+
+
+def bootstrap_unique_id(rank: int, world_size: int, device_index: int = 0) -> bytes:
+    """Rank 0 creates the NCCL unique id, every rank receives it through torch.distributed
+    (works over gloo or nccl process groups)."""
+    L = _lib.lib()
+    ident = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)()
+    if rank == 0:
+        check(L.drl_comm_unique_id(ident), 'comm_unique_id')
+    t = tc.tensor(list(ident), dtype=tc.uint8)
+    if world_size > 1:
+        if not dist.is_initialized():
+            raise RuntimeError('torch.distributed must be initialised to bootstrap the communicator')
+        if dist.get_backend() == 'nccl':
+            t = t.cuda(device_index)
+        dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
 class Communicator:
     def __init__(self, rank: int, world_size: int, device_index: int):
         self.rank, self.world = rank, world_size
         L = _lib.lib()
-        ident = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)()
-        if rank == 0:
-            check(L.drl_comm_unique_id(ident), 'comm_unique_id')
-        t = tc.tensor(list(ident), dtype=tc.uint8)
-        if world_size > 1:
-            if not dist.is_initialized():
-                raise RuntimeError('torch.distributed must be initialised to bootstrap the communicator')
-            if dist.get_backend() == 'nccl':
-                t = t.cuda(device_index)
-            dist.broadcast(t, src=0)
-        ident = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)(*t.cpu().tolist())
+        ident = (ctypes.c_uint8 * _lib.NCCL_ID_BYTES)(*bootstrap_unique_id(rank, world_size, device_index))
         h = ctypes.c_void_p()
         check(L.drl_comm_create(ctypes.byref(h), ident, rank, world_size, device_index), 'comm_create')
         self._h, self._L = h, L

@@ -102,11 +102,13 @@ struct WeightFwd {            // B(k=(ky,kx,ci), n=co) = W[co, ci, ky, kx]
   }
 };
 
+// act: 0 identity, 1 ReLU, 2 LeakyReLU(0.2)
 template <typename TOut>
 struct EpiBiasRelu {
-  const float* bias; TOut* out; int N;
+  const float* bias; TOut* out; int N; int act;
   __device__ __forceinline__ void operator()(int m, int n, float acc) const {
-    out[(size_t)m * N + n] = fmaxf(acc + __ldg(bias + n), 0.f);
+    const float v = acc + __ldg(bias + n);
+    out[(size_t)m * N + n] = act == 1 ? fmaxf(v, 0.f) : (act == 2 ? (v > 0.f ? v : 0.2f * v) : v);
   }
 };
 
@@ -138,11 +140,11 @@ struct WeightDgrad {          // B(k=(ky,kx,co), n=ci) = W[co, ci, ky, kx]
   }
 };
 
-struct EpiReluMask {          // dX = acc * (X > 0): ReLU of the producing layer
-  const float* x_act; float* dx; int N;
+struct EpiReluMask {          // dX = acc * act'(X): activation of the producing layer (1 ReLU, 2 LeakyReLU 0.2)
+  const float* x_act; float* dx; int N; int act;
   __device__ __forceinline__ void operator()(int m, int n, float acc) const {
     const size_t i = (size_t)m * N + n;
-    dx[i] = __ldg(x_act + i) > 0.f ? acc : 0.f;
+    dx[i] = __ldg(x_act + i) > 0.f ? acc : (act == 2 ? 0.2f * acc : 0.f);
   }
 };
 
@@ -171,31 +173,55 @@ struct EpiWgrad {             // scatter-add into the OIHW gradient (+ bias grad
   }
 };
 
+// RND first conv: the LAST channel of the uint8 frame, scaled by 1/255, normalised with the running
+// moments and clipped to [-5, 5] (random_network_distillation.py:228-229; normalize.py:149-162),
+// fused into the im2col gather.  Cin = 1.
+struct NormPatchGather {
+  const uint8_t* obs; const int64_t* row_idx; const float* m1; const float* m2; ConvGeom g;
+  __device__ __forceinline__ float operator()(int r, int c) const {
+    const int pos = g.OH * g.OW;
+    const int b = r / pos, rem = r - b * pos;
+    const int oy = rem / g.OW, ox = rem - oy * g.OW;
+    const int ky = c / g.KW, kx = c - ky * g.KW;
+    const int y = oy * g.S + ky, x = ox * g.S + kx;
+    const size_t row = row_idx ? (size_t)row_idx[b] : (size_t)b;
+    const float v = __fmul_rn((float)__ldg(obs + ((row * 84 + y) * 84 + x) * 4 + 3), __uint_as_float(0x3b808081u));
+    const float mu = __ldg(m1 + y * 84 + x);
+    const float var = __fsub_rn(__ldg(m2 + y * 84 + x), __fmul_rn(mu, mu));
+    const float z = __fmul_rn(__fsub_rn(v, mu), rsqrtf(__fadd_rn(var, 1e-8f)));
+    return fminf(fmaxf(z, -5.f), 5.f);
+  }
+};
+struct NormPatchGatherT {
+  NormPatchGather pg; int Kp;
+  __device__ __forceinline__ float operator()(int k, int n) const { return n < Kp ? pg(k, n) : 1.f; }
+};
+
 static inline dim3 tiles(int M, int N, int z = 1) { return dim3((M + BM - 1) / BM, (N + BN - 1) / BN, z); }
 
 template <typename TIn>
 int simt_conv_forward(const TIn* in, const int64_t* row_idx, int nb, const ConvGeom& g, const float* w,
-                      const float* bias, float* out, cudaStream_t st) {
+                      const float* bias, float* out, cudaStream_t st, int act) {
   const int M = nb * g.OH * g.OW, N = g.Cout, K = g.KH * g.KW * g.Cin;
   PatchGather<TIn> af{in, row_idx, g};
   WeightFwd bf{w, g};
-  EpiBiasRelu<float> ef{bias, out, N};
+  EpiBiasRelu<float> ef{bias, out, N, act};
   ProfileScope prof("simt_fwd", st);
   simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
 template int simt_conv_forward<float>(const float*, const int64_t*, int, const ConvGeom&, const float*,
-                                      const float*, float*, cudaStream_t);
+                                      const float*, float*, cudaStream_t, int);
 template int simt_conv_forward<uint8_t>(const uint8_t*, const int64_t*, int, const ConvGeom&,
-                                        const float*, const float*, float*, cudaStream_t);
+                                        const float*, const float*, float*, cudaStream_t, int);
 
 int simt_conv_dgrad(const float* dy, int nb, const ConvGeom& g, const float* w, const float* x_act,
-                    float* dx, cudaStream_t st) {
+                    float* dx, cudaStream_t st, int act) {
   const int M = nb * g.H * g.W, N = g.Cin, K = g.KH * g.KW * g.Cout;
   DyGather af{dy, g};
   WeightDgrad bf{w, g};
-  EpiReluMask ef{x_act, dx, N};
+  EpiReluMask ef{x_act, dx, N, act};
   ProfileScope prof("simt_dgrad", st);
   simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
@@ -225,5 +251,39 @@ template int simt_conv_wgrad<float>(const float*, const float*, const int64_t*, 
                                     float*, float*, cudaStream_t);
 template int simt_conv_wgrad<uint8_t>(const float*, const uint8_t*, const int64_t*, int,
                                       const ConvGeom&, float*, float*, cudaStream_t);
+
+}  // namespace drl
+
+namespace drl {
+
+int simt_rnd_conv1_forward(const uint8_t* obs, const int64_t* row_idx, int nb, const float* m1, const float* m2,
+                           const ConvGeom& g, const float* w, const float* bias, float* out, cudaStream_t st) {
+  const int M = nb * g.OH * g.OW, N = g.Cout, K = g.KH * g.KW;
+  NormPatchGather af{obs, row_idx, m1, m2, g};
+  WeightFwd bf{w, g};
+  EpiBiasRelu<float> ef{bias, out, N, 2};
+  ProfileScope prof("rnd_simt_fwd", st);
+  simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+int simt_rnd_conv1_wgrad(const float* dy, const uint8_t* obs, const int64_t* row_idx, int nb, const float* m1,
+                         const float* m2, const ConvGeom& g, float* gw, float* gb, cudaStream_t st) {
+  const int Kp = g.KH * g.KW;
+  const int M = g.Cout, N = Kp + 1, K = nb * g.OH * g.OW;
+  const int base = tiles(M, N).x * tiles(M, N).y;
+  int splits = (sm_count() * 4 + base - 1) / base;
+  int k_per = (K + splits - 1) / splits;
+  k_per = ((k_per + BK - 1) / BK) * BK;
+  splits = (K + k_per - 1) / k_per;
+  DyT af{dy, g.Cout};
+  NormPatchGatherT bf{NormPatchGather{obs, row_idx, m1, m2, g}, Kp};
+  EpiWgrad ef{gw, gb, g, Kp};
+  ProfileScope prof("rnd_simt_wgrad", st);
+  simt_gemm_kernel<true><<<tiles(M, N, splits), 256, 0, st>>>(M, N, K, k_per, af, bf, ef);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
 
 }  // namespace drl

@@ -22,11 +22,17 @@ inline ConvGeom nature_layer(int l) {
 
 template <typename TIn>
 int simt_conv_forward(const TIn* in, const int64_t* row_idx, int nb, const ConvGeom& g, const float* w,
-                      const float* bias, float* out, cudaStream_t st);
+                      const float* bias, float* out, cudaStream_t st, int act = 1);
 int simt_conv_dgrad(const float* dy, int nb, const ConvGeom& g, const float* w, const float* x_act,
-                    float* dx, cudaStream_t st);
+                    float* dx, cudaStream_t st, int act = 1);
 template <typename TIn>
 int simt_conv_wgrad(const float* dy, const TIn* in, const int64_t* row_idx, int nb, const ConvGeom& g,
                     float* gw, float* gb, cudaStream_t st);
+
+// RND first conv (normalise + clip of the last frame channel fused into the gather)
+int simt_rnd_conv1_forward(const uint8_t* obs, const int64_t* row_idx, int nb, const float* m1, const float* m2,
+                           const ConvGeom& g, const float* w, const float* bias, float* out, cudaStream_t st);
+int simt_rnd_conv1_wgrad(const float* dy, const uint8_t* obs, const int64_t* row_idx, int nb, const float* m1,
+                         const float* m2, const ConvGeom& g, float* gw, float* gb, cudaStream_t st);
 
 }  // namespace drl

@@ -92,8 +92,9 @@ __device__ __forceinline__ uint4 u8x8_to_bf16x8(uint2 w) {
 // forward
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kC1ProdWarps = 8;
-constexpr int kC1Threads = 32 * (5 + kC1ProdWarps);
-constexpr int kC1FwdSmem = 16384 /*B*/ + 4 * 16384 /*A*/ + 2 * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
+constexpr int kC1Threads = 32 * (5 + kC1ProdWarps + 1);   // 4 epilogue + 1 MMA + 8 converters + 1 TMA warp
+constexpr int kC1NR = 4;                                    // raw staging buffers (tiles in flight)
+constexpr int kC1FwdSmem = 16384 /*B*/ + 4 * 16384 /*A*/ + kC1NR * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
 
 __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Args args) {
   using namespace umma;
@@ -104,25 +105,23 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
   uint8_t* sB = smem;
   uint8_t* sA = smem + 16384;
   uint8_t* sRaw = smem + 16384 + 4 * 16384;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + 2 * 2 * kC1SegBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1NR * 2 * kC1SegBytes);
   uint64_t* full = bars;            // [4] one per k-block tile
   uint64_t* empty = bars + 4;       // [4]
   uint64_t* tfull = bars + 8;       // [2]
   uint64_t* tempty = bars + 10;     // [2]
-  uint64_t* raw_full = bars + 12;   // [2]
-  uint64_t* raw_empty = bars + 14;  // [2]
-  uint64_t* b_full = bars + 16;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* raw_full = bars + 12;   // [kC1NR]
+  uint64_t* raw_empty = bars + 16;  // [kC1NR]
+  uint64_t* b_full = bars + 20;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = args.nb * 400;
   const int num_tiles = (M + 127) / 128;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull + a, 1); mbar_init(tempty + a, 128);
-      mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP);
-    }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < kC1NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -132,34 +131,36 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 5) {
-    // ================= producers: TMA-stage the raw rows, convert u8 -> fp16 into the A tiles ===========
-    const int pt = threadIdx.x - 160;
-    const int c = pt & 7, rg = pt >> 3;
-    auto issue_raw = [&](int tile, uint32_t j) {      // thread 0 only
-      const uint32_t buf = j & 1;
-      mbar_wait(raw_empty + buf, ((j >> 1) & 1) ^ 1);
-      C1Seg s0, s1;
-      c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
-      c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
-      mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes);
-      uint8_t* dst = sRaw + buf * 2 * kC1SegBytes;
-      if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
-      if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
-    };
-    if (pt == 0) {
+  if (warp == 5 + kC1ProdWarps) {
+    // ================= TMA warp: stage the raw frame rows of up to kC1NR tiles ahead ====================
+    if (lane == 0) {
       mbar_arrive_expect_tx(b_full, 16384);
       tma_bulk_g2s(sB, args.bpack, 16384, b_full);
-      if ((int)blockIdx.x < num_tiles) issue_raw(blockIdx.x, 0);
+      uint32_t j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t buf = j % kC1NR;
+        mbar_wait(raw_empty + buf, ((j / kC1NR) & 1) ^ 1);
+        C1Seg s0, s1;
+        c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
+        c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
+        mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes);
+        uint8_t* dst = sRaw + buf * 2 * kC1SegBytes;
+        if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
+        if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
+      }
     }
+    __syncwarp();
+  } else if (warp >= 5) {
+    // ================= converters: raw u8 rows -> fp16 im2col rows of the 4 swizzled A tiles =============
+    const int pt = threadIdx.x - 160;
+    const int c = pt & 7, rg = pt >> 3;
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-      const uint32_t buf = j & 1;
-      if (pt == 0 && tile + (int)gridDim.x < num_tiles) issue_raw(tile + gridDim.x, j + 1);
+      const uint32_t buf = j % kC1NR;
       int rb[RPT];
 #pragma unroll
       for (int q = 0; q < RPT; ++q) rb[q] = c1_row_base(tile * 128, q * (NP / 8) + rg, args.nb);
-      mbar_wait(raw_full + buf, (j >> 1) & 1);
+      mbar_wait(raw_full + buf, (j / kC1NR) & 1);
       const uint32_t raw_addr = smem_u32(sRaw + buf * 2 * kC1SegBytes);
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
@@ -248,7 +249,7 @@ namespace drl {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kC1wStage = 4 * 4096 + 2048;                 // 18 KB
 constexpr int kC1wRaw = 2 * kC1SegBytes + 8192;            // frames (2 segments) + dY rows
-constexpr int kC1WgradSmem = 4 * kC1wStage + 2 * kC1wRaw + 256 + 1024;
+constexpr int kC1WgradSmem = 4 * kC1wStage + kC1NR * kC1wRaw + 256 + 1024;
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
   uint4 v;
@@ -262,14 +263,14 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sSt = smem;                                   // 4 sub-stages
-  uint8_t* sRaw = smem + 4 * kC1wStage;                  // 2 raw buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + 2 * kC1wRaw);
+  uint8_t* sRaw = smem + 4 * kC1wStage;                  // kC1NR raw buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1NR * kC1wRaw);
   uint64_t* full = bars;            // [4]
   uint64_t* empty = bars + 4;       // [4]
-  uint64_t* raw_full = bars + 8;    // [2]
-  uint64_t* raw_empty = bars + 10;  // [2]
-  uint64_t* done = bars + 12;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* raw_full = bars + 8;    // [kC1NR]
+  uint64_t* raw_empty = bars + 12;  // [kC1NR]
+  uint64_t* done = bars + 16;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = args.nb * 400;
   const int num_tiles = (M + 127) / 128;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
+    for (int a = 0; a < kC1NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -290,31 +291,34 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
   const uint32_t tmem_base = *tmem_slot;
 
   if (t_begin < t_end) {
-    if (warp >= 5) {
+    if (warp == 5 + kC1ProdWarps) {
+      if (lane == 0) {
+        uint32_t j = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++j) {
+          const uint32_t buf = j % kC1NR;
+          mbar_wait(raw_empty + buf, ((j / kC1NR) & 1) ^ 1);
+          C1Seg s0, s1;
+          c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
+          c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
+          const uint32_t dy_bytes = (uint32_t)min(128, M - tile * 128) * 64u;
+          mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes + dy_bytes);
+          uint8_t* dst = sRaw + buf * kC1wRaw;
+          if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
+          if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
+          tma_bulk_g2s(dst + 2 * kC1SegBytes, args.dy + (int64_t)tile * 128 * 32, dy_bytes, raw_full + buf);
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 5) {
       const int pt = threadIdx.x - 160;
       const int c = pt & 7, row = pt >> 3;         // one row of each 32-row sub-stage per thread
-      auto issue_raw = [&](int tile, uint32_t j) {
-        const uint32_t buf = j & 1;
-        mbar_wait(raw_empty + buf, ((j >> 1) & 1) ^ 1);
-        C1Seg s0, s1;
-        c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
-        c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
-        const uint32_t dy_bytes = (uint32_t)min(128, M - tile * 128) * 64u;
-        mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes + dy_bytes);
-        uint8_t* dst = sRaw + buf * kC1wRaw;
-        if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
-        if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
-        tma_bulk_g2s(dst + 2 * kC1SegBytes, args.dy + (int64_t)tile * 128 * 32, dy_bytes, raw_full + buf);
-      };
-      if (pt == 0) issue_raw(t_begin, 0);
       uint32_t j = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++j) {
-        const uint32_t buf = j & 1;
-        if (pt == 0 && tile + 1 < t_end) issue_raw(tile + 1, j + 1);
+        const uint32_t buf = j % kC1NR;
         int rb[4];
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) rb[ss] = c1_row_base(tile * 128, ss * 32 + row, args.nb);
-        mbar_wait(raw_full + buf, (j >> 1) & 1);
+        mbar_wait(raw_full + buf, (j / kC1NR) & 1);
         const uint32_t raw_addr = smem_u32(sRaw + buf * kC1wRaw);
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) {

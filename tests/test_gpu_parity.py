@@ -376,3 +376,57 @@ def test_ppo_optimize_vs_reference_2rank_golden(golden_dir, precision, tag):
         got = np.array([algo.last_epoch_metrics[ep][n] for n in algos.ppo.METRIC_NAMES])
         np.testing.assert_allclose(got[:4], em[ep][:4], rtol=5e-3, atol=5e-5)
         assert abs(got[4] - em[ep][4]) <= 2.0 / T + 1e-6
+
+
+# ---- RND predictor ---------------------------------------------------------------------------------------
+def test_rnd_learn_vs_reference_golden(golden_dir):
+    """Predictor loss, per-sample intrinsic reward and student gradients against the UNMODIFIED
+    reference networks (tests/golden/rnd.npz) and the oracle, fp32 engine: rel-L2 <= 2e-4."""
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
+    g = np.load(os.path.join(golden_dir, 'rnd.npz'))
+    items, obs_u8 = ro.rnd_fixture_inputs()
+    rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=32, max_batch=16)
+    teacher, student = ro.init_net(False, 100), ro.init_net(True, 200)
+    rnd.load({k: tc.from_numpy(v) for k, v in teacher.items()}, {k: tc.from_numpy(v) for k, v in student.items()})
+    rnd.observe(cu(items))
+    rnd._sync_normalizers_global(); rnd._sync_normalizers_local()
+    nz = ro.Normalizer([84, 84, 1])
+    for it in items:
+        nz.update(it)
+    loss_ref, per_ref, y_ref, yh_ref, grads_ref = ro.rnd_learn_loss_and_grads(teacher, student, nz, obs_u8)
+    np.testing.assert_allclose(loss_ref, float(g['loss']), rtol=1e-5)
+    obs = cu(obs_u8)
+    err = rnd.intrinsic_reward(obs).cpu().numpy()
+    np.testing.assert_allclose(err, g['per'], rtol=2e-4)
+    before = rnd.student_params.clone()
+    rows = tc.arange(obs_u8.shape[0], device=dev(), dtype=tc.int64)
+    loss = rnd.learn_rows(obs, rows)
+    np.testing.assert_allclose(float(loss.item()), float(g['loss']), rtol=2e-4)
+    gv = rnd.student_views(rnd.student_grads)
+    for k in ro.STUDENT_KEYS:
+        assert rel_l2(gv[k].cpu().numpy(), grads_ref[k]) < 2e-4, k
+    # one Adam step moved the student (lr 1e-4, first step = lr * sign)
+    delta = (rnd.student_params - before).abs().max().item()
+    assert 0.5e-4 < delta < 1.5e-4
+
+
+def test_rnd_learn_wrapper_semantics():
+    """learn(mb): row dropping by world/32 (random_network_distillation.py:203-207), no update before
+    non_learning_steps, normaliser sync aliasing."""
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
+    from pytorch_drl_b200.utils import MinibatchView
+    rs = np.random.RandomState(0)
+    obs = cu(rs.randint(0, 256, size=(1, 16, 84, 84, 4), dtype=np.uint8))
+    rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=8, non_learning_steps=4, max_batch=16)
+    rnd.observe(cu(rs.uniform(0, 1, size=(3, 84, 84, 1)).astype(F32)))
+    mb = MinibatchView({'observations': obs}, tc.arange(16, device=dev(), dtype=tc.int64))
+    p0 = rnd.student_params.clone()
+    rnd.learn(mb)                                   # steps (3) < non_learning_steps (4): no predictor update
+    assert tc.equal(rnd.student_params, p0) and rnd._synced_normalizer.steps == 3.0
+    assert rnd._unsynced_normalizer.moment1 is rnd._synced_normalizer.moment1      # aliasing quirk reproduced
+    rnd.observe(cu(rs.uniform(0, 1, size=(2, 84, 84, 1)).astype(F32)))
+    rnd.learn(mb)                                   # the check reads the SYNCED steps (still 3, :224): no update yet
+    assert tc.equal(rnd.student_params, p0) and rnd._synced_normalizer.steps == 5.0
+    np.random.seed(0)
+    rnd.learn(mb)                                   # now 5 >= 4: keeps int(8/32 * 16) = 4 rows and updates
+    assert not tc.equal(rnd.student_params, p0) and rnd.adam_steps == 1
