@@ -93,8 +93,8 @@ __device__ __forceinline__ uint4 u8x8_to_bf16x8(uint2 w) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kC1ProdWarps = 8;
 constexpr int kC1Threads = 32 * (5 + kC1ProdWarps + 1);   // 4 epilogue + 1 MMA + 8 converters + 1 TMA warp
-constexpr int kC1NR = 4;                                    // raw staging buffers (tiles in flight)
-constexpr int kC1FwdSmem = 16384 /*B*/ + 4 * 16384 /*A*/ + kC1NR * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
+constexpr int kC1NR = 3;                                    // raw staging buffers (tiles in flight)
+constexpr int kC1FwdSmem = 16384 /*B*/ + 2 * 65536 /*A: two whole tiles*/ + kC1NR * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
 
 __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Args args) {
   using namespace umma;
@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;
   uint8_t* sA = smem + 16384;
-  uint8_t* sRaw = smem + 16384 + 4 * 16384;
+  uint8_t* sRaw = smem + 16384 + 2 * 65536;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1NR * 2 * kC1SegBytes);
-  uint64_t* full = bars;            // [4] one per k-block tile
-  uint64_t* empty = bars + 4;       // [4]
+  uint64_t* full = bars;            // [2] one per A buffer (a whole 128 x 256 tile = 4 k-block images)
+  uint64_t* empty = bars + 4;       // [2]
   uint64_t* tfull = bars + 8;       // [2]
   uint64_t* tempty = bars + 10;     // [2]
   uint64_t* raw_full = bars + 12;   // [kC1NR]
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
   const int num_tiles = (M + 127) / 128;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
     for (int a = 0; a < kC1NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
     mbar_init(b_full, 1);
@@ -162,19 +162,20 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
       for (int q = 0; q < RPT; ++q) rb[q] = c1_row_base(tile * 128, q * (NP / 8) + rg, args.nb);
       mbar_wait(raw_full + buf, (j / kC1NR) & 1);
       const uint32_t raw_addr = smem_u32(sRaw + buf * 2 * kC1SegBytes);
+      const uint32_t ab = j & 1;
+      mbar_wait(empty + ab, ((j >> 1) & 1) ^ 1);
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        mbar_wait(empty + kb, (j & 1) ^ 1);
-        const uint32_t a_addr = smem_u32(sA + kb * 16384);
+        const uint32_t a_addr = smem_u32(sA + ab * 65536 + kb * 16384);
         const uint32_t koff = (uint32_t)((2 * kb + (c >> 2)) * kC1RowBytes + (c & 3) * 8);
         uint2 v[RPT];
 #pragma unroll
         for (int q = 0; q < RPT; ++q) v[q] = rb[q] >= 0 ? lds_v2(raw_addr + rb[q] + koff) : make_uint2(0u, 0u);
 #pragma unroll
         for (int q = 0; q < RPT; ++q) st_shared_v4(a_addr + swz_off<128>(q * (NP / 8) + rg, c), u8x8_to_f16x8(v[q]));
-        fence_proxy_async_smem();
-        mbar_arrive(full + kb);
       }
+      fence_proxy_async_smem();
+      mbar_arrive(full + ab);
       mbar_arrive(raw_empty + buf);
     }
   } else if (warp == 4) {
@@ -183,20 +184,19 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
       mbar_wait(b_full, 0);
       uint32_t j = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-        const uint32_t acc = j & 1;
+        const uint32_t acc = j & 1, ab = j & 1;
         mbar_wait(tempty + acc, ((j >> 1) & 1) ^ 1);
+        mbar_wait(full + ab, (j >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(full + kb, j & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + kb * 16384), b_addr = smem_u32(sB + kb * 4096);
+          const uint32_t a_addr = smem_u32(sA + ab * 65536 + kb * 16384), b_addr = smem_u32(sB + kb * 4096);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             mma_f16_ss(tmem_base + acc * 32, make_smem_desc(a_addr + k * 32, 0, 1024, LAYOUT_SW128),
                        make_smem_desc(b_addr + k * 32, 0, 1024, LAYOUT_SW128), idesc, (kb | k) != 0);
-          mma_commit(empty + kb);
         }
+        mma_commit(empty + ab);
         mma_commit(tfull + acc);
       }
     }
@@ -249,7 +249,8 @@ namespace drl {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kC1wStage = 4 * 4096 + 2048;                 // 18 KB
 constexpr int kC1wRaw = 2 * kC1SegBytes + 8192;            // frames (2 segments) + dY rows
-constexpr int kC1WgradSmem = 4 * kC1wStage + kC1NR * kC1wRaw + 256 + 1024;
+constexpr int kC1wNR = 2;                                   // raw buffers of the wgrad kernel
+constexpr int kC1WgradSmem = 8 * kC1wStage + kC1wNR * kC1wRaw + 256 + 1024;
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
   uint4 v;
@@ -262,13 +263,13 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
   constexpr int NP = 32 * kC1ProdWarps;          // 256 producer threads
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sSt = smem;                                   // 4 sub-stages
-  uint8_t* sRaw = smem + 4 * kC1wStage;                  // kC1NR raw buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1NR * kC1wRaw);
-  uint64_t* full = bars;            // [4]
-  uint64_t* empty = bars + 4;       // [4]
-  uint64_t* raw_full = bars + 8;    // [kC1NR]
-  uint64_t* raw_empty = bars + 12;  // [kC1NR]
+  uint8_t* sSt = smem;                                   // 2 tiles x 4 sub-stages
+  uint8_t* sRaw = smem + 8 * kC1wStage;                  // kC1wNR raw buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1wNR * kC1wRaw);
+  uint64_t* full = bars;            // [2] one per tile buffer
+  uint64_t* empty = bars + 4;       // [2]
+  uint64_t* raw_full = bars + 8;    // [kC1wNR]
+  uint64_t* raw_empty = bars + 12;  // [kC1wNR]
   uint64_t* done = bars + 16;       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -279,8 +280,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
   const int t_begin = blockIdx.x * per, t_end = min(num_tiles, t_begin + per);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
-    for (int a = 0; a < kC1NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
+    for (int s = 0; s < 2; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
+    for (int a = 0; a < kC1wNR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -295,8 +296,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
       if (lane == 0) {
         uint32_t j = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++j) {
-          const uint32_t buf = j % kC1NR;
-          mbar_wait(raw_empty + buf, ((j / kC1NR) & 1) ^ 1);
+          const uint32_t buf = j % kC1wNR;
+          mbar_wait(raw_empty + buf, ((j / kC1wNR) & 1) ^ 1);
           C1Seg s0, s1;
           c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
           c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
@@ -314,16 +315,17 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
       const int c = pt & 7, row = pt >> 3;         // one row of each 32-row sub-stage per thread
       uint32_t j = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++j) {
-        const uint32_t buf = j % kC1NR;
+        const uint32_t buf = j % kC1wNR;
         int rb[4];
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) rb[ss] = c1_row_base(tile * 128, ss * 32 + row, args.nb);
-        mbar_wait(raw_full + buf, (j / kC1NR) & 1);
+        mbar_wait(raw_full + buf, (j / kC1wNR) & 1);
         const uint32_t raw_addr = smem_u32(sRaw + buf * kC1wRaw);
+        const uint32_t tb = j & 1;
+        mbar_wait(empty + tb, ((j >> 1) & 1) ^ 1);
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) {
-          mbar_wait(empty + ss, (j & 1) ^ 1);
-          const uint32_t st_addr = smem_u32(sSt + ss * kC1wStage);
+          const uint32_t st_addr = smem_u32(sSt + (tb * 4 + ss) * kC1wStage);
           uint2 v[4];
 #pragma unroll
           for (int a = 0; a < 4; ++a)
@@ -334,9 +336,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
 #pragma unroll
           for (int a = 0; a < 4; ++a) st_shared_v4(st_addr + a * 4096 + swz_off<128>(row, c), u8x8_to_bf16x8(v[a]));
           if (c < 4) st_shared_v4(st_addr + 4 * 4096 + swz_off<64>(row, c), dyv);
-          fence_proxy_async_smem();
-          mbar_arrive(full + ss);
         }
+        fence_proxy_async_smem();
+        mbar_arrive(full + tb);
         mbar_arrive(raw_empty + buf);
       }
     } else if (warp == 4) {
@@ -344,11 +346,12 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, 32, 1, 1);   // bf16, MN-major A and B
         uint32_t j = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++j) {
+          const uint32_t tb = j & 1;
+          mbar_wait(full + tb, (j >> 1) & 1);
+          tc_fence_after();
 #pragma unroll
           for (int ss = 0; ss < 4; ++ss) {
-            mbar_wait(full + ss, j & 1);
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sSt + ss * kC1wStage), d_addr = p_addr + 4 * 4096;
+            const uint32_t p_addr = smem_u32(sSt + (tb * 4 + ss) * kC1wStage), d_addr = p_addr + 4 * 4096;
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
@@ -357,8 +360,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
                            make_smem_desc(p_addr + (2 * mb) * 4096 + k * 16 * 128, 4096, 1024, LAYOUT_SW128),
                            make_smem_desc(d_addr + k * 16 * 64, 0, 512, LAYOUT_SW64), idesc,
                            (j > 0 || ss > 0 || k > 0) ? 1u : 0u);
-            mma_commit(empty + ss);
           }
+          mma_commit(empty + tb);
         }
         mma_commit(done);
       }

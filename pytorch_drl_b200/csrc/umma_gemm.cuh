@@ -110,23 +110,39 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
     constexpr int ES = SRC == SRC_U8 ? 1 : 2;  // source element bytes
     constexpr uint32_t LAG = 2;                // async-copy k-blocks in flight behind the newest one
     uint32_t it = 0;                           // k-block iteration counter (across tiles)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int64_t base[8];       // byte offset of the (tap 0,0) source pixel of each of my 8 rows; INT64_MIN: row invalid
-      int py0[8], px0[8];    // source pixel coords of tap (0,0) (only needed when pad > 0)
+    // loop-invariant pieces of the addressing: swizzled destination of my 8 rows, element->byte factors
+    uint32_t dst_off[8];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int m = tile * 128 + p * 16 + rg;
-        if (m < args.M) {
-          const int b = m / args.P, rem = m - b * args.P;
+    for (int p = 0; p < 8; ++p) dst_off[p] = swz_off<128>(p * 16 + rg, c);
+    const int row_bytes = args.W * args.C * ES;           // one source map row
+    const int c_shift = 31 - __clz(args.C);               // C is a power of two (32 / 64 / 512)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // tap-(0,0) source pointer of each of my 8 rows; one div/mod pair per tile, the rest incremental
+      const uint8_t* rptr[8];
+      int py0[8], px0[8];
+      uint32_t valid = 0;
+      {
+        const int m0 = tile * 128 + rg;
+        int b = m0 / args.P, rem = m0 - b * args.P;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int m = m0 + p * 16;
           const int oy = rem / args.OW, ox = rem - oy * args.OW;
-          const int64_t srow = args.row_idx ? args.row_idx[b] : (int64_t)b;
           py0[p] = oy * args.stride - args.pad;
           px0[p] = ox * args.stride - args.pad;
-          base[p] = ((srow * args.H + py0[p]) * (int64_t)args.W + px0[p]) * args.C * ES;
-        } else {
-          base[p] = INT64_MIN; py0[p] = 0; px0[p] = 0;
+          if (m < args.M) {
+            const int64_t srow = args.row_idx ? args.row_idx[b] : (int64_t)b;
+            rptr[p] = reinterpret_cast<const uint8_t*>(args.src) +
+                      ((srow * args.H + py0[p]) * (int64_t)args.W + px0[p]) * (args.C * ES);
+            valid |= 1u << p;
+          } else {
+            rptr[p] = reinterpret_cast<const uint8_t*>(args.src);
+          }
+          rem += 16;
+          while (rem >= args.P) { rem -= args.P; ++b; }
         }
       }
+      int ty = 0, kbx = 0;
       for (int kb = 0; kb < args.KB; ++kb, ++it) {
         const uint32_t stage = it % S, phase = (it / S) & 1;
         mbar_wait(empty + stage, phase ^ 1);
@@ -137,30 +153,31 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
         const uint32_t a_addr = smem_u32(sA + stage * L::kABytes);
         if (SRC == SRC_U8) {
           // k-block = 2 kernel rows x (8 px x 4 ch): chunk c -> ky = 2kb + (c>>2), 2 pixels at (c&3)*2
-          const int ky = 2 * kb + (c >> 2);
-          const int64_t koff = (int64_t)ky * args.W * args.C + (c & 3) * 8;
+          const int koff = (2 * kb + (c >> 2)) * row_bytes + (c & 3) * 8;
           uint2 v[8];
 #pragma unroll
-          for (int p = 0; p < 8; ++p)
-            v[p] = base[p] != INT64_MIN ? ldg_v2(reinterpret_cast<const uint8_t*>(args.src) + base[p] + koff) : make_uint2(0u, 0u);
+          for (int p = 0; p < 8; ++p) v[p] = (valid >> p) & 1u ? ldg_v2(rptr[p] + koff) : make_uint2(0u, 0u);
 #pragma unroll
-          for (int p = 0; p < 8; ++p) st_shared_v4(a_addr + swz_off<128>(p * 16 + rg, c), u8x8_to_f16x8(v[p]));
+          for (int p = 0; p < 8; ++p) st_shared_v4(a_addr + dst_off[p], u8x8_to_f16x8(v[p]));
           fence_proxy_async_smem();
           mbar_arrive(full + stage);
         } else {
-          const int ty = kb / args.KBX, kbx = kb - ty * args.KBX;
           const int eoff = kbx * 64 + c * 8;                      // element offset inside the tap row
-          const int64_t koff = ((int64_t)ty * args.W * args.C + eoff) * ES;
-          const int tx = eoff / args.C;                           // pixel offset (bounds check only)
+          const int koff = ty * row_bytes + eoff * ES;
+          if (args.pad > 0) {
+            const int tx = eoff >> c_shift;                       // pixel offset of this chunk
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            bool ok = base[p] != INT64_MIN;
-            if (args.pad > 0) {
+            for (int p = 0; p < 8; ++p) {
               const int y = py0[p] + ty, x = px0[p] + tx;
-              ok = ok && y >= 0 && y < args.H && x >= 0 && x < args.W;
+              const bool ok = ((valid >> p) & 1u) && y >= 0 && y < args.H && x >= 0 && x < args.W;
+              cp_async_16(a_addr + dst_off[p], ok ? rptr[p] + koff : reinterpret_cast<const uint8_t*>(args.src), ok ? 16u : 0u);
             }
-            const uint8_t* g = reinterpret_cast<const uint8_t*>(args.src) + (ok ? base[p] + koff : 0);
-            cp_async_16(a_addr + swz_off<128>(p * 16 + rg, c), g, ok ? 16u : 0u);
+          } else {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+              const bool ok = (valid >> p) & 1u;
+              cp_async_16(a_addr + dst_off[p], ok ? rptr[p] + koff : rptr[p], ok ? 16u : 0u);
+            }
           }
           cp_async_commit();
           if (it >= LAG) {
@@ -168,6 +185,7 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
             fence_proxy_async_smem();
             mbar_arrive(full + ((it - LAG) % S));
           }
+          if (++kbx == args.KBX) { kbx = 0; ++ty; }
         }
       }
     }
@@ -328,7 +346,7 @@ struct WgradCfg {
 };
 
 template <int NT, int SRC, int MB>     // MB: accumulator blocks (128 kp each) per CTA
-__global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args) {
+__global__ void __launch_bounds__(288, (MB == 1 ? 2 : 1)) wgrad_gemm_kernel(const WgradArgs args) {
   using namespace umma;
   using Cf = WgradCfg<NT>;
   constexpr int S = Cf::kStages;
@@ -376,44 +394,65 @@ __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args
       const int c = pt & 7, slot = pt >> 3;      // rows slot*2, slot*2+1 of the stage
       constexpr int ES = SRC == SRC_U8 ? 1 : 2;
       constexpr uint32_t LAG = 2;
+      // loop invariants: per-atom source offset / validity, swizzled destinations of my two rows
+      int aoff[NA];
+      uint32_t avalid = 0;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int atom = atom0 + a;
+        if (atom < args.n_atoms_valid) avalid |= 1u << a;
+        if (SRC == SRC_U8) {
+          aoff[a] = (2 * atom + (c >> 2)) * args.W * args.C + (c & 3) * 8;
+        } else {
+          const int ty = atom / args.KBX, kbx = atom - ty * args.KBX;
+          aoff[a] = (ty * args.W * args.C + kbx * 64 + c * 8) * ES;
+        }
+      }
+      const uint32_t sw128[2] = {swz_off<128>(slot * 2, c), swz_off<128>(slot * 2 + 1, c)};
+      const uint32_t sw64[2] = {swz_off<64>(slot * 2, c & 3), swz_off<64>(slot * 2 + 1, c & 3)};
+      // (sample, position) of my first row at the first stage; advanced incrementally afterwards
+      int b_cur, rem_cur;
+      {
+        const int m0 = st_begin * ROWS + slot * 2;
+        b_cur = m0 / args.P;
+        rem_cur = m0 - b_cur * args.P;
+      }
+      const int64_t pix_bytes = (int64_t)args.C * ES;
       uint32_t it = 0;
       for (int st = st_begin; st < st_end; ++st, ++it) {
         const uint32_t stage = it & (S - 1), phase = (it / S) & 1;
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* base_s = smem + stage * STAGE;
         const uint32_t p_addr = smem_u32(base_s), d_addr = smem_u32(base_s + P_BYTES);
+        int b = b_cur, rem = rem_cur;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int r = slot * 2 + i;
-          const int m = st * ROWS + r;
+          const int m = st * ROWS + slot * 2 + i;
           const bool live = m < args.M;
-          int64_t base = 0;
+          const uint8_t* rptr = reinterpret_cast<const uint8_t*>(args.src);
           if (live) {
-            const int b = m / args.P, rem = m - b * args.P;
             const int oy = rem / args.OW, ox = rem - oy * args.OW;
             const int64_t srow = args.row_idx ? args.row_idx[b] : (int64_t)b;
-            base = ((srow * args.H + oy * args.stride) * (int64_t)args.W + ox * args.stride) * args.C * ES;
+            rptr += ((srow * args.H + oy * args.stride) * (int64_t)args.W + ox * args.stride) * pix_bytes;
           }
           // dY tile row (bf16, always an async copy)
+          const __nv_bfloat16* dyp = args.dy + (live ? (int64_t)m * args.dy_ld + n0 + c * 8 : 0);
           if (NT >= 64) {
 #pragma unroll
             for (int a = 0; a < Cf::kDyAtoms; ++a)
-              cp_async_16(d_addr + a * Cf::kDyAtomBytes + swz_off<128>(r, c),
-                          args.dy + (live ? (int64_t)m * args.dy_ld + n0 + a * 64 + c * 8 : 0), live ? 16u : 0u);
+              cp_async_16(d_addr + a * Cf::kDyAtomBytes + sw128[i], dyp + (live ? a * 64 : 0), live ? 16u : 0u);
           } else if (c < 4) {
-            cp_async_16(d_addr + swz_off<64>(r, c), args.dy + (live ? (int64_t)m * args.dy_ld + n0 + c * 8 : 0), live ? 16u : 0u);
+            cp_async_16(d_addr + sw64[i], dyp, live ? 16u : 0u);
           }
           // patch row: atoms atom0 .. atom0+NA-1
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
-            const int atom = atom0 + a;
-            const bool ok = live && atom < args.n_atoms_valid;
-            const uint32_t dst = p_addr + a * Cf::kAtomBytes + swz_off<128>(r, c);
+            const bool ok = live && ((avalid >> a) & 1u);
+            const uint32_t dst = p_addr + a * Cf::kAtomBytes + sw128[i];
             if (SRC == SRC_U8) {
               uint4 v = make_uint4(0u, 0u, 0u, 0u);
               if (ok) {
-                const int ky = 2 * atom + (c >> 2);
-                const uint2 w = ldg_v2(reinterpret_cast<const uint8_t*>(args.src) + base + (int64_t)ky * args.W * args.C + (c & 3) * 8);
+                const uint2 w = ldg_v2(rptr + aoff[a]);
                 v.x = pack_bf16x2((float)(w.x & 0xffu), (float)((w.x >> 8) & 0xffu));
                 v.y = pack_bf16x2((float)((w.x >> 16) & 0xffu), (float)(w.x >> 24));
                 v.z = pack_bf16x2((float)(w.y & 0xffu), (float)((w.y >> 8) & 0xffu));
@@ -421,12 +460,10 @@ __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args
               }
               st_shared_v4(dst, v);
             } else {
-              const int ty = atom / args.KBX, kbx = atom - ty * args.KBX;
-              const uint8_t* g = reinterpret_cast<const uint8_t*>(args.src) +
-                                 (ok ? base + ((int64_t)ty * args.W * args.C + kbx * 64 + c * 8) * ES : 0);
-              cp_async_16(dst, g, ok ? 16u : 0u);
+              cp_async_16(dst, ok ? rptr + aoff[a] : rptr, ok ? 16u : 0u);
             }
           }
+          if (++rem == args.P) { rem = 0; ++b; }
         }
         cp_async_commit();
         if (it >= LAG) {
@@ -434,6 +471,8 @@ __global__ void __launch_bounds__(288, 1) wgrad_gemm_kernel(const WgradArgs args
           fence_proxy_async_smem();
           mbar_arrive(full + ((it - LAG) & (S - 1)));
         }
+        rem_cur += ROWS;
+        while (rem_cur >= args.P) { rem_cur -= args.P; ++b_cur; }
       }
       cp_async_wait<0>();
       fence_proxy_async_smem();
