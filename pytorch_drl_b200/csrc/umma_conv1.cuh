@@ -20,7 +20,7 @@ struct Conv1Args {
   const int64_t* row_idx;    // [nb] or nullptr
   int nb;
   const void* bpack;         // fwd: fp16 [4][32 x 64] swizzled tile images (16 KB)
-  const float* bias;         // fwd: [32]
+  const float* bias;         // fwd: [32] EFFECTIVE bias = b - 1024 * scale * sum_k fp16(W[n][k]) (operands hold 1024 + pixel)
   float scale;               // float32(1/255)
   __nv_bfloat16* out;        // fwd: act1 [nb*400, 32]
   const __nv_bfloat16* dy;   // wgrad: dY1 [nb*400, 32]
@@ -31,17 +31,29 @@ constexpr int kC1SegBytes = 12288;
 constexpr int kC1FrameBytes = 84 * 84 * 4;
 constexpr int kC1RowBytes = 84 * 4;
 
+// p / 400 for 0 <= p < 2^24 without an integer division (float reciprocal + one-step correction)
+__device__ __forceinline__ int c1_div400(int p, int& rem) {
+  int q = (int)((float)p * 0.0025f);
+  rem = p - q * 400;
+  if (rem < 0) { rem += 400; --q; }
+  if (rem >= 400) { rem -= 400; ++q; }
+  return q;
+}
+// x / 20 for 0 <= x < 400 (exact: 3277 = ceil(2^16 / 20))
+__device__ __forceinline__ int c1_div20(int x) { return (x * 3277) >> 16; }
+
 struct C1Seg { int rows_begin; int oy_a; uint32_t bytes; int64_t src_off; bool valid; };
 
 // Segment s (0/1) of the tile starting at flattened position p0.
 __device__ __forceinline__ void c1_segment(int p0, int s, int nb, const int64_t* row_idx, C1Seg& g) {
-  const int b0 = p0 / 400, r0 = p0 - b0 * 400;
+  int r0;
+  const int b0 = c1_div400(p0, r0);
   int b, ra, rb;
   if (s == 0) { b = b0; ra = r0; rb = min(399, r0 + 127); }
   else { b = b0 + 1; ra = 0; rb = r0 + 127 - 400; }
   g.valid = b < nb && rb >= ra;
   if (!g.valid) { g.bytes = 0; g.oy_a = 0; g.src_off = 0; g.rows_begin = 0; return; }
-  const int oy_a = ra / 20, oy_b = rb / 20;
+  const int oy_a = c1_div20(ra), oy_b = c1_div20(rb);
   g.oy_a = oy_a;
   g.bytes = (uint32_t)(((oy_b - oy_a) * 4 + 8) * kC1RowBytes);
   const int64_t srow = row_idx ? row_idx[b] : (int64_t)b;
@@ -51,14 +63,12 @@ __device__ __forceinline__ void c1_segment(int p0, int s, int nb, const int64_t*
 // smem byte offset (inside the raw staging buffer pair of one tile) of the tap-(0,0) pixel of tile
 // row r, or -1 if the row lies past the end of the batch.
 __device__ __forceinline__ int c1_row_base(int p0, int r, int nb) {
-  const int p = p0 + r;
-  const int b0 = p0 / 400;
-  const int b = p / 400;
+  int rem0, rem;
+  const int b0 = c1_div400(p0, rem0);
+  const int b = c1_div400(p0 + r, rem);
   if (b >= nb) return -1;
-  const int rem = p - b * 400;
-  const int oy = rem / 20, ox = rem - oy * 20;
-  int oy_a;
-  if (b == b0) oy_a = (p0 - b0 * 400) / 20; else oy_a = 0;
+  const int oy = c1_div20(rem), ox = rem - oy * 20;
+  const int oy_a = b == b0 ? c1_div20(rem0) : 0;
   return (b - b0) * kC1SegBytes + (oy - oy_a) * 4 * kC1RowBytes + ox * 16;
 }
 
@@ -66,6 +76,15 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
   uint2 v;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
   return v;
+}
+
+// 8 uint8 -> 8 fp16 holding 1024 + b (bytes become the mantissa of 0x6400 = 1024.0): one PRMT per pair.
+// The constant 1024 * sum_k W[n][k] this adds to every accumulator is folded into the bias
+// (conv1_bias_eff_kernel), so the forward conversion costs 4 instructions per 8 pixels.
+__device__ __forceinline__ uint4 u8x8_to_f16x8_biased(uint2 w) {
+  const uint32_t magic = 0x64006400u;
+  return make_uint4(__byte_perm(w.x, magic, 0x7170), __byte_perm(w.x, magic, 0x7372),
+                    __byte_perm(w.y, magic, 0x7170), __byte_perm(w.y, magic, 0x7372));
 }
 
 // 8 uint8 -> 8 bf16 (exact: 0..255 fit the 8-bit significand): fp32 magic number then truncation.
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
 #pragma unroll
         for (int q = 0; q < RPT; ++q) v[q] = rb[q] >= 0 ? lds_v2(raw_addr + rb[q] + koff) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) st_shared_v4(a_addr + swz_off<128>(q * (NP / 8) + rg, c), u8x8_to_f16x8(v[q]));
+        for (int q = 0; q < RPT; ++q) st_shared_v4(a_addr + swz_off<128>(q * (NP / 8) + rg, c), u8x8_to_f16x8_biased(v[q]));
       }
       fence_proxy_async_smem();
       mbar_arrive(full + ab);
@@ -181,6 +200,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
   } else if (warp == 4) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(0u, 128, 32, 0, 0);     // fp16 operands
+      constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
+      const uint32_t a_lo0 = desc_lo(smem_u32(sA), 0), b_lo0 = desc_lo(smem_u32(sB), 0);
       mbar_wait(b_full, 0);
       uint32_t j = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
@@ -188,13 +209,16 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
         mbar_wait(tempty + acc, ((j >> 1) & 1) ^ 1);
         mbar_wait(full + ab, (j >> 1) & 1);
         tc_fence_after();
+        const uint32_t a_lo = a_lo0 + ab * (65536 >> 4);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-          const uint32_t a_addr = smem_u32(sA + ab * 65536 + kb * 16384), b_addr = smem_u32(sB + kb * 4096);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_f16_ss(tmem_base + acc * 32, make_smem_desc(a_addr + k * 32, 0, 1024, LAYOUT_SW128),
-                       make_smem_desc(b_addr + k * 32, 0, 1024, LAYOUT_SW128), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            if (kb == 0 && k == 0)
+              mma_f16_lohi<false>(tmem_base + acc * 32, a_lo, hi, b_lo0, hi, idesc);
+            else
+              mma_f16_lohi<true>(tmem_base + acc * 32, a_lo + kb * (16384 >> 4) + k * 2, hi, b_lo0 + kb * (4096 >> 4) + k * 2, hi, idesc);
+          }
         }
         mma_commit(empty + ab);
         mma_commit(tfull + acc);
@@ -344,6 +368,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
     } else if (warp == 4) {
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, 32, 1, 1);   // bf16, MN-major A and B
+        constexpr uint32_t a_hi = desc_hi(1024, LAYOUT_SW128), b_hi = desc_hi(512, LAYOUT_SW64);
+        const uint32_t st_lo0 = desc_lo(smem_u32(sSt), 0);
         uint32_t j = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++j) {
           const uint32_t tb = j & 1;
@@ -351,15 +377,20 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
           tc_fence_after();
 #pragma unroll
           for (int ss = 0; ss < 4; ++ss) {
-            const uint32_t p_addr = smem_u32(sSt + (tb * 4 + ss) * kC1wStage), d_addr = p_addr + 4 * 4096;
+            const uint32_t p_lo = st_lo0 + (tb * 4 + ss) * (kC1wStage >> 4), d_lo = p_lo + ((4 * 4096) >> 4);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                mma_f16_ss(tmem_base + mb * 32,
-                           make_smem_desc(p_addr + (2 * mb) * 4096 + k * 16 * 128, 4096, 1024, LAYOUT_SW128),
-                           make_smem_desc(d_addr + k * 16 * 64, 0, 512, LAYOUT_SW64), idesc,
-                           (j > 0 || ss > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 2; ++k) {
+                const uint32_t al = (p_lo + mb * ((2 * 4096) >> 4) + k * ((16 * 128) >> 4)) | (((4096u >> 4) & 0x3FFFu) << 16);
+                const uint32_t bl = d_lo + k * ((16 * 64) >> 4);
+                if (ss == 0 && k == 0) {
+                  if (j == 0) mma_f16_lohi<false>(tmem_base + mb * 32, al, a_hi, bl, b_hi, idesc);
+                  else mma_f16_lohi<true>(tmem_base + mb * 32, al, a_hi, bl, b_hi, idesc);
+                } else {
+                  mma_f16_lohi<true>(tmem_base + mb * 32, al, a_hi, bl, b_hi, idesc);
+                }
+              }
           }
           mma_commit(empty + tb);
         }

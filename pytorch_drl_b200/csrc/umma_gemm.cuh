@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(SRC == SRC_U8 ? 0u : 1u, 128, N, 0, 0);
+      constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
+      const uint32_t a_lo0 = desc_lo(smem_u32(sA), 0), b_lo0 = desc_lo(smem_u32(sB), 0);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
@@ -207,14 +209,12 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
         for (int kb = 0; kb < args.KB; ++kb) {
           mbar_wait(full + stage, phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * L::kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * L::kBBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, 1024, LAYOUT_SW128);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, 1024, LAYOUT_SW128);
-            mma_f16_ss(tmem_d, ad, bd, idesc, (kb | k) != 0);
-          }
+          const uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = b_lo0 + stage * (L::kBBytes >> 4);
+          if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, hi, b_lo, hi, idesc);
+          else mma_f16_lohi<true>(tmem_d, a_lo, hi, b_lo, hi, idesc);
+          mma_f16_lohi<true>(tmem_d, a_lo + 2, hi, b_lo + 2, hi, idesc);
+          mma_f16_lohi<true>(tmem_d, a_lo + 4, hi, b_lo + 4, hi, idesc);
+          mma_f16_lohi<true>(tmem_d, a_lo + 6, hi, b_lo + 6, hi, idesc);
           mma_commit(empty + stage);
           if (kb == args.KB - 1) mma_commit(tfull + acc);
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -481,23 +481,34 @@ __global__ void __launch_bounds__(288, (MB == 1 ? 2 : 1)) wgrad_gemm_kernel(cons
       // ================= MMA issuer =================
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);       // bf16, both operands MN-major
+        constexpr uint32_t a_hi = desc_hi(1024, LAYOUT_SW128);
+        constexpr uint32_t b_hi = NT >= 64 ? desc_hi(1024, LAYOUT_SW128) : desc_hi(512, LAYOUT_SW64);
+        constexpr uint32_t b_kstep = NT >= 64 ? (16 * 128) >> 4 : (16 * 64) >> 4;
+        // A: 2 MN-atoms of 64 kp per accumulator block (LBO = atom stride), 16 reduction rows per MMA
+        const uint32_t a_lo0 = desc_lo(smem_u32(smem), Cf::kAtomBytes);
+        const uint32_t b_lo0 = desc_lo(smem_u32(smem) + P_BYTES, NT >= 64 ? Cf::kDyAtomBytes : 0);
         uint32_t it = 0;
         for (int st = st_begin; st < st_end; ++st, ++it) {
           const uint32_t stage = it & (S - 1), phase = (it / S) & 1;
           mbar_wait(full + stage, phase);
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + stage * STAGE), d_addr = p_addr + P_BYTES;
+          const uint32_t a_lo = a_lo0 + stage * (STAGE >> 4), b_lo = b_lo0 + stage * (STAGE >> 4);
+          if (it == 0) {
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) {
+            for (int mb = 0; mb < MB; ++mb) {
+              mma_f16_lohi<false>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4), a_hi, b_lo, b_hi, idesc);
 #pragma unroll
-            for (int k = 0; k < ROWS / 16; ++k) {
-              // A: 2 MN-atoms of 64 kp (LBO = atom stride), 16 reduction rows per MMA (128 B each)
-              const uint64_t ad = make_smem_desc(p_addr + (2 * mb) * Cf::kAtomBytes + k * 16 * 128, Cf::kAtomBytes, 1024, LAYOUT_SW128);
-              const uint64_t bd = NT >= 64
-                  ? make_smem_desc(d_addr + k * 16 * 128, Cf::kDyAtomBytes, 1024, LAYOUT_SW128)
-                  : make_smem_desc(d_addr + k * 16 * 64, 0, 512, LAYOUT_SW64);
-              mma_f16_ss(tmem_base + mb * NT, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 1; k < ROWS / 16; ++k)
+                mma_f16_lohi<true>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4) + k * ((16 * 128) >> 4), a_hi,
+                                   b_lo + k * b_kstep, b_hi, idesc);
             }
+          } else {
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+              for (int k = 0; k < ROWS / 16; ++k)
+                mma_f16_lohi<true>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4) + k * ((16 * 128) >> 4), a_hi,
+                                   b_lo + k * b_kstep, b_hi, idesc);
           }
           mma_commit(empty + stage);
         }

@@ -24,6 +24,7 @@ struct Bf16Engine {
   void* wff = nullptr;   // fc fwd      bf16 [4 n-tiles][49][128x64]
   void* wfd = nullptr;   // fc dgrad    bf16 [49 n-tiles][8][64x64]
   void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
+  float* b1eff = nullptr; // conv1 effective bias (see conv1_bias_eff_kernel)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
 };
 
@@ -90,6 +91,18 @@ static int pack_one(const float* w, void* out, int mode, int fp16, int variants,
   pack_tiles_kernel<<<blocks, 256, 0, st>>>(a);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
+}
+
+// conv1 forward feeds the tensor core fp16 operands holding 1024 + pixel; the resulting constant
+// 1024 * sum_k fp16(W1[n][k]) per output channel is removed through the bias:
+//   y = acc * s + b_eff,  b_eff[n] = b[n] - 1024 * s * sum_k fp16(W1[n][k])      (s = float32(1/255))
+__global__ void conv1_bias_eff_kernel(const float* __restrict__ w, const float* __restrict__ b, float scale,
+                                      float* __restrict__ out) {
+  const int n = threadIdx.x;
+  if (n >= 32) return;
+  double s = 0.0;
+  for (int k = 0; k < 256; ++k) s += (double)__half2float(__float2half_rn(w[n * 256 + k]));
+  out[n] = (float)((double)b[n] - 1024.0 * (double)scale * s);
 }
 
 // ---- bias gradients: column sums of a bf16 [R, C] matrix, C in {32, 64, 512} -----------------------------
@@ -164,13 +177,14 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&e->wfd, (size_t)49 * 8 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w3d, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
+  DRL_CUDA(cudaMalloc(&e->b1eff, 32 * sizeof(float)));
   return DRL_OK;
 }
 
 void bf16_free(drl_net* n) {
   Bf16Engine* e = n->bf16;
   if (!e) return;
-  cudaFree(e->w1f); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d);
+  cudaFree(e->w1f); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff);
   delete e;
   n->bf16 = nullptr;
 }
@@ -181,6 +195,8 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   const float* p = n->params;
   const int64_t* o = n->off;
   DRL_TRY(pack_one(p + o[0], e->w1f, PK_CONV_FWD, 1, 1, 4, 32, 4, 8, 8, 32, st));
+  conv1_bias_eff_kernel<<<1, 32, 0, st>>>(p + o[0], p + o[1], kInv255, e->b1eff);
+  DRL_LAUNCH_CHECK();
   DRL_TRY(pack_one(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64, st));
   DRL_TRY(pack_one(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64, st));
   DRL_TRY(pack_one(p + o[6], e->wff, PK_FC_FWD, 0, 4, 49, 128, 64, 7, 7, 512, st));
@@ -244,7 +260,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   {
     ProfileScope prof("conv1_fwd", st);
     Conv1Args a1{};
-    a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.bpack = e->w1f; a1.bias = p + o[1]; a1.scale = kInv255;
+    a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.bpack = e->w1f; a1.bias = e->b1eff; a1.scale = kInv255;
     a1.out = reinterpret_cast<__nv_bfloat16*>(n->act[0]);
     static bool configured = false;
     if (!configured) {
