@@ -11,6 +11,7 @@
 #include <new>
 #include "umma_gemm.cuh"
 #include "umma_conv1.cuh"
+#include "umma_tma_gemm.cuh"
 
 namespace drl {
 
@@ -21,8 +22,8 @@ struct Bf16Engine {
   void* w1f = nullptr;   // conv1 fwd   fp16 [4][32x64]
   void* w2f = nullptr;   // conv2 fwd   bf16 [8][64x64]
   void* w3f = nullptr;   // conv3 fwd   bf16 [9][64x64]
-  void* wff = nullptr;   // fc fwd      bf16 [4 n-tiles][49][128x64]
-  void* wfd = nullptr;   // fc dgrad    bf16 [49 n-tiles][8][64x64]
+  void* wff = nullptr;   // fc fwd      bf16 row-major [512][3136], k = (hw, c)  (TMA tensor map)
+  void* wfd = nullptr;   // fc dgrad    bf16 row-major [3136][512] = the transpose      (TMA tensor map)
   void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
   float* b1eff = nullptr; // conv1 effective bias (see conv1_bias_eff_kernel)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
@@ -30,6 +31,19 @@ struct Bf16Engine {
 
 // ---- packing -----------------------------------------------------------------------------------------
 enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4 };
+
+// fc weights as plain row-major bf16 matrices in the NHWC feature order k = hw*64 + c (TMA operands)
+__global__ void __launch_bounds__(256) pack_fc_plain_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                                            __nv_bfloat16* __restrict__ dgrad) {
+  const int total = 512 * 3136;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int n = e / 3136, k = e - n * 3136;
+    const int hw = k >> 6, c = k & 63;
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[(size_t)n * 3136 + c * 49 + hw]);
+    fwd[e] = v;
+    dgrad[(size_t)k * 512 + n] = v;
+  }
+}
 
 struct PackArgs {
   const float* w;      // reference-layout fp32 weights of the layer
@@ -173,8 +187,8 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&e->w1f, 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->w2f, 8 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w3f, 9 * 64 * 128));
-  DRL_CUDA(cudaMalloc(&e->wff, (size_t)4 * 49 * 128 * 128));
-  DRL_CUDA(cudaMalloc(&e->wfd, (size_t)49 * 8 * 64 * 128));
+  DRL_CUDA(cudaMalloc(&e->wff, (size_t)512 * 3136 * 2));
+  DRL_CUDA(cudaMalloc(&e->wfd, (size_t)3136 * 512 * 2));
   DRL_CUDA(cudaMalloc(&e->w3d, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->b1eff, 32 * sizeof(float)));
@@ -199,8 +213,8 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   DRL_LAUNCH_CHECK();
   DRL_TRY(pack_one(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64, st));
   DRL_TRY(pack_one(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64, st));
-  DRL_TRY(pack_one(p + o[6], e->wff, PK_FC_FWD, 0, 4, 49, 128, 64, 7, 7, 512, st));
-  DRL_TRY(pack_one(p + o[6], e->wfd, PK_FC_DGRAD, 0, 49, 8, 64, 64, 7, 7, 512, st));
+  pack_fc_plain_kernel<<<sm_count() * 4, 256, 0, st>>>(p + o[6], (__nv_bfloat16*)e->wff, (__nv_bfloat16*)e->wfd);
+  DRL_LAUNCH_CHECK();
   DRL_TRY(pack_one(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64, st));
   DRL_TRY(pack_one(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 1, 4, 128, 32, 4, 4, 64, st));
   return DRL_OK;
@@ -241,6 +255,56 @@ static int launch_wgrad(const char* site, const WgradArgs& a, int grid_x, int gr
   return DRL_OK;
 }
 
+// ---- TMA tensor maps (driver entry point resolved at run time: no link-time libcuda dependency) -----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major bf16 matrix [rows, cols] -> tiles of (64 columns = 128 B, box_rows rows), 128B swizzle, zero OOB fill
+static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return DRL_ERR_CUDA;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
+}
+
+template <int BN, int EPI>
+static int launch_tma_gemm(const char* site, const void* a, int M, int K, const void* b, int N_total, const TmaGemmArgs& args,
+                           cudaStream_t st) {
+  ProfileScope prof(site, st);
+  CUtensorMap ta, tb;
+  DRL_TRY(make_tmap_bf16(&ta, a, (uint64_t)M, (uint64_t)K, 128));
+  DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, BN));
+  auto kern = tma_gemm_kernel<BN, EPI>;
+  constexpr int smem = TmaGemmCfg<BN>::kSmem;
+  static bool configured = false;
+  if (!configured) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles = ((M + 127) / 128) * ((N_total + BN - 1) / BN);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, smem, st>>>(ta, tb, args);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
 static RowGatherArgs fwd_args(int nb, const void* src, const int64_t* row_idx, int P, int OW, int H, int W, int C,
                               int stride, int KB, int KBX, const void* bpack, void* out, const float* bias,
                               float scale, int Ntotal) {
@@ -275,10 +339,11 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
   RowGatherArgs a3 = fwd_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 9, 3, e->w3f, n->act[2], p + o[5], 1.f, 64);
   DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
-  RowGatherArgs a4 = fwd_args(nb, n->act[2], nullptr, 1, 1, 7, 7, 64, 1, 49, 7, e->wff, n->feat, p + o[7], 1.f, 512);
-  a4.b_variant_stride = (int64_t)49 * 128 * 128;
-  a4.n_variant_stride = 128;
-  DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_BIAS_RELU_F32>("fc_fwd", a4, 4, st)));
+  {
+    TmaGemmArgs g{};
+    g.M = nb; g.N_total = 512; g.KB = 49; g.out = n->feat; g.out_ld = 512; g.bias = p + o[7]; g.mask_src = nullptr;
+    DRL_TRY((launch_tma_gemm<256, EPI_BIAS_RELU_F32>("fc_fwd", n->act[2], nb, 3136, e->wff, 512, g, st)));
+  }
   return DRL_OK;
 }
 
@@ -304,16 +369,31 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     colsum512_bf16_kernel<<<sms * 2 < nb ? sms * 2 : nb, 256, 0, st>>>((const __nv_bfloat16*)n->dpre, nb, g + o[7]);
     DRL_LAUNCH_CHECK();
   }
-  WgradArgs wf = wgrad_args(nb, n->act[2], nullptr, 1, 1, 7, 7, 64, 1, 7, 49, n->dpre, 512, 1, 2, g + o[6], 64, 7, 7);
-  DRL_TRY((launch_wgrad<256, SRC_BF16, 1>("fc_wgrad", wf, splits(nb, 50), 50, st)));
   {
-    RowGatherArgs a{};
-    a.M = nb; a.KB = 8; a.src = n->dpre; a.row_idx = nullptr; a.P = 1; a.OW = 1; a.H = 1; a.W = 1; a.C = 512;
-    a.stride = 1; a.pad = 0; a.KBX = 8; a.bpack = e->wfd; a.b_variant_stride = (int64_t)8 * 64 * 128;
-    a.out = n->dact[2]; a.mask_src = (const __nv_bfloat16*)n->act[2]; a.scale = 1.f; a.bias = nullptr;
-    a.out_sample_pitch = 3136; a.out_row_pitch = 3136; a.out_C = 3136; a.osy = 1; a.osx = 1;
-    a.n_variant_stride = 64; a.classes = 0;
-    DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("fc_dgrad", a, 49, st)));
+    ProfileScope prof("fc_wgrad", st);
+    using Cf = WgradTmaCfg<256, 1>;
+    CUtensorMap tp, td;
+    DRL_TRY(make_tmap_bf16(&tp, n->act[2], (uint64_t)nb, 3136, 32));
+    DRL_TRY(make_tmap_bf16(&td, n->dpre, (uint64_t)nb, 512, 32));
+    WgradTmaArgs w{};
+    w.M = nb; w.n_tiles = 2; w.kp_valid = 3136; w.gw = g + o[6]; w.Cin = 64; w.KH = 7; w.KW = 7;
+    auto kern = wgrad_tma_kernel<256, 1>;
+    static bool configured = false;
+    if (!configured) {
+      DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cf::kSmem));
+      configured = true;
+    }
+    int gx = 2 * sms / 50;                       // two CTAs per SM
+    if (gx > (nb + 31) / 32) gx = (nb + 31) / 32;
+    if (gx < 1) gx = 1;
+    kern<<<dim3(gx, 50), 192, Cf::kSmem, st>>>(tp, td, w);
+    DRL_LAUNCH_CHECK();
+  }
+  {
+    TmaGemmArgs a{};
+    a.M = nb; a.N_total = 3136; a.KB = 8; a.out = n->dact[2]; a.out_ld = 3136; a.bias = nullptr;
+    a.mask_src = (const __nv_bfloat16*)n->act[2];
+    DRL_TRY((launch_tma_gemm<256, EPI_MASK_BF16>("fc_dgrad", n->dpre, nb, 512, e->wfd, 3136, a, st)));
   }
   // ---- conv3
   DRL_TRY(colsum(n->dact[2], (int64_t)nb * 49, 64, g + o[5], st));
