@@ -39,6 +39,7 @@ PROTOTYPES = {
     'drl_check_device': (c_int, [c_int]),
     'drl_launch_count': (ctypes.c_longlong, []),
     'drl_profile_enable': (c_int, [c_int]),
+    'drl_debug_set': (c_int, [c_int, c_int]),
     'drl_profile_read': (c_int, [c_int, ctypes.c_char_p, POINTER(c_float), POINTER(c_int), POINTER(c_int)]),
     'drl_gae_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                             c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -12,6 +12,7 @@
 #include "umma_gemm.cuh"
 #include "umma_conv1.cuh"
 #include "umma_tma_gemm.cuh"
+#include "umma_tma_conv.cuh"
 
 namespace drl {
 
@@ -285,6 +286,59 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
   return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
 }
 
+// [0] descriptor base-offset field for shifted operands: MEASURED on B200 (scripts/try_base_offset.py): the
+//     128B swizzle is applied to the absolute smem address bits, so shifted starts need base offset 0.
+// [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
+int g_debug_flags[8] = {0, 1, 0, 0, 0, 0, 0, 0};
+
+// NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
+static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return DRL_ERR_CUDA;
+  const cuuint64_t dims[4] = {64, W, H, nb};
+  const cuuint64_t strides[3] = {128, W * 128, H * W * 128};
+  const cuuint32_t box[4] = {64, BW, BH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
+}
+
+template <int N, int EPI, int NR>
+static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st) {
+  ProfileScope prof(site, st);
+  CUtensorMap tm;
+  DRL_TRY(make_tmap_act4d(&tm, src, (uint64_t)nb, (uint64_t)H, (uint64_t)W, (uint32_t)BW, (uint32_t)BH));
+  a.nb = nb;
+  a.box_bytes = BW * BH * 128;
+  const int max_shift = ((a.KB - 1) / a.KBX) * a.SHIFT_RW + (a.KBX - 1);
+  a.raw_buf_bytes = ((a.MT * 128 + max_shift) * 128 + 1023) / 1024 * 1024;
+  if (a.raw_buf_bytes < (a.box_bytes + 1023) / 1024 * 1024) a.raw_buf_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  a.use_base_offset = g_debug_flags[0];
+  auto kern = tma_conv_kernel<N, EPI, NR>;
+  const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR);
+  static int configured = 0;
+  if (configured < smem) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int ctas = (NR == 2 ? 2 : 1) * sm_count();
+  kern<<<nb < ctas ? nb : ctas, 192, smem, st>>>(tm, a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+static TmaConvArgs tma_conv_args(int KB, int KBX, int RW, int SHIFT_RW, int pad, int MT, int OH, int OW, const void* bpack,
+                                 void* out, const float* bias, const void* mask, int64_t sample_pitch, int row_pitch, int out_C,
+                                 int os, int classes) {
+  TmaConvArgs a{};
+  a.KB = KB; a.KBX = KBX; a.RW = RW; a.SHIFT_RW = SHIFT_RW; a.pad = pad; a.MT = MT; a.OH = OH; a.OW = OW; a.bpack = bpack;
+  a.out = out; a.bias = bias; a.scale = 1.f; a.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask);
+  a.out_sample_pitch = sample_pitch; a.out_row_pitch = row_pitch; a.out_C = out_C; a.osy = os; a.osx = os; a.classes = classes;
+  return a;
+}
+
 template <int BN, int EPI>
 static int launch_tma_gemm(const char* site, const void* a, int M, int K, const void* b, int N_total, const TmaGemmArgs& args,
                            cudaStream_t st) {
@@ -336,9 +390,20 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     DRL_LAUNCH_CHECK();
   }
   RowGatherArgs a2 = fwd_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 8, 2, e->w2f, n->act[1], p + o[3], 1.f, 64);
-  DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
+  if (g_debug_flags[1]) {
+    // act1 seen as [nb, 20 rows, 10 pixel pairs, 64]: k-block (ky, half) = pair row shift ky*10 + half, GEMM rows oy*20 + ox
+    TmaConvArgs c2 = tma_conv_args(8, 2, 20, 10, 0, 2, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 3>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
+  } else {
+    DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
+  }
   RowGatherArgs a3 = fwd_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 9, 3, e->w3f, n->act[2], p + o[5], 1.f, 64);
-  DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
+  if (g_debug_flags[1]) {
+    TmaConvArgs c3 = tma_conv_args(9, 3, 9, 9, 0, 1, 7, 7, e->w3f, n->act[2], p + o[5], nullptr, 3136, 7 * 64, 64, 1, 0);
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 2>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
+  } else {
+    DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
+  }
   {
     TmaGemmArgs g{};
     g.M = nb; g.N_total = 512; g.KB = 49; g.out = n->feat; g.out_ld = 512; g.bias = p + o[7]; g.mask_src = nullptr;
@@ -406,7 +471,13 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     a.out = n->dact[1]; a.mask_src = (const __nv_bfloat16*)n->act[1]; a.scale = 1.f; a.bias = nullptr;
     a.out_sample_pitch = 5184; a.out_row_pitch = 9 * 64; a.out_C = 64; a.osy = 1; a.osx = 1;
     a.n_variant_stride = 0; a.classes = 0;
-    DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
+    if (g_debug_flags[1]) {
+      // dY3 zero-padded by 2 (TMA out-of-bounds fill) to 11x11; output rows y*11 + x over the 9x9 input grid
+      TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
+      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 2>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
+    } else {
+      DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
+    }
   }
   // ---- conv2
   DRL_TRY(colsum(n->dact[1], (int64_t)nb * 81, 64, g + o[3], st));
@@ -421,7 +492,13 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     a.out = n->dact[0]; a.mask_src = (const __nv_bfloat16*)n->act[0]; a.scale = 1.f; a.bias = nullptr;
     a.out_sample_pitch = 12800; a.out_row_pitch = 20 * 32; a.out_C = 32; a.osy = 2; a.osx = 2;
     a.n_variant_stride = 0; a.classes = 1;
-    DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
+    if (g_debug_flags[1]) {
+      // dY2 zero-padded by 1 to 11x11; GEMM rows u*11 + v over the 10x10 grid of 2x2 output blocks
+      TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
+      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 2>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
+    } else {
+      DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
+    }
   }
   // ---- conv1 (no data gradient: observations need none, agent.py:66-67)
   DRL_TRY(colsum(n->dact[0], (int64_t)nb * 400, 32, g + o[1], st));
@@ -443,3 +520,11 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
 }
 
 }  // namespace drl
+
+// debug switches (parity experiments): key 0 = descriptor base offset for shifted operands,
+// key 1 = TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
+extern "C" int drl_debug_set(int key, int value) {
+  if (key < 0 || key >= 8) return DRL_ERR_BAD_ARG;
+  drl::g_debug_flags[key] = value;
+  return DRL_OK;
+}

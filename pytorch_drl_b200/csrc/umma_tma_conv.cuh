@@ -1,0 +1,206 @@
+// Family 1c — `tma_conv_kernel`: implicit-GEMM convolution with NO im2col materialisation.
+//
+// One tile = one sample.  Its NHWC bf16 activation (zero-padded by the TMA unit's out-of-bounds
+// fill where the convolution needs padding) lands in shared memory with ONE 4-D tensor-map TMA load
+// as a stack of "pixel rows" of 128 bytes (64 channels, or a pair of 32-channel pixels), 128B-swizzled.
+// The GEMM rows are indexed on the INPUT-width grid (row r = y * RW + x with RW the staged row width),
+// so for tap (ty, tx) the A operand is simply the staged image shifted by ty*RW + tx pixel rows:
+// the MMA reads it in place through a shared-memory descriptor whose start address is advanced by
+// the shift.  (Measured on B200: the 128B swizzle XOR uses the ABSOLUTE smem address bits [7,10), so a
+// start address that is not 1024-byte aligned needs no matrix-base-offset: scripts/try_base_offset.py.)  Rows whose x falls
+// outside the output width are computed and discarded (51-82 % of the rows are useful), which is
+// cheap because these small-N layers are operand-bandwidth bound, not tensor bound.
+// All weight k-block tiles of the layer stay resident in shared memory (one bulk copy per CTA).
+// No producer warps, no generic-proxy writes, no proxy fences: warps 0-3 epilogue, 4 MMA, 5 TMA.
+#pragma once
+#include <cuda.h>
+#include "umma_tma_gemm.cuh"
+
+namespace drl {
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          umma::smem_u32(smem_dst)),
+      "l"(tmap), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+struct TmaConvArgs {
+  int nb;
+  int KB, KBX;            // taps (k-blocks of 64) and taps per tap-row
+  int RW;                 // GEMM row pitch: row r = y * RW + x
+  int SHIFT_RW;           // staged pixel rows per tap row: tap (ty, tx) shifts the image by ty*SHIFT_RW + tx
+  int pad;                // TMA start coordinate = (-pad, -pad)
+  int box_bytes;          // bytes one sample's TMA box writes
+  int raw_buf_bytes;      // staging buffer size (>= 128*MT + max shift rows, multiple of 1024)
+  int MT;                 // M tiles (of 128 GEMM rows) per sample
+  int OH, OW;             // valid output grid
+  const void* bpack;      // [KB][N x 64] swizzled weight tile images
+  // epilogue (same conventions as RowGatherArgs)
+  void* out; const float* bias; float scale; const __nv_bfloat16* mask_src;
+  int64_t out_sample_pitch; int out_row_pitch; int out_C; int osy, osx; int classes;
+  int use_base_offset;    // debug switch for the descriptor base-offset field
+};
+
+template <int N>
+constexpr int tma_conv_smem(int KB, int raw_buf_bytes, int NR) { return KB * N * 128 + NR * raw_buf_bytes + 1280 + 1024; }
+
+template <int N, int EPI, int NR>
+__global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                          const TmaConvArgs args) {
+  using namespace umma;
+  constexpr int B_BYTES = N * 128;
+  constexpr int TMEM_COLS = 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;                                         // KB weight tiles, resident
+  uint8_t* sRaw = smem + args.KB * B_BYTES;                   // NR staged samples
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + NR * args.raw_buf_bytes);
+  uint64_t* raw_full = bars;            // [NR]
+  uint64_t* raw_empty = bars + NR;      // [NR]
+  uint64_t* tfull = bars + 2 * NR;      // [2]
+  uint64_t* tempty = bars + 2 * NR + 2; // [2]
+  uint64_t* b_full = bars + 2 * NR + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NR + 5);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (EPI != EPI_MASK_BF16 && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 5 && lane == 0) tma_prefetch_desc(&tmap);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (lane == 0) {
+      // weights: resident for the whole kernel
+      mbar_arrive_expect_tx(b_full, (uint32_t)(args.KB * B_BYTES));
+      for (int kb = 0; kb < args.KB; ++kb)
+        tma_bulk_g2s(sB + kb * B_BYTES, reinterpret_cast<const uint8_t*>(args.bpack) + (int64_t)kb * B_BYTES, B_BYTES, b_full);
+      uint32_t j = 0;
+      for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
+        const uint32_t buf = j % NR;
+        mbar_wait(raw_empty + buf, ((j / NR) & 1) ^ 1);
+        mbar_arrive_expect_tx(raw_full + buf, (uint32_t)args.box_bytes);
+        tma_load_4d(sRaw + buf * args.raw_buf_bytes, &tmap, 0, -args.pad, -args.pad, b, raw_full + buf);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(1u, 128, N, 0, 0);
+      constexpr uint32_t hi0 = desc_hi(1024, LAYOUT_SW128);
+      const uint32_t b_lo0 = desc_lo(smem_u32(sB), 0);
+      mbar_wait(b_full, 0);
+      uint32_t j = 0, it = 0;
+      for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
+        const uint32_t buf = j % NR;
+        mbar_wait(raw_full + buf, (j / NR) & 1);
+        const uint32_t raw_addr = smem_u32(sRaw + buf * args.raw_buf_bytes);
+        for (int mt = 0; mt < args.MT; ++mt, ++it) {
+          const uint32_t acc = it & 1;
+          mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * N;
+          int ty = 0, tx = 0;
+          for (int kb = 0; kb < args.KB; ++kb) {
+            const uint32_t a_addr = raw_addr + (uint32_t)(mt * 128 + ty * args.SHIFT_RW + tx) * 128u;
+            const uint32_t a_hi = args.use_base_offset ? (hi0 | (((a_addr >> 7) & 7u) << 17)) : hi0;
+            const uint32_t a_lo = desc_lo(a_addr, 0);
+            const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
+            if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, a_hi, b_lo, hi0, idesc);
+            else mma_f16_lohi<true>(tmem_d, a_lo, a_hi, b_lo, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 2, a_hi, b_lo + 2, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 4, a_hi, b_lo + 4, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 6, a_hi, b_lo + 6, hi0, idesc);
+            if (++tx == args.KBX) { tx = 0; ++ty; }
+          }
+          mma_commit(tfull + acc);
+        }
+        mma_commit(raw_empty + buf);           // staged sample free once every MMA reading it has retired
+      }
+    }
+    __syncwarp();
+  } else {
+    auto coff = [&](int ch) -> int64_t {
+      return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
+    };
+    uint32_t it = 0;
+    for (int b = blockIdx.x; b < args.nb; b += gridDim.x) {
+      for (int mt = 0; mt < args.MT; ++mt, ++it) {
+        const uint32_t acc = it & 1;
+        const int r = mt * 128 + threadIdx.x;
+        const int y = r / args.RW, x = r - y * args.RW;
+        const bool ok = y < args.OH && x < args.OW;
+        const int64_t ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(y * args.osy) * args.out_row_pitch +
+                             (int64_t)(x * args.osx) * args.out_C;
+        uint4 mk[N <= 64 ? N / 8 : 1];
+        if (EPI == EPI_MASK_BF16 && N <= 64 && ok) {
+#pragma unroll
+          for (int ch = 0; ch < N / 32; ++ch)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mk[ch * 4 + q] = ldg_v4(args.mask_src + ooff + coff(ch) + 8 * q);
+        }
+        mbar_wait(tfull + acc, (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < N / 32; ++ch) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N + ch * 32, rr);
+          tmem_ld_wait();
+          if (ch == N / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty + acc);
+          }
+          if (ok) {
+            if (EPI == EPI_BIAS_RELU_BF16) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  f[i] = fmaxf(fmaf(__uint_as_float(rr[8 * q + i]), args.scale, sBias[ch * 32 + 8 * q + i]), 0.f);
+                reinterpret_cast<uint4*>(o)[q] =
+                    make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              }
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 mv = N <= 64 ? mk[ch * 4 + q] : ldg_v4(args.mask_src + ooff + coff(ch) + 8 * q);
+                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float lo = (mw[i] & 0x00007fffu) ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
+                  const float hi2 = (mw[i] & 0x7fff0000u) ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
+                  pk[i] = pack_bf16x2(lo, hi2);
+                }
+                reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace drl
