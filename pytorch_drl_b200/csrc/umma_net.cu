@@ -289,16 +289,18 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [0] descriptor base-offset field for shifted operands: MEASURED on B200 (scripts/try_base_offset.py): the
 //     128B swizzle is applied to the absolute smem address bits, so shifted starts need base offset 0.
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
-int g_debug_flags[8] = {0, 1, 0, 0, 0, 0, 0, 0};
+// [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
+int g_debug_flags[8] = {0, 1, 1, 0, 0, 0, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
-static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH) {
+static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
+                           uint32_t h_stride = 1) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return DRL_ERR_CUDA;
   const cuuint64_t dims[4] = {64, W, H, nb};
   const cuuint64_t strides[3] = {128, W * 128, H * W * 128};
   const cuuint32_t box[4] = {64, BW, BH, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, h_stride, 1};   // h_stride 2: every other map row (box BH spans BH/2 rows)
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -309,12 +311,14 @@ template <int N, int EPI, int NR>
 static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st) {
   ProfileScope prof(site, st);
   CUtensorMap tm;
-  DRL_TRY(make_tmap_act4d(&tm, src, (uint64_t)nb, (uint64_t)H, (uint64_t)W, (uint32_t)BW, (uint32_t)BH));
+  DRL_TRY(make_tmap_act4d(&tm, src, (uint64_t)nb, (uint64_t)H, (uint64_t)W, (uint32_t)BW, (uint32_t)BH, (uint32_t)a.planes));
   a.nb = nb;
-  a.box_bytes = BW * BH * 128;
-  const int max_shift = ((a.KB - 1) / a.KBX) * a.SHIFT_RW + (a.KBX - 1);
-  a.raw_buf_bytes = ((a.MT * 128 + max_shift) * 128 + 1023) / 1024 * 1024;
-  if (a.raw_buf_bytes < (a.box_bytes + 1023) / 1024 * 1024) a.raw_buf_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  a.box_bytes = BW * (BH / a.planes) * 128;
+  const int tap_rows = (a.KB - 1) / a.KBX;               // last tap row
+  const int max_shift = (a.planes == 2 ? tap_rows / 2 : tap_rows) * a.SHIFT_RW + (a.KBX - 1);
+  a.plane_bytes = ((a.MT * 128 + max_shift) * 128 + 1023) / 1024 * 1024;
+  if (a.plane_bytes < (a.box_bytes + 1023) / 1024 * 1024) a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  a.raw_buf_bytes = a.plane_bytes * a.planes;
   a.use_base_offset = g_debug_flags[0];
   auto kern = tma_conv_kernel<N, EPI, NR>;
   const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR);
@@ -323,7 +327,8 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
     DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const int ctas = (NR == 2 ? 2 : 1) * sm_count();
+  const int per_sm = (NR == 2 && 2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;   // co-resident CTAs by shared memory
+  const int ctas = per_sm * sm_count();
   kern<<<nb < ctas ? nb : ctas, 192, smem, st>>>(tm, a);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
@@ -333,10 +338,35 @@ static TmaConvArgs tma_conv_args(int KB, int KBX, int RW, int SHIFT_RW, int pad,
                                  void* out, const float* bias, const void* mask, int64_t sample_pitch, int row_pitch, int out_C,
                                  int os, int classes) {
   TmaConvArgs a{};
-  a.KB = KB; a.KBX = KBX; a.RW = RW; a.SHIFT_RW = SHIFT_RW; a.pad = pad; a.MT = MT; a.OH = OH; a.OW = OW; a.bpack = bpack;
+  a.KB = KB; a.KBX = KBX; a.RW = RW; a.SHIFT_RW = SHIFT_RW; a.pad = pad; a.planes = 1; a.MT = MT; a.OH = OH; a.OW = OW; a.bpack = bpack;
   a.out = out; a.bias = bias; a.scale = 1.f; a.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask);
   a.out_sample_pitch = sample_pitch; a.out_row_pitch = row_pitch; a.out_C = out_C; a.osy = os; a.osx = os; a.classes = classes;
   return a;
+}
+
+template <int NT, int MB, int NR>
+static int launch_wgrad_conv(const char* site, const void* p_src, int pH, int pW, int pBW, int pBH, const void* dy_src, int dH,
+                             int dW, int dBW, int dBH, int nb, WgradConvArgs a, cudaStream_t st) {
+  ProfileScope prof(site, st);
+  CUtensorMap tp, td;
+  DRL_TRY(make_tmap_act4d(&tp, p_src, (uint64_t)nb, (uint64_t)pH, (uint64_t)pW, (uint32_t)pBW, (uint32_t)pBH, (uint32_t)a.p_planes));
+  DRL_TRY(make_tmap_act4d(&td, dy_src, (uint64_t)nb, (uint64_t)dH, (uint64_t)dW, (uint32_t)dBW, (uint32_t)dBH));
+  a.nb = nb;
+  a.p_box_bytes = pBW * (pBH / a.p_planes) * 128;
+  a.dy_box_bytes = dBW * dBH * 128;
+  a.p_buf_bytes = a.p_plane_bytes * a.p_planes;
+  a.dy_buf_bytes = (a.dy_box_bytes + 1023) / 1024 * 1024;
+  if (a.dy_buf_bytes < a.ksteps * 16 * 128) a.dy_buf_bytes = (a.ksteps * 16 * 128 + 1023) / 1024 * 1024;
+  auto kern = wgrad_conv_tma_kernel<NT, MB, NR>;
+  const int smem = NR * (a.p_buf_bytes + a.dy_buf_bytes) + 256 + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  kern<<<nb < sm_count() ? nb : sm_count(), 192, smem, st>>>(tp, td, a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
 }
 
 template <int BN, int EPI>
@@ -391,9 +421,11 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   }
   RowGatherArgs a2 = fwd_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 8, 2, e->w2f, n->act[1], p + o[3], 1.f, 64);
   if (g_debug_flags[1]) {
-    // act1 seen as [nb, 20 rows, 10 pixel pairs, 64]: k-block (ky, half) = pair row shift ky*10 + half, GEMM rows oy*20 + ox
-    TmaConvArgs c2 = tma_conv_args(8, 2, 20, 10, 0, 2, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 3>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
+    // act1 seen as [nb, 20 rows, 10 pixel pairs, 64]; even / odd rows are staged as two 10x10 planes (TMA row
+    // stride 2), so tap row ky reads plane ky&1 shifted by (ky>>1)*10 + half and the GEMM rows are oy*10 + ox
+    TmaConvArgs c2 = tma_conv_args(8, 2, 10, 10, 0, 1, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
+    c2.planes = 2;
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
   }
@@ -463,7 +495,18 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   // ---- conv3
   DRL_TRY(colsum(n->dact[2], (int64_t)nb * 49, 64, g + o[5], st));
   WgradArgs w3 = wgrad_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 3, 9, n->dact[2], 64, 5, 1, g + o[4], 64, 3, 3);
-  DRL_TRY((launch_wgrad<64, SRC_BF16, 5>("conv3_wgrad", w3, splits(nb * 49, 1), 1, st)));
+  if (g_debug_flags[2]) {
+    // taps t = (ty, tx) shift the staged 9x9 input by ty*9 + tx rows; blocks = tap pairs (0,1)(2,3)(4,5)(6,7)(8,-)
+    WgradConvArgs w{};
+    w.ksteps = 4; w.n_blocks = 5; w.p_planes = 1; w.p_pad = 0;
+    const int sh[10] = {0, 1, 2, 9, 10, 11, 18, 19, 20, 21};
+    for (int mb = 0; mb < 5; ++mb) { w.a_off[mb] = sh[2 * mb] * 128; w.a_lbo[mb] = (sh[2 * mb + 1] - sh[2 * mb]) * 128; }
+    w.p_plane_bytes = 11264;                         // 88 rows >= 63 + 21 + 1
+    w.gw = g + o[4]; w.Cin = 64; w.KH = 3; w.KW = 3; w.kp_valid = 576;
+    DRL_TRY((launch_wgrad_conv<64, 5, 4>("conv3_wgrad", n->act[1], 9, 9, 9, 9, n->dact[2], 7, 7, 9, 8, nb, w, st)));
+  } else {
+    DRL_TRY((launch_wgrad<64, SRC_BF16, 5>("conv3_wgrad", w3, splits(nb * 49, 1), 1, st)));
+  }
   {
     RowGatherArgs a{};
     a.M = nb * 81; a.KB = 9; a.src = n->dact[2]; a.row_idx = nullptr; a.P = 81; a.OW = 9; a.H = 7; a.W = 7; a.C = 64;
@@ -482,7 +525,17 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   // ---- conv2
   DRL_TRY(colsum(n->dact[1], (int64_t)nb * 81, 64, g + o[3], st));
   WgradArgs w2 = wgrad_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 2, 8, n->dact[1], 64, 4, 1, g + o[2], 32, 4, 4);
-  DRL_TRY((launch_wgrad<64, SRC_BF16, 4>("conv2_wgrad", w2, splits(nb * 81, 1), 1, st)));
+  if (g_debug_flags[2]) {
+    // act1 as pixel pairs, even / odd rows in two planes; block ky = atoms (ky, half 0/1): plane ky&1, shift (ky>>1)*10 + half
+    WgradConvArgs w{};
+    w.ksteps = 6; w.n_blocks = 4; w.p_planes = 2; w.p_pad = 0;
+    w.p_plane_bytes = 14336;                         // 112 rows >= 95 + 11 + 1
+    for (int ky = 0; ky < 4; ++ky) { w.a_off[ky] = (ky & 1) * w.p_plane_bytes + (ky >> 1) * 10 * 128; w.a_lbo[ky] = 128; }
+    w.gw = g + o[2]; w.Cin = 32; w.KH = 4; w.KW = 4; w.kp_valid = 512;
+    DRL_TRY((launch_wgrad_conv<64, 4, 4>("conv2_wgrad", n->act[0], 20, 10, 10, 20, n->dact[1], 9, 9, 10, 10, nb, w, st)));
+  } else {
+    DRL_TRY((launch_wgrad<64, SRC_BF16, 4>("conv2_wgrad", w2, splits(nb * 81, 1), 1, st)));
+  }
   {
     // the four parity classes of the stride-2 transposed convolution share their 2x2-tap gather over dY2:
     // ONE GEMM with N = 4 classes x 32 ci; column chunk `cls` lands on output pixel (2u + cls/2, 2v + cls%2)

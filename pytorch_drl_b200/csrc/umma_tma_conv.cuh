@@ -33,6 +33,9 @@ struct TmaConvArgs {
   int RW;                 // GEMM row pitch: row r = y * RW + x
   int SHIFT_RW;           // staged pixel rows per tap row: tap (ty, tx) shifts the image by ty*SHIFT_RW + tx
   int pad;                // TMA start coordinate = (-pad, -pad)
+  int planes;             // 1, or 2: stride-2 conv, even / odd input rows staged as separate planes (tap row ty
+                          //    reads plane ty & 1 shifted by (ty >> 1) * SHIFT_RW + tx)
+  int plane_bytes;        // smem bytes of one plane (multiple of 1024)
   int box_bytes;          // bytes one sample's TMA box writes
   int raw_buf_bytes;      // staging buffer size (>= 128*MT + max shift rows, multiple of 1024)
   int MT;                 // M tiles (of 128 GEMM rows) per sample
@@ -91,8 +94,9 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
       for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
         const uint32_t buf = j % NR;
         mbar_wait(raw_empty + buf, ((j / NR) & 1) ^ 1);
-        mbar_arrive_expect_tx(raw_full + buf, (uint32_t)args.box_bytes);
-        tma_load_4d(sRaw + buf * args.raw_buf_bytes, &tmap, 0, -args.pad, -args.pad, b, raw_full + buf);
+        mbar_arrive_expect_tx(raw_full + buf, (uint32_t)(args.box_bytes * args.planes));
+        for (int pl = 0; pl < args.planes; ++pl)
+          tma_load_4d(sRaw + buf * args.raw_buf_bytes + pl * args.plane_bytes, &tmap, 0, -args.pad, -args.pad + pl, b, raw_full + buf);
       }
     }
     __syncwarp();
@@ -114,7 +118,9 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
           const uint32_t tmem_d = tmem_base + acc * N;
           int ty = 0, tx = 0;
           for (int kb = 0; kb < args.KB; ++kb) {
-            const uint32_t a_addr = raw_addr + (uint32_t)(mt * 128 + ty * args.SHIFT_RW + tx) * 128u;
+            const uint32_t a_addr = args.planes == 2
+                ? raw_addr + (uint32_t)((ty & 1) * args.plane_bytes) + (uint32_t)(mt * 128 + (ty >> 1) * args.SHIFT_RW + tx) * 128u
+                : raw_addr + (uint32_t)(mt * 128 + ty * args.SHIFT_RW + tx) * 128u;
             const uint32_t a_hi = args.use_base_offset ? (hi0 | (((a_addr >> 7) & 7u) << 17)) : hi0;
             const uint32_t a_lo = desc_lo(a_addr, 0);
             const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
@@ -190,6 +196,135 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
                 reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace drl
+
+namespace drl {
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient of a conv layer with TMA-staged operands and descriptor-shifted windows:
+//   dW^T[kp = (ky,kx,ci)][co] += sum over positions r of  P[r][kp] * dY[r][co]
+// Per sample the input activation (P source) and dY land in shared memory by tensor-map TMA loads; dY is
+// laid out on the same width-RW row grid as the forward GEMM rows, its out-of-range columns/rows are zero
+// (TMA out-of-bounds fill), so the discarded grid positions contribute nothing.  For tap t the MN-major A
+// operand is the staged input shifted by the tap offset; two taps form one 128-row accumulator block
+// (leading-dimension byte offset = distance between their windows).  All accumulator blocks stay in
+// TMEM for the whole kernel; partial sums are added with red.global.add.f32 in OIHW order.
+// ---------------------------------------------------------------------------------------------------------
+struct WgradConvArgs {
+  int nb;
+  int ksteps;               // reduction extent in 16-row MMA steps
+  int n_blocks;             // accumulator blocks (2 taps/atoms each)
+  uint32_t a_off[8];        // byte offset of the first atom of each block inside the staged input
+  uint32_t a_lbo[8];        // byte distance to the block's second atom
+  int p_planes, p_pad, p_box_bytes, p_plane_bytes, p_buf_bytes;
+  int dy_box_bytes, dy_buf_bytes;
+  float* gw; int Cin, KH, KW, kp_valid;
+};
+
+template <int NT, int MB, int NR>
+__global__ void __launch_bounds__(192, 1) wgrad_conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
+                                                                const __grid_constant__ CUtensorMap tmap_dy,
+                                                                const WgradConvArgs args) {
+  using namespace umma;
+  constexpr int ACC_COLS = MB * NT;
+  constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = args.p_buf_bytes + args.dy_buf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NR * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NR;
+  uint64_t* done = bars + 2 * NR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NR + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // rows the TMA never writes must read as zero (they meet zero dY rows, but 0 * NaN would poison the sum)
+  for (int i = threadIdx.x * 16; i < NR * stage_bytes; i += blockDim.x * 16) st_shared_v4(smem_u32(smem + i), make_uint4(0u, 0u, 0u, 0u));
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NR; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool has_work = (int)blockIdx.x < args.nb;
+
+  if (has_work) {
+    if (warp == 5) {
+      if (lane == 0) {
+        uint32_t j = 0;
+        for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
+          const uint32_t buf = j % NR;
+          mbar_wait(empty + buf, ((j / NR) & 1) ^ 1);
+          mbar_arrive_expect_tx(full + buf, (uint32_t)(args.p_box_bytes * args.p_planes + args.dy_box_bytes));
+          uint8_t* sp = smem + buf * stage_bytes;
+          for (int pl = 0; pl < args.p_planes; ++pl)
+            tma_load_4d(sp + pl * args.p_plane_bytes, &tmap_p, 0, -args.p_pad, -args.p_pad + pl, b, full + buf);
+          tma_load_4d(sp + args.p_buf_bytes, &tmap_dy, 0, 0, 0, b, full + buf);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 4) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);       // bf16, MN-major A and B
+        constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
+        uint32_t j = 0;
+        for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
+          const uint32_t buf = j % NR;
+          mbar_wait(full + buf, (j / NR) & 1);
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(smem + buf * stage_bytes), d_addr = p_addr + args.p_buf_bytes;
+          const uint32_t b_lo0 = desc_lo(d_addr, 0);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint32_t a_lo0 = desc_lo(p_addr + args.a_off[mb], args.a_lbo[mb]);
+            for (int k = 0; k < args.ksteps; ++k) {
+              if (j == 0 && k == 0) mma_f16_lohi<false>(tmem_base + mb * NT, a_lo0, hi, b_lo0, hi, idesc);
+              else mma_f16_lohi<true>(tmem_base + mb * NT, a_lo0 + k * ((16 * 128) >> 4), hi, b_lo0 + k * ((16 * 128) >> 4), hi, idesc);
+            }
+          }
+          mma_commit(empty + buf);
+        }
+        mma_commit(done);
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int khw = args.KH * args.KW;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int kp = mb * 128 + threadIdx.x;
+        const bool ok = kp < args.kp_valid;
+        const int kc = args.KW * args.Cin;
+        const int ky = kp / kc, r2 = kp - ky * kc;
+        const int kx = r2 / args.Cin, ci = r2 - kx * args.Cin;
+        float* g0 = args.gw + ((int64_t)ci * args.KH + ky) * args.KW + kx;
+#pragma unroll 1
+        for (int ch = 0; ch < NT / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * NT + ch * 32, r);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int jn = 0; jn < 32; ++jn) atomicAdd(g0 + (int64_t)(ch * 32 + jn) * args.Cin * khw, __uint_as_float(r[jn]));
           }
         }
       }
