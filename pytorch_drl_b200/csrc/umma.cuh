@@ -203,6 +203,22 @@ __device__ __forceinline__ uint4 u8x8_to_f16x8(uint2 w) {
   return o;
 }
 
+// Column sums across a warp: every lane holds one row of 32 values; returns in lane j the sum over the
+// 32 lanes of v[j] (a transpose-reduce: 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -290,7 +290,7 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 //     128B swizzle is applied to the absolute smem address bits, so shifted starts need base offset 0.
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
 // [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
-int g_debug_flags[8] = {0, 1, 1, 0, 0, 0, 0, 0};
+int g_debug_flags[8] = {0, 1, 0, 0, 0, 0, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -439,6 +439,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   {
     TmaGemmArgs g{};
     g.M = nb; g.N_total = 512; g.KB = 49; g.out = n->feat; g.out_ld = 512; g.bias = p + o[7]; g.mask_src = nullptr;
+    g.bias_grad = nullptr; g.bias_mod = 1;
     DRL_TRY((launch_tma_gemm<256, EPI_BIAS_RELU_F32>("fc_fwd", n->act[2], nb, 3136, e->wff, 512, g, st)));
   }
   return DRL_OK;
@@ -490,10 +491,10 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     TmaGemmArgs a{};
     a.M = nb; a.N_total = 3136; a.KB = 8; a.out = n->dact[2]; a.out_ld = 3136; a.bias = nullptr;
     a.mask_src = (const __nv_bfloat16*)n->act[2];
+    a.bias_grad = g + o[5]; a.bias_mod = 64;          // conv3 bias gradient = column sums of dact3 (column % 64)
     DRL_TRY((launch_tma_gemm<256, EPI_MASK_BF16>("fc_dgrad", n->dpre, nb, 512, e->wfd, 3136, a, st)));
   }
-  // ---- conv3
-  DRL_TRY(colsum(n->dact[2], (int64_t)nb * 49, 64, g + o[5], st));
+  // ---- conv3 (its bias gradient was accumulated by the fc data-gradient epilogue)
   WgradArgs w3 = wgrad_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 3, 9, n->dact[2], 64, 5, 1, g + o[4], 64, 3, 3);
   if (g_debug_flags[2]) {
     // taps t = (ty, tx) shift the staged 9x9 input by ty*9 + tx rows; blocks = tap pairs (0,1)(2,3)(4,5)(6,7)(8,-)
@@ -517,13 +518,14 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     if (g_debug_flags[1]) {
       // dY3 zero-padded by 2 (TMA out-of-bounds fill) to 11x11; output rows y*11 + x over the 9x9 input grid
       TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
+      c.bias_grad = g + o[3]; c.bias_mod = 64;       // conv2 bias gradient
       DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 2>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
     }
   }
   // ---- conv2
-  DRL_TRY(colsum(n->dact[1], (int64_t)nb * 81, 64, g + o[3], st));
+  if (!g_debug_flags[1]) DRL_TRY(colsum(n->dact[1], (int64_t)nb * 81, 64, g + o[3], st));
   WgradArgs w2 = wgrad_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 2, 8, n->dact[1], 64, 4, 1, g + o[2], 32, 4, 4);
   if (g_debug_flags[2]) {
     // act1 as pixel pairs, even / odd rows in two planes; block ky = atoms (ky, half 0/1): plane ky&1, shift (ky>>1)*10 + half
@@ -548,13 +550,14 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     if (g_debug_flags[1]) {
       // dY2 zero-padded by 1 to 11x11; GEMM rows u*11 + v over the 10x10 grid of 2x2 output blocks
       TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
+      c.bias_grad = g + o[1]; c.bias_mod = 32;       // conv1 bias gradient
       DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 2>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
     }
   }
   // ---- conv1 (no data gradient: observations need none, agent.py:66-67)
-  DRL_TRY(colsum(n->dact[0], (int64_t)nb * 400, 32, g + o[1], st));
+  if (!g_debug_flags[1]) DRL_TRY(colsum(n->dact[0], (int64_t)nb * 400, 32, g + o[1], st));
   {
     ProfileScope prof("conv1_wgrad", st);
     Conv1Args a1{};

@@ -45,6 +45,8 @@ struct TmaConvArgs {
   void* out; const float* bias; float scale; const __nv_bfloat16* mask_src;
   int64_t out_sample_pitch; int out_row_pitch; int out_C; int osy, osx; int classes;
   int use_base_offset;    // debug switch for the descriptor base-offset field
+  float* bias_grad;       // EPI_MASK: += column sums of the produced gradient, index = column % bias_mod (or nullptr)
+  int bias_mod;
 };
 
 template <int N>
@@ -141,6 +143,9 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
     auto coff = [&](int ch) -> int64_t {
       return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
     };
+    float colacc[N / 32];
+#pragma unroll
+    for (int ch = 0; ch < N / 32; ++ch) colacc[ch] = 0.f;
     uint32_t it = 0;
     for (int b = blockIdx.x; b < args.nb; b += gridDim.x) {
       for (int mt = 0; mt < args.MT; ++mt, ++it) {
@@ -192,13 +197,25 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
                   const float lo = (mw[i] & 0x00007fffu) ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
                   const float hi2 = (mw[i] & 0x7fff0000u) ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
                   pk[i] = pack_bf16x2(lo, hi2);
+                  rr[8 * q + 2 * i] = __float_as_uint(lo);
+                  rr[8 * q + 2 * i + 1] = __float_as_uint(hi2);
                 }
                 reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
+          if (EPI == EPI_MASK_BF16 && args.bias_grad) {      // fused bias gradient of the layer below
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = ok ? __uint_as_float(rr[i]) : 0.f;
+            colacc[ch] += warp_colsum32(v, lane);
+          }
         }
       }
+    }
+    if (EPI == EPI_MASK_BF16 && args.bias_grad) {
+#pragma unroll
+      for (int ch = 0; ch < N / 32; ++ch) atomicAdd(args.bias_grad + (ch * 32 + lane) % args.bias_mod, colacc[ch]);
     }
   }
   tc_fence_before();

@@ -34,6 +34,8 @@ struct TmaGemmArgs {
   int out_ld;
   const float* bias;           // EPI_BIAS_RELU_F32
   const __nv_bfloat16* mask_src;   // EPI_MASK_BF16 (same layout as out)
+  float* bias_grad;            // EPI_MASK_BF16: += column sums of the produced gradient at index column % bias_mod
+  int bias_mod;
 };
 
 template <int BN>
@@ -125,6 +127,9 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
   } else {
     uint32_t j = 0;
     int last_nt = -1;
+    float colacc[BN / 32];
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) colacc[ch] = 0.f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
       const uint32_t acc = j & 1;
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
       }
       mbar_wait(tfull + acc, (j >> 1) & 1);
       tc_fence_after();
-#pragma unroll 2
+#pragma unroll
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN + ch * 32, r);
@@ -174,12 +179,25 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
                 const float lo = (mw[i] & 0x00007fffu) ? __uint_as_float(r[8 * q + 2 * i]) : 0.f;
                 const float hi2 = (mw[i] & 0x7fff0000u) ? __uint_as_float(r[8 * q + 2 * i + 1]) : 0.f;
                 pk[i] = pack_bf16x2(lo, hi2);
+                r[8 * q + 2 * i] = __float_as_uint(lo);
+                r[8 * q + 2 * i + 1] = __float_as_uint(hi2);
               }
               reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
+        if (EPI == EPI_MASK_BF16 && args.bias_grad) {        // fused bias gradient of the layer below
+          float v[32];
+          const bool live = m < args.M && n < args.N_total;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = live ? __uint_as_float(r[i]) : 0.f;
+          colacc[ch] += warp_colsum32(v, lane);
+        }
       }
+    }
+    if (EPI == EPI_MASK_BF16 && args.bias_grad) {
+#pragma unroll
+      for (int ch = 0; ch < BN / 32; ++ch) atomicAdd(args.bias_grad + (ch * 32 + lane) % args.bias_mod, colacc[ch]);
     }
   }
   tc_fence_before();
