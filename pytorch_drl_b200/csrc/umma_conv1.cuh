@@ -23,6 +23,7 @@ struct Conv1Args {
   const float* bias;         // fwd: [32] EFFECTIVE bias = b - 1024 * scale * sum_k fp16(W[n][k]) (operands hold 1024 + pixel)
   float scale;               // float32(1/255)
   __nv_bfloat16* out;        // fwd: act1 [nb*400, 32]
+  uint32_t* mask_bits;       // fwd: bit c of word m = (act1[m][c] > 0): the ReLU mask conv2's data gradient needs
   const __nv_bfloat16* dy;   // wgrad: dY1 [nb*400, 32]
   float* gw;                 // wgrad: fp32 [32][4][8][8]
 };
@@ -243,13 +244,18 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
       mbar_arrive(tempty + acc);
       if (m < M) {
         uint4* o = reinterpret_cast<uint4*>(args.out + (int64_t)m * 32);
+        uint32_t bits = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(__uint_as_float(r[8 * q + i]), args.scale, bias[8 * q + i]), 0.f);
+          for (int i = 0; i < 8; ++i) {
+            f[i] = fmaxf(fmaf(__uint_as_float(r[8 * q + i]), args.scale, bias[8 * q + i]), 0.f);
+            bits |= (f[i] > 0.f ? 1u : 0u) << (8 * q + i);
+          }
           o[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
+        args.mask_bits[m] = bits;
       }
     }
   }

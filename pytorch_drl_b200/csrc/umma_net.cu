@@ -26,6 +26,7 @@ struct Bf16Engine {
   void* wff = nullptr;   // fc fwd      bf16 row-major [512][3136], k = (hw, c)  (TMA tensor map)
   void* wfd = nullptr;   // fc dgrad    bf16 row-major [3136][512] = the transpose      (TMA tensor map)
   void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
+  uint32_t* bits[3] = {nullptr, nullptr, nullptr};   // ReLU masks of act1/act2/act3, 1 bit per element
   float* b1eff = nullptr; // conv1 effective bias (see conv1_bias_eff_kernel)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
 };
@@ -193,13 +194,16 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&e->w3d, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->b1eff, 32 * sizeof(float)));
+  DRL_CUDA(cudaMalloc(&e->bits[0], nb * 12800 / 8));
+  DRL_CUDA(cudaMalloc(&e->bits[1], nb * 5184 / 8));
+  DRL_CUDA(cudaMalloc(&e->bits[2], nb * 3136 / 8));
   return DRL_OK;
 }
 
 void bf16_free(drl_net* n) {
   Bf16Engine* e = n->bf16;
   if (!e) return;
-  cudaFree(e->w1f); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff);
+  cudaFree(e->w1f); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
   delete e;
   n->bf16 = nullptr;
 }
@@ -409,7 +413,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     ProfileScope prof("conv1_fwd", st);
     Conv1Args a1{};
     a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.bpack = e->w1f; a1.bias = e->b1eff; a1.scale = kInv255;
-    a1.out = reinterpret_cast<__nv_bfloat16*>(n->act[0]);
+    a1.out = reinterpret_cast<__nv_bfloat16*>(n->act[0]); a1.mask_bits = e->bits[0];
     static bool configured = false;
     if (!configured) {
       DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1FwdSmem));
@@ -424,7 +428,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     // act1 seen as [nb, 20 rows, 10 pixel pairs, 64]; even / odd rows are staged as two 10x10 planes (TMA row
     // stride 2), so tap row ky reads plane ky&1 shifted by (ky>>1)*10 + half and the GEMM rows are oy*10 + ox
     TmaConvArgs c2 = tma_conv_args(8, 2, 10, 10, 0, 1, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
-    c2.planes = 2;
+    c2.planes = 2; c2.bits_out = e->bits[1];
     DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
@@ -432,6 +436,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   RowGatherArgs a3 = fwd_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 9, 3, e->w3f, n->act[2], p + o[5], 1.f, 64);
   if (g_debug_flags[1]) {
     TmaConvArgs c3 = tma_conv_args(9, 3, 9, 9, 0, 1, 7, 7, e->w3f, n->act[2], p + o[5], nullptr, 3136, 7 * 64, 64, 1, 0);
+    c3.bits_out = e->bits[2];
     DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 2>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
@@ -439,7 +444,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   {
     TmaGemmArgs g{};
     g.M = nb; g.N_total = 512; g.KB = 49; g.out = n->feat; g.out_ld = 512; g.bias = p + o[7]; g.mask_src = nullptr;
-    g.bias_grad = nullptr; g.bias_mod = 1;
+    g.bias_grad = nullptr; g.bias_mod = 1; g.bits_in = nullptr;
     DRL_TRY((launch_tma_gemm<256, EPI_BIAS_RELU_F32>("fc_fwd", n->act[2], nb, 3136, e->wff, 512, g, st)));
   }
   return DRL_OK;
@@ -492,6 +497,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     a.M = nb; a.N_total = 3136; a.KB = 8; a.out = n->dact[2]; a.out_ld = 3136; a.bias = nullptr;
     a.mask_src = (const __nv_bfloat16*)n->act[2];
     a.bias_grad = g + o[5]; a.bias_mod = 64;          // conv3 bias gradient = column sums of dact3 (column % 64)
+    a.bits_in = g_debug_flags[1] ? e->bits[2] : nullptr;   // bits are written by the TMA conv3 forward
     DRL_TRY((launch_tma_gemm<256, EPI_MASK_BF16>("fc_dgrad", n->dpre, nb, 512, e->wfd, 3136, a, st)));
   }
   // ---- conv3 (its bias gradient was accumulated by the fc data-gradient epilogue)
@@ -519,6 +525,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       // dY3 zero-padded by 2 (TMA out-of-bounds fill) to 11x11; output rows y*11 + x over the 9x9 input grid
       TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
       c.bias_grad = g + o[3]; c.bias_mod = 64;       // conv2 bias gradient
+      c.bits_in = e->bits[1];
       DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 2>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
@@ -551,6 +558,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       // dY2 zero-padded by 1 to 11x11; GEMM rows u*11 + v over the 10x10 grid of 2x2 output blocks
       TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
       c.bias_grad = g + o[1]; c.bias_mod = 32;       // conv1 bias gradient
+      c.bits_in = e->bits[0];
       DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 2>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));

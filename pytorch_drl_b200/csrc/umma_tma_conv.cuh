@@ -45,6 +45,8 @@ struct TmaConvArgs {
   void* out; const float* bias; float scale; const __nv_bfloat16* mask_src;
   int64_t out_sample_pitch; int out_row_pitch; int out_C; int osy, osx; int classes;
   int use_base_offset;    // debug switch for the descriptor base-offset field
+  uint32_t* bits_out;     // EPI_BIAS_RELU: bit (e & 31) of word (e >> 5) = (out[e] > 0) for output element index e
+  const uint32_t* bits_in; // EPI_MASK: the same bit layout for the tensor shaped like `out` (replaces mask_src reads)
   float* bias_grad;       // EPI_MASK: += column sums of the produced gradient, index = column % bias_mod (or nullptr)
   int bias_mod;
 };
@@ -155,12 +157,10 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
         const bool ok = y < args.OH && x < args.OW;
         const int64_t ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(y * args.osy) * args.out_row_pitch +
                              (int64_t)(x * args.osx) * args.out_C;
-        uint4 mk[N <= 64 ? N / 8 : 1];
-        if (EPI == EPI_MASK_BF16 && N <= 64 && ok) {
+        uint32_t mbits[N / 32];                           // ReLU mask bits of this row, one word per 32-column chunk
+        if (EPI == EPI_MASK_BF16 && ok) {
 #pragma unroll
-          for (int ch = 0; ch < N / 32; ++ch)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) mk[ch * 4 + q] = ldg_v4(args.mask_src + ooff + coff(ch) + 8 * q);
+          for (int ch = 0; ch < N / 32; ++ch) mbits[ch] = __ldg(args.bits_in + ((ooff + coff(ch)) >> 5));
         }
         mbar_wait(tfull + acc, (it >> 1) & 1);
         tc_fence_after();
@@ -176,26 +176,28 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
           if (ok) {
             if (EPI == EPI_BIAS_RELU_BF16) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
+              uint32_t bits = 0;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float f[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i) {
                   f[i] = fmaxf(fmaf(__uint_as_float(rr[8 * q + i]), args.scale, sBias[ch * 32 + 8 * q + i]), 0.f);
+                  bits |= (f[i] > 0.f ? 1u : 0u) << (8 * q + i);
+                }
                 reinterpret_cast<uint4*>(o)[q] =
                     make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
               }
+              if (args.bits_out) args.bits_out[(ooff + ch * 32) >> 5] = bits;
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 mv = N <= 64 ? mk[ch * 4 + q] : ldg_v4(args.mask_src + ooff + coff(ch) + 8 * q);
-                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
                 uint32_t pk[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float lo = (mw[i] & 0x00007fffu) ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
-                  const float hi2 = (mw[i] & 0x7fff0000u) ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
+                  const float lo = (mbits[ch] >> (8 * q + 2 * i)) & 1u ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
+                  const float hi2 = (mbits[ch] >> (8 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
                   pk[i] = pack_bf16x2(lo, hi2);
                   rr[8 * q + 2 * i] = __float_as_uint(lo);
                   rr[8 * q + 2 * i + 1] = __float_as_uint(hi2);

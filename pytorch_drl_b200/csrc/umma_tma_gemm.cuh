@@ -34,6 +34,7 @@ struct TmaGemmArgs {
   int out_ld;
   const float* bias;           // EPI_BIAS_RELU_F32
   const __nv_bfloat16* mask_src;   // EPI_MASK_BF16 (same layout as out)
+  const uint32_t* bits_in;     // EPI_MASK_BF16: bit (e & 31) of word (e >> 5) = (act[e] > 0), e = m*out_ld + n
   float* bias_grad;            // EPI_MASK_BF16: += column sums of the produced gradient at index column % bias_mod
   int bias_mod;
 };
@@ -169,15 +170,27 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
           } else {
             const int64_t off = (int64_t)m * args.out_ld + n;
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + off;
+            uint32_t mb;                                   // ReLU mask of these 32 columns, 1 bit per element
+            if (args.bits_in) {
+              mb = __ldg(args.bits_in + (off >> 5));
+            } else {                                       // fallback: derive it from the bf16 activation itself
+              mb = 0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 mv = ldg_v4(args.mask_src + off + 8 * q);
+                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  mb |= ((mw[i] & 0x00007fffu) ? 1u : 0u) << (8 * q + 2 * i) | ((mw[i] & 0x7fff0000u) ? 1u : 0u) << (8 * q + 2 * i + 1);
+              }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 mv = ldg_v4(args.mask_src + off + 8 * q);
-              const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
               uint32_t pk[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float lo = (mw[i] & 0x00007fffu) ? __uint_as_float(r[8 * q + 2 * i]) : 0.f;
-                const float hi2 = (mw[i] & 0x7fff0000u) ? __uint_as_float(r[8 * q + 2 * i + 1]) : 0.f;
+                const float lo = (mb >> (8 * q + 2 * i)) & 1u ? __uint_as_float(r[8 * q + 2 * i]) : 0.f;
+                const float hi2 = (mb >> (8 * q + 2 * i + 1)) & 1u ? __uint_as_float(r[8 * q + 2 * i + 1]) : 0.f;
                 pk[i] = pack_bf16x2(lo, hi2);
                 r[8 * q + 2 * i] = __float_as_uint(lo);
                 r[8 * q + 2 * i + 1] = __float_as_uint(hi2);

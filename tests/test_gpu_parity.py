@@ -430,3 +430,42 @@ def test_rnd_learn_wrapper_semantics():
     np.random.seed(0)
     rnd.learn(mb)                                   # now 5 >= 4: keeps int(8/32 * 16) = 4 rows and updates
     assert not tc.equal(rnd.student_params, p0) and rnd.adam_steps == 1
+
+
+def test_alternative_bf16_engines_stay_in_parity():
+    """The cp.async row-gather conv kernels and the TMA shifted-descriptor conv wgrad kernels are kept
+    behind drl_debug_set (they measured slower or equal): they must keep producing the same gradients."""
+    from pytorch_drl_b200 import _lib, ops
+    from pytorch_drl_b200.algos import RolloutStorage
+    L = _lib.lib()
+    A, rk, rw = 6, ['extrinsic'], {'extrinsic': 1.0}
+    n_envs, T, B = 3, 16, 8
+    params, raws, rollouts, credit = _ppo_case(A, rk, n_envs, T, B)
+    st = RolloutStorage(n_envs, T, rk, dev())
+    d = st.as_dict()
+    for e in range(n_envs):
+        st.load_env(e, raws[e]['observations'], raws[e]['actions'], raws[e]['rewards'], raws[e]['dones'])
+        d['logprobs'][e, :T] = cu(rollouts[e]['logprobs'])
+        for k in rk:
+            for name in ('advantages', 'vpreds', 'vtargs'):
+                d[name][k][e, :T] = cu(rollouts[e][name][k])
+    rs = np.random.RandomState(9)
+    blocks = [rs.permutation(T)[:B] for _ in range(n_envs)]
+    rows = cu(np.concatenate([b + e * st.Tp for e, b in enumerate(blocks)]).astype(np.int64))
+    hp = po.Hyper(rw, 0.1, 0.01, 0.5, False, True)
+    _, ref_g = po.minibatch_losses_and_grads(params, [po.slice_env(rollouts[e], blocks[e]) for e in range(n_envs)], hp)
+    hyper = ops.make_hyper(A, [1.0], 0.1, 0.01, 0.5, False, True)
+    batch = ops.make_batch(d['actions'], d['logprobs'], [d['advantages']['extrinsic']], [d['vpreds']['extrinsic']],
+                           [d['vtargs']['extrinsic']])
+    try:
+        for flags in ((0, 0), (1, 1)):          # (tma conv fwd/dgrad kernels, tma conv wgrad kernels)
+            L.drl_debug_set(1, flags[0])
+            L.drl_debug_set(2, flags[1])
+            eng, _ = _build('bf16', A, rk, n_envs * B)
+            eng.ppo_step(d['observations'], rows, batch, hyper)
+            gv = eng.named_views(eng.grads)
+            for k in po.param_keys(rk):
+                assert rel_l2(gv[k].cpu().numpy(), ref_g[k]) < TOL['bf16']['grad'], (flags, k)
+    finally:
+        L.drl_debug_set(1, 1)
+        L.drl_debug_set(2, 0)
