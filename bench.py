@@ -32,6 +32,12 @@ MACS = {  # algorithmic multiply-accumulates per sample
     'conv1_wgrad': 3276800, 'conv2_wgrad': 2654208, 'conv3_wgrad': 1806336, 'fc_wgrad': 1605632,
     'conv2_dgrad': 2654208, 'conv3_dgrad': 1806336, 'fc_dgrad': 1605632,
 }
+BYTES = {  # algorithmic HBM bytes per sample: operands read once + result written once
+    'conv1_fwd': 28224 + 25600, 'conv1_wgrad': 28224 + 25600,
+    'conv2_fwd': 25600 + 10368, 'conv2_dgrad': 10368 + 25600, 'conv2_wgrad': 25600 + 10368,
+    'conv3_fwd': 10368 + 6272, 'conv3_dgrad': 6272 + 10368, 'conv3_wgrad': 10368 + 6272,
+    'fc_fwd': 6272 + 2048, 'fc_dgrad': 1024 + 6272, 'fc_wgrad': 6272 + 1024,
+}
 STEP_FLOPS_PER_SAMPLE = 49525760          # fwd 18.69 + bwd 30.83 MFLOP (A=6, K=1), SURVEY §8d
 
 
@@ -281,12 +287,28 @@ def main():
     if dom:
         flops = 2.0 * MACS[dom] * nb
         ach = flops / (sites[dom][0] * 1e-3) / 1e12
+        gbs = BYTES[dom] * nb / (sites[dom][0] * 1e-3) / 1e9
+        # report against the roofline that binds first for this kernel (higher fraction); the other one is kept
+        # beside it.  `traffic` = dram read+write bytes per launch from the committed ncu --set full capture of
+        # the same kernel at the same size (profiles/r01_kernel_traffic.json), null if the size differs.
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'r01_kernel_traffic.json')
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get('samples_per_launch') == nb and dom in tj.get('kernels', {}):
+                traffic = tj['kernels'][dom]['dram_bytes']
         roof = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                'frac': ach / pk['tflops'], 'traffic': None, 'peak_source': pk['src'],
+                'frac': ach / pk['tflops'], 'traffic': traffic, 'peak_source': pk['src'],
+                'algorithmic_bytes_per_launch': BYTES[dom] * nb, 'algorithmic_flops_per_launch': flops,
+                'other': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm']},
                 'avg_launch_ms': sites[dom][0], 'kernel_share_of_step': sites[dom][0] / ms_per_step,
                 'step_achieved': STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12,
                 'step_frac': STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12 / pk['tflops'],
                 'per_kernel_ms': per_kernel}
+        if roof['other']['frac'] > roof['frac']:
+            o = roof['other']
+            roof['other'] = {k: roof[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
+            roof.update(o)
     cpu = None
     if world == 1 and not args.no_cpu:
         rate, n, threads, el = cpu_reference_step_rate(8, args.cpu_seconds)

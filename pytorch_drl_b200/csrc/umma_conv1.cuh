@@ -79,6 +79,12 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
   return v;
 }
 
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
 // 8 uint8 -> 8 fp16 holding 1024 + b (bytes become the mantissa of 0x6400 = 1024.0): one PRMT per pair.
 // The constant 1024 * sum_k W[n][k] this adds to every accumulator is folded into the bias
 // (conv1_bias_eff_kernel), so the forward conversion costs 4 instructions per 8 pixels.
@@ -267,6 +273,172 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// forward, A operand in TENSOR MEMORY.  The im2col row of an output position is 8 runs of 32 contiguous
+// bytes of the staged frame rows, so one converter thread owns one tile row (= one TMEM lane): it reads its
+// runs with LDS.128, turns them into 1024-biased fp16 pairs and writes them with tcgen05.st into the
+// [128 lanes x 128 columns] A buffer; the MMA then takes A from TMEM and only the 16 KB of weights from
+// shared memory.  Per tile the shared-memory traffic drops from ~176 KB (raw read + swizzled fp16 write +
+// operand read) to ~72 KB, and the generic->async proxy fence disappears from the converter path.
+// TMEM columns: [0,64) two accumulators, [128,256) and [256,384) the two A buffers (512 allocated).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kC1tNR = 4;                                   // raw staging buffers (tiles in flight)
+constexpr int kC1FwdTsSmem = 16384 /*B*/ + kC1tNR * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
+
+__global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_ts_kernel(const Conv1Args args) {
+  using namespace umma;
+  constexpr int NP = 32 * kC1ProdWarps;          // converter threads
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sRaw = smem + 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1tNR * 2 * kC1SegBytes);
+  uint64_t* full = bars;            // [2] one per TMEM A buffer
+  uint64_t* empty = bars + 2;       // [2]
+  uint64_t* tfull = bars + 4;       // [2]
+  uint64_t* tempty = bars + 6;      // [2]
+  uint64_t* raw_full = bars + 8;    // [kC1tNR]
+  uint64_t* raw_empty = bars + 8 + kC1tNR;
+  uint64_t* b_full = bars + 8 + 2 * kC1tNR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * kC1tNR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = args.nb * 400;
+  const int num_tiles = (M + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < kC1tNR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5 + kC1ProdWarps) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, 16384);
+      tma_bulk_g2s(sB, args.bpack, 16384, b_full);
+      uint32_t j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t buf = j % kC1tNR;
+        mbar_wait(raw_empty + buf, ((j / kC1tNR) & 1) ^ 1);
+        C1Seg s0, s1;
+        c1_segment(tile * 128, 0, args.nb, args.row_idx, s0);
+        c1_segment(tile * 128, 1, args.nb, args.row_idx, s1);
+        mbar_arrive_expect_tx(raw_full + buf, s0.bytes + s1.bytes);
+        uint8_t* dst = sRaw + buf * 2 * kC1SegBytes;
+        if (s0.valid) tma_bulk_g2s(dst, args.obs + s0.src_off, s0.bytes, raw_full + buf);
+        if (s1.valid) tma_bulk_g2s(dst + kC1SegBytes, args.obs + s1.src_off, s1.bytes, raw_full + buf);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 5) {
+    // ================= converters: one tile row (TMEM lane) per thread, half of K per warp ==============
+    const int quarter = warp & 3;                 // the TMEM lanes this warp may access
+    const int khalf = (warp - 5) >> 2;            // ky in [4*khalf, 4*khalf + 4)
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t buf = j % kC1tNR;
+      const int rb = c1_row_base(tile * 128, row, args.nb);
+      const uint32_t ab = j & 1;
+      mbar_wait(raw_full + buf, (j / kC1tNR) & 1);
+      const uint32_t src = smem_u32(sRaw + buf * 2 * kC1SegBytes) + (uint32_t)max(rb, 0) + (uint32_t)(khalf * 4 * kC1RowBytes);
+      mbar_wait(empty + ab, ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t t_a = tmem_base + t_lane + 128 + ab * 128 + khalf * 64;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t r[32];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+          if (rb >= 0) {
+            v0 = lds_v4(src + (uint32_t)((h2 * 2 + kk) * kC1RowBytes));
+            v1 = lds_v4(src + (uint32_t)((h2 * 2 + kk) * kC1RowBytes) + 16);
+          }
+          const uint4 a = u8x8_to_f16x8_biased(make_uint2(v0.x, v0.y)), b = u8x8_to_f16x8_biased(make_uint2(v0.z, v0.w));
+          const uint4 c = u8x8_to_f16x8_biased(make_uint2(v1.x, v1.y)), d = u8x8_to_f16x8_biased(make_uint2(v1.z, v1.w));
+          uint32_t* o = r + kk * 16;
+          o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+          o[8] = c.x; o[9] = c.y; o[10] = c.z; o[11] = c.w; o[12] = d.x; o[13] = d.y; o[14] = d.z; o[15] = d.w;
+        }
+        tmem_st_32x32b_x32(t_a + h2 * 32, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(full + ab);
+      mbar_arrive(raw_empty + buf);
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(0u, 128, 32, 0, 0);     // fp16 operands
+      constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
+      const uint32_t b_lo0 = desc_lo(smem_u32(sB), 0);
+      mbar_wait(b_full, 0);
+      uint32_t j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t acc = j & 1, ab = j & 1;
+        mbar_wait(tempty + acc, ((j >> 1) & 1) ^ 1);
+        mbar_wait(full + ab, (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_a = tmem_base + 128 + ab * 128;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t b_lo = b_lo0 + (i >> 2) * (4096 >> 4) + (i & 3) * 2;
+          if (i == 0) mma_f16_ts<false>(tmem_base + acc * 32, t_a, b_lo, hi, idesc);
+          else mma_f16_ts<true>(tmem_base + acc * 32, t_a + i * 8, b_lo, hi, idesc);
+        }
+        mma_commit(empty + ab);
+        mma_commit(tfull + acc);
+      }
+    }
+    __syncwarp();
+  } else {
+    float bias[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias[i] = __ldg(args.bias + i);
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t acc = j & 1;
+      const int m = tile * 128 + threadIdx.x;
+      mbar_wait(tfull + acc, (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(tempty + acc);
+      if (m < M) {
+        uint4* o = reinterpret_cast<uint4*>(args.out + (int64_t)m * 32);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            f[i] = fmaxf(fmaf(__uint_as_float(r[8 * q + i]), args.scale, bias[8 * q + i]), 0.f);
+            bits |= (f[i] > 0.f ? 1u : 0u) << (8 * q + i);
+          }
+          o[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+        args.mask_bits[m] = bits;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace drl
 
 namespace drl {
@@ -281,12 +453,6 @@ constexpr int kC1wStage = 4 * 4096 + 2048;                 // 18 KB
 constexpr int kC1wRaw = 2 * kC1SegBytes + 8192;            // frames (2 segments) + dY rows
 constexpr int kC1wNR = 2;                                   // raw buffers of the wgrad kernel
 constexpr int kC1WgradSmem = 8 * kC1wStage + kC1wNR * kC1wRaw + 256 + 1024;
-
-__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-  return v;
-}
 
 __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1Args args) {
   using namespace umma;

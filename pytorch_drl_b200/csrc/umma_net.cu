@@ -294,7 +294,8 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 //     128B swizzle is applied to the absolute smem address bits, so shifted starts need base offset 0.
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
 // [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
-int g_debug_flags[8] = {0, 1, 0, 0, 0, 0, 0, 0};
+// [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
+int g_debug_flags[8] = {0, 1, 0, 1, 0, 0, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -311,7 +312,7 @@ static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64
   return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
 }
 
-template <int N, int EPI, int NR>
+template <int N, int EPI, int NR, int NACC, int NEPI>
 static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st) {
   ProfileScope prof(site, st);
   CUtensorMap tm;
@@ -320,20 +321,21 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   a.box_bytes = BW * (BH / a.planes) * 128;
   const int tap_rows = (a.KB - 1) / a.KBX;               // last tap row
   const int max_shift = (a.planes == 2 ? tap_rows / 2 : tap_rows) * a.SHIFT_RW + (a.KBX - 1);
-  a.plane_bytes = ((a.MT * 128 + max_shift) * 128 + 1023) / 1024 * 1024;
-  if (a.plane_bytes < (a.box_bytes + 1023) / 1024 * 1024) a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   a.raw_buf_bytes = a.plane_bytes * a.planes;
+  const int window = (a.MT * 128 + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
+  a.slack_bytes = window > a.plane_bytes ? (window - a.plane_bytes + 1023) / 1024 * 1024 : 0;
   a.use_base_offset = g_debug_flags[0];
-  auto kern = tma_conv_kernel<N, EPI, NR>;
-  const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR);
+  auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI>;
+  const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
+  if (smem > 227 * 1024) return DRL_ERR_BAD_ARG;
   static int configured = 0;
   if (configured < smem) {
     DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  const int per_sm = (NR == 2 && 2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;   // co-resident CTAs by shared memory
-  const int ctas = per_sm * sm_count();
-  kern<<<nb < ctas ? nb : ctas, 192, smem, st>>>(tm, a);
+  const int ctas = sm_count();
+  kern<<<nb < ctas ? nb : ctas, 32 * (4 * NEPI + 2), smem, st>>>(tm, a);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -417,10 +419,14 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     static bool configured = false;
     if (!configured) {
       DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1FwdSmem));
+      DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1FwdTsSmem));
       configured = true;
     }
     const int tiles = (nb * 400 + 127) / 128;
-    conv1_fwd_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdSmem, st>>>(a1);
+    if (g_debug_flags[3])   // A operand staged in tensor memory (tcgen05.st + TS-form MMA)
+      conv1_fwd_ts_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdTsSmem, st>>>(a1);
+    else
+      conv1_fwd_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdSmem, st>>>(a1);
     DRL_LAUNCH_CHECK();
   }
   RowGatherArgs a2 = fwd_args(nb, n->act[0], nullptr, 81, 9, 20, 20, 32, 2, 8, 2, e->w2f, n->act[1], p + o[3], 1.f, 64);
@@ -429,7 +435,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     // stride 2), so tap row ky reads plane ky&1 shifted by (ky>>1)*10 + half and the GEMM rows are oy*10 + ox
     TmaConvArgs c2 = tma_conv_args(8, 2, 10, 10, 0, 1, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
     c2.planes = 2; c2.bits_out = e->bits[1];
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 4, 4, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
   }
@@ -437,7 +443,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   if (g_debug_flags[1]) {
     TmaConvArgs c3 = tma_conv_args(9, 3, 9, 9, 0, 1, 7, 7, e->w3f, n->act[2], p + o[5], nullptr, 3136, 7 * 64, 64, 1, 0);
     c3.bits_out = e->bits[2];
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 2>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 6, 4, 2>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
   }
@@ -526,7 +532,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
       c.bias_grad = g + o[3]; c.bias_mod = 64;       // conv2 bias gradient
       c.bits_in = e->bits[1];
-      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 2>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
+      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
     }
@@ -559,7 +565,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
       c.bias_grad = g + o[1]; c.bias_mod = 32;       // conv1 bias gradient
       c.bits_in = e->bits[0];
-      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 2>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
+      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 2>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
     }

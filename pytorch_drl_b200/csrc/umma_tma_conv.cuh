@@ -35,9 +35,10 @@ struct TmaConvArgs {
   int pad;                // TMA start coordinate = (-pad, -pad)
   int planes;             // 1, or 2: stride-2 conv, even / odd input rows staged as separate planes (tap row ty
                           //    reads plane ty & 1 shifted by (ty >> 1) * SHIFT_RW + tx)
-  int plane_bytes;        // smem bytes of one plane (multiple of 1024)
+  int plane_bytes;        // smem pitch of one plane (box bytes rounded up to 1024)
   int box_bytes;          // bytes one sample's TMA box writes
-  int raw_buf_bytes;      // staging buffer size (>= 128*MT + max shift rows, multiple of 1024)
+  int raw_buf_bytes;      // staging buffer pitch (planes * plane_bytes, multiple of 1024)
+  int slack_bytes;        // readable tail after the last staging buffer (window over-read of discarded rows)
   int MT;                 // M tiles (of 128 GEMM rows) per sample
   int OH, OW;             // valid output grid
   const void* bpack;      // [KB][N x 64] swizzled weight tile images
@@ -51,44 +52,53 @@ struct TmaConvArgs {
   int bias_mod;
 };
 
+// One CTA per SM: NR staged samples in flight, NACC accumulators in TMEM, NEPI epilogue warpgroups that take
+// tiles round-robin.  The staging buffers are packed at the TMA box size: the 128-row MMA window of a tap
+// may read past its sample into the next buffer (or the `slack_bytes` tail) — those rows belong to grid
+// positions that are discarded, and a GEMM row only ever influences its own output row.
 template <int N>
-constexpr int tma_conv_smem(int KB, int raw_buf_bytes, int NR) { return KB * N * 128 + NR * raw_buf_bytes + 1280 + 1024; }
+constexpr int tma_conv_smem(int KB, int raw_buf_bytes, int NR, int slack) {
+  return KB * N * 128 + NR * raw_buf_bytes + slack + 1280 + 1024;
+}
 
-template <int N, int EPI, int NR>
-__global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                          const TmaConvArgs args) {
+template <int N, int EPI, int NR, int NACC, int NEPI>
+__global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                           const TmaConvArgs args) {
   using namespace umma;
   constexpr int B_BYTES = N * 128;
-  constexpr int TMEM_COLS = 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 256;
+  constexpr int TMEM_COLS = NACC * N <= 64 ? 64 : NACC * N <= 128 ? 128 : NACC * N <= 256 ? 256 : 512;
+  static_assert(NACC * N <= 512, "accumulators exceed tensor memory");
+  constexpr int W_MMA = 4 * NEPI, W_TMA = 4 * NEPI + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                         // KB weight tiles, resident
   uint8_t* sRaw = smem + args.KB * B_BYTES;                   // NR staged samples
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + NR * args.raw_buf_bytes);
-  uint64_t* raw_full = bars;            // [NR]
-  uint64_t* raw_empty = bars + NR;      // [NR]
-  uint64_t* tfull = bars + 2 * NR;      // [2]
-  uint64_t* tempty = bars + 2 * NR + 2; // [2]
-  uint64_t* b_full = bars + 2 * NR + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NR + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + NR * args.raw_buf_bytes + args.slack_bytes);
+  uint64_t* raw_full = bars;                    // [NR]
+  uint64_t* raw_empty = bars + NR;              // [NR]
+  uint64_t* tfull = bars + 2 * NR;              // [NACC]
+  uint64_t* tempty = bars + 2 * NR + NACC;      // [NACC]
+  uint64_t* b_full = bars + 2 * NR + 2 * NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NR + 2 * NACC + 1);
+  static_assert((2 * NR + 2 * NACC + 2) * 8 <= 256, "barrier block overflows");
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (EPI != EPI_MASK_BF16 && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int a = 0; a < NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
-  if (warp == 5 && lane == 0) tma_prefetch_desc(&tmap);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == W_TMA && lane == 0) tma_prefetch_desc(&tmap);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == W_TMA) {
     if (lane == 0) {
       // weights: resident for the whole kernel
       mbar_arrive_expect_tx(b_full, (uint32_t)(args.KB * B_BYTES));
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
+  } else if (warp == W_MMA) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(1u, 128, N, 0, 0);
       constexpr uint32_t hi0 = desc_hi(1024, LAYOUT_SW128);
@@ -116,8 +126,8 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
         mbar_wait(raw_full + buf, (j / NR) & 1);
         const uint32_t raw_addr = smem_u32(sRaw + buf * args.raw_buf_bytes);
         for (int mt = 0; mt < args.MT; ++mt, ++it) {
-          const uint32_t acc = it & 1;
-          mbar_wait(tempty + acc, ((it >> 1) & 1) ^ 1);
+          const uint32_t acc = it % NACC;
+          mbar_wait(tempty + acc, ((it / NACC) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * N;
           int ty = 0, tx = 0;
@@ -148,11 +158,13 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
     float colacc[N / 32];
 #pragma unroll
     for (int ch = 0; ch < N / 32; ++ch) colacc[ch] = 0.f;
+    const int wg = warp >> 2, trow = threadIdx.x & 127;
     uint32_t it = 0;
     for (int b = blockIdx.x; b < args.nb; b += gridDim.x) {
       for (int mt = 0; mt < args.MT; ++mt, ++it) {
-        const uint32_t acc = it & 1;
-        const int r = mt * 128 + threadIdx.x;
+        if (NEPI > 1 && (int)(it % NEPI) != wg) continue;
+        const uint32_t acc = it % NACC;
+        const int r = mt * 128 + trow;
         const int y = r / args.RW, x = r - y * args.RW;
         const bool ok = y < args.OH && x < args.OW;
         const int64_t ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(y * args.osy) * args.out_row_pitch +
@@ -162,12 +174,12 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
 #pragma unroll
           for (int ch = 0; ch < N / 32; ++ch) mbits[ch] = __ldg(args.bits_in + ((ooff + coff(ch)) >> 5));
         }
-        mbar_wait(tfull + acc, (it >> 1) & 1);
+        mbar_wait(tfull + acc, (it / NACC) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < N / 32; ++ch) {
           uint32_t rr[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * N + ch * 32, rr);
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * N + ch * 32, rr);
           tmem_ld_wait();
           if (ch == N / 32 - 1) {
             tc_fence_before();
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(192, (NR == 2 ? 2 : 1)) tma_conv_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }

@@ -458,9 +458,11 @@ def test_alternative_bf16_engines_stay_in_parity():
     batch = ops.make_batch(d['actions'], d['logprobs'], [d['advantages']['extrinsic']], [d['vpreds']['extrinsic']],
                            [d['vtargs']['extrinsic']])
     try:
-        for flags in ((0, 0), (1, 1)):          # (tma conv fwd/dgrad kernels, tma conv wgrad kernels)
+        # (tma conv fwd/dgrad kernels, tma conv wgrad kernels, conv1 forward A operand in TMEM)
+        for flags in ((0, 0, 0), (1, 1, 1)):
             L.drl_debug_set(1, flags[0])
             L.drl_debug_set(2, flags[1])
+            L.drl_debug_set(3, flags[2])
             eng, _ = _build('bf16', A, rk, n_envs * B)
             eng.ppo_step(d['observations'], rows, batch, hyper)
             gv = eng.named_views(eng.grads)
@@ -469,3 +471,4 @@ def test_alternative_bf16_engines_stay_in_parity():
     finally:
         L.drl_debug_set(1, 1)
         L.drl_debug_set(2, 0)
+        L.drl_debug_set(3, 1)
