@@ -96,6 +96,7 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// WARP-COLLECTIVE (all 32 lanes converged; one elected lane issues) — see elect_one() below.
 // Split descriptor form for the issue loop: the high word (SBO, version, swizzle) is a constant of the
 // kernel, the low word is (address >> 4) | LBO << 16 and advances by plain 32-bit adds, so one MMA
 // costs ~4 instructions of the single issuing thread instead of ~20.
@@ -110,18 +111,20 @@ __device__ __forceinline__ void mma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uin
                                              uint32_t idesc) {
   if (ACC) {
     asm volatile(
-        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p, e;\n\t"
         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
         "setp.eq.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p, e;\n\t"
         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
         "setp.ne.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   }
@@ -133,18 +136,20 @@ template <bool ACC>
 __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
   if (ACC) {
     asm volatile(
-        "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .b64 db;\n\t.reg .pred p, e;\n\t"
         "mov.b64 db, {%2, %3};\n\t"
         "setp.eq.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .b64 db;\n\t.reg .pred p, e;\n\t"
         "mov.b64 db, {%2, %3};\n\t"
         "setp.ne.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   }
@@ -164,9 +169,23 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before).
+// One lane of the (converged) warp.  MMA-issuing warps keep ALL lanes in the loop and elect only around the
+// tcgen05 instructions (inside mma_f16_lohi / mma_f16_ts / mma_commit): addresses and descriptors then stay warp-uniform for the compiler
+// (uniform registers feed UTCHMMA directly); a loop run under `if (lane == 0)` instead makes every operand a
+// per-thread value and costs an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// All previously issued MMAs of the elected lane arrive on `bar` when complete (implies fence::before).
+// WARP-COLLECTIVE like the mma_* wrappers: call with all 32 lanes converged.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive columns (one fp32 row chunk per thread).
@@ -254,6 +273,27 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     }
   }
   return v[0];
+}
+
+// ---- ReLU mask words ------------------------------------------------------------------------------------------
+// One 32-bit word per 32 consecutive output elements (word index = element index >> 5).  The bit of
+// element k (0..31) inside its word sits at relu_bit_pos(k): elements are produced as bf16x2 pairs, pair i =
+// elements (2i, 2i+1), and  (pair + 0x7FFF7FFF)  raises bit 15 / bit 31 exactly when the low / high bf16 (both
+// non-negative after the ReLU) is non-zero, so the producer needs 3 integer ops per PAIR:
+//     acc = (acc >> 1) | ((pair_i + 0x7FFF7FFF) & 0x80008000)      for i = 15 .. 0
+// which leaves element 2i at bit 15 - i and element 2i + 1 at bit 31 - i.
+__host__ __device__ constexpr int relu_bit_pos(int k) { return ((k & 1) ? 31 : 15) - (k >> 1); }
+__device__ __forceinline__ uint32_t relu_bits_from_pairs(const uint32_t (&w)[16]) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 15; i >= 0; --i) acc = (acc >> 1) | ((w[i] + 0x7FFF7FFFu) & 0x80008000u);
+  return acc;
+}
+// {lo, hi} -> bf16x2 with the ReLU folded into the conversion (negative -> +0)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

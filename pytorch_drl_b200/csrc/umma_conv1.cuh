@@ -23,7 +23,7 @@ struct Conv1Args {
   const float* bias;         // fwd: [32] EFFECTIVE bias = b - 1024 * scale * sum_k fp16(W[n][k]) (operands hold 1024 + pixel)
   float scale;               // float32(1/255)
   __nv_bfloat16* out;        // fwd: act1 [nb*400, 32]
-  uint32_t* mask_bits;       // fwd: bit c of word m = (act1[m][c] > 0): the ReLU mask conv2's data gradient needs
+  uint32_t* mask_bits;       // fwd: ReLU mask word of position m (umma.cuh relu_bit_pos): what conv2's data gradient needs
   const __nv_bfloat16* dy;   // wgrad: dY1 [nb*400, 32]
   float* gw;                 // wgrad: fp32 [32][4][8][8]
 };
@@ -112,6 +112,20 @@ __device__ __forceinline__ uint4 u8x8_to_bf16x8(uint2 w) {
   o.z = __byte_perm(__float_as_uint(f[4]), __float_as_uint(f[5]), 0x7632);
   o.w = __byte_perm(__float_as_uint(f[6]), __float_as_uint(f[7]), 0x7632);
   return o;
+}
+
+// conv1 epilogue of one output position: relu(acc * (1/255) + bias) -> 32 bf16 (one 64-byte row) + its ReLU mask word
+__device__ __forceinline__ void c1_store_row(const uint32_t (&r)[32], const float (&bias)[32], float scale,
+                                             __nv_bfloat16* out_row, uint32_t* bits_dst) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    pk[i] = umma::pack_bf16x2_relu(fmaf(__uint_as_float(r[2 * i]), scale, bias[2 * i]),
+                                   fmaf(__uint_as_float(r[2 * i + 1]), scale, bias[2 * i + 1]));
+  uint4* o = reinterpret_cast<uint4*>(out_row);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) o[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  *bits_dst = umma::relu_bits_from_pairs(pk);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
       mbar_arrive(raw_empty + buf);
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_f16(0u, 128, 32, 0, 0);     // fp16 operands
       constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
       const uint32_t a_lo0 = desc_lo(smem_u32(sA), 0), b_lo0 = desc_lo(smem_u32(sB), 0);
@@ -248,21 +262,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(tempty + acc);
-      if (m < M) {
-        uint4* o = reinterpret_cast<uint4*>(args.out + (int64_t)m * 32);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[i] = fmaxf(fmaf(__uint_as_float(r[8 * q + i]), args.scale, bias[8 * q + i]), 0.f);
-            bits |= (f[i] > 0.f ? 1u : 0u) << (8 * q + i);
-          }
-          o[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        }
-        args.mask_bits[m] = bits;
-      }
+      if (m < M) c1_store_row(r, bias, args.scale, args.out + (int64_t)m * 32, args.mask_bits + m);
     }
   }
   tc_fence_before();
@@ -280,45 +280,53 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
 // [128 lanes x 128 columns] A buffer; the MMA then takes A from TMEM and only the 16 KB of weights from
 // shared memory.  Per tile the shared-memory traffic drops from ~176 KB (raw read + swizzled fp16 write +
 // operand read) to ~72 KB, and the generic->async proxy fence disappears from the converter path.
-// TMEM columns: [0,64) two accumulators, [128,256) and [256,384) the two A buffers (512 allocated).
+// TMEM columns: [0,128) four accumulators, then three 128-column A buffers (all 512 columns, one CTA per SM).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kC1tNR = 4;                                   // raw staging buffers (tiles in flight)
+constexpr int kC1tNA = 3;                                   // A buffers in tensor memory
+constexpr int kC1tNACC = 4;                                 // accumulators
+constexpr int kC1tEpiWG = 2;                                // epilogue warpgroups (tiles round-robin)
+constexpr int kC1tThreads = 32 * (4 * kC1tEpiWG + 1 + kC1ProdWarps + 1);
 constexpr int kC1FwdTsSmem = 16384 /*B*/ + kC1tNR * 2 * kC1SegBytes /*raw*/ + 256 + 1024;
 
-__global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_ts_kernel(const Conv1Args args) {
+__global__ void __launch_bounds__(kC1tThreads, 1) conv1_fwd_ts_kernel(const Conv1Args args) {
   using namespace umma;
   constexpr int NP = 32 * kC1ProdWarps;          // converter threads
+  constexpr int W_MMA = 4 * kC1tEpiWG, W_CONV = W_MMA + 1, W_TMA = W_CONV + kC1ProdWarps;
+  constexpr uint32_t ACC_COL = 0, A_COL = kC1tNACC * 32;   // tensor-memory columns: accumulators, then the A buffers
+  static_assert(A_COL + kC1tNA * 128 <= 512, "tensor memory budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;
   uint8_t* sRaw = smem + 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kC1tNR * 2 * kC1SegBytes);
-  uint64_t* full = bars;            // [2] one per TMEM A buffer
-  uint64_t* empty = bars + 2;       // [2]
-  uint64_t* tfull = bars + 4;       // [2]
-  uint64_t* tempty = bars + 6;      // [2]
-  uint64_t* raw_full = bars + 8;    // [kC1tNR]
-  uint64_t* raw_empty = bars + 8 + kC1tNR;
-  uint64_t* b_full = bars + 8 + 2 * kC1tNR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * kC1tNR);
+  uint64_t* full = bars;                         // [NA] A buffer written
+  uint64_t* empty = full + kC1tNA;               // [NA] A buffer consumed by the MMAs
+  uint64_t* tfull = empty + kC1tNA;              // [NACC]
+  uint64_t* tempty = tfull + kC1tNACC;           // [NACC]
+  uint64_t* raw_full = tempty + kC1tNACC;        // [NR]
+  uint64_t* raw_empty = raw_full + kC1tNR;       // [NR]
+  uint64_t* b_full = raw_empty + kC1tNR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  static_assert((2 * kC1tNA + 2 * kC1tNACC + 2 * kC1tNR + 2) * 8 <= 256, "barrier block");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = args.nb * 400;
   const int num_tiles = (M + 127) / 128;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int s = 0; s < kC1tNA; ++s) { mbar_init(full + s, NP); mbar_init(empty + s, 1); }
+    for (int a = 0; a < kC1tNACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
     for (int a = 0; a < kC1tNR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, NP); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5 + kC1ProdWarps) {
+  if (warp == W_TMA) {
     if (lane == 0) {
       mbar_arrive_expect_tx(b_full, 16384);
       tma_bulk_g2s(sB, args.bpack, 16384, b_full);
@@ -336,63 +344,63 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_ts_kernel(const Conv1
       }
     }
     __syncwarp();
-  } else if (warp >= 5) {
+  } else if (warp >= W_CONV) {
     // ================= converters: one tile row (TMEM lane) per thread, half of K per warp ==============
     const int quarter = warp & 3;                 // the TMEM lanes this warp may access
-    const int khalf = (warp - 5) >> 2;            // ky in [4*khalf, 4*khalf + 4)
+    const int khalf = (warp - W_CONV) >> 2;       // ky in [4*khalf, 4*khalf + 4)
     const int row = quarter * 32 + lane;
     const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-      const uint32_t buf = j % kC1tNR;
-      const int rb = c1_row_base(tile * 128, row, args.nb);
-      const uint32_t ab = j & 1;
+      const uint32_t buf = j % kC1tNR, ab = j % kC1tNA;
+      // rows past the end of the batch read row 0 of the staging buffer: their outputs are never stored
+      const int rb = max(c1_row_base(tile * 128, row, args.nb), 0);
+      const uint32_t src = smem_u32(sRaw + buf * 2 * kC1SegBytes) + (uint32_t)rb + (uint32_t)(khalf * 4 * kC1RowBytes);
       mbar_wait(raw_full + buf, (j / kC1tNR) & 1);
-      const uint32_t src = smem_u32(sRaw + buf * 2 * kC1SegBytes) + (uint32_t)max(rb, 0) + (uint32_t)(khalf * 4 * kC1RowBytes);
-      mbar_wait(empty + ab, ((j >> 1) & 1) ^ 1);
+      uint4 v[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[2 * q] = lds_v4(src + (uint32_t)(q * kC1RowBytes));
+        v[2 * q + 1] = lds_v4(src + (uint32_t)(q * kC1RowBytes) + 16);
+      }
+      mbar_wait(empty + ab, ((j / kC1tNA) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t t_a = tmem_base + t_lane + 128 + ab * 128 + khalf * 64;
+      const uint32_t t_a = tmem_base + t_lane + A_COL + ab * 128 + khalf * 64;
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
         uint32_t r[32];
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-          if (rb >= 0) {
-            v0 = lds_v4(src + (uint32_t)((h2 * 2 + kk) * kC1RowBytes));
-            v1 = lds_v4(src + (uint32_t)((h2 * 2 + kk) * kC1RowBytes) + 16);
-          }
-          const uint4 a = u8x8_to_f16x8_biased(make_uint2(v0.x, v0.y)), b = u8x8_to_f16x8_biased(make_uint2(v0.z, v0.w));
-          const uint4 c = u8x8_to_f16x8_biased(make_uint2(v1.x, v1.y)), d = u8x8_to_f16x8_biased(make_uint2(v1.z, v1.w));
-          uint32_t* o = r + kk * 16;
-          o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-          o[8] = c.x; o[9] = c.y; o[10] = c.z; o[11] = c.w; o[12] = d.x; o[13] = d.y; o[14] = d.z; o[15] = d.w;
+        for (int q = 0; q < 4; ++q) {
+          const uint4 w = v[4 * h2 + q];
+          const uint4 a = u8x8_to_f16x8_biased(make_uint2(w.x, w.y)), b = u8x8_to_f16x8_biased(make_uint2(w.z, w.w));
+          r[8 * q] = a.x; r[8 * q + 1] = a.y; r[8 * q + 2] = a.z; r[8 * q + 3] = a.w;
+          r[8 * q + 4] = b.x; r[8 * q + 5] = b.y; r[8 * q + 6] = b.z; r[8 * q + 7] = b.w;
         }
         tmem_st_32x32b_x32(t_a + h2 * 32, r);
       }
+      mbar_arrive(raw_empty + buf);                // the raw rows are in registers / tensor memory now
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(full + ab);
-      mbar_arrive(raw_empty + buf);
     }
-  } else if (warp == 4) {
-    if (lane == 0) {
+  } else if (warp == W_MMA) {
+    {
       constexpr uint32_t idesc = make_idesc_f16(0u, 128, 32, 0, 0);     // fp16 operands
       constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
       const uint32_t b_lo0 = desc_lo(smem_u32(sB), 0);
       mbar_wait(b_full, 0);
       uint32_t j = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-        const uint32_t acc = j & 1, ab = j & 1;
-        mbar_wait(tempty + acc, ((j >> 1) & 1) ^ 1);
-        mbar_wait(full + ab, (j >> 1) & 1);
+        const uint32_t acc = j % kC1tNACC, ab = j % kC1tNA;
+        mbar_wait(tempty + acc, ((j / kC1tNACC) & 1) ^ 1);
+        mbar_wait(full + ab, (j / kC1tNA) & 1);
         tc_fence_after();
-        const uint32_t t_a = tmem_base + 128 + ab * 128;
+        const uint32_t t_a = tmem_base + A_COL + ab * 128, t_d = tmem_base + ACC_COL + acc * 32;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint32_t b_lo = b_lo0 + (i >> 2) * (4096 >> 4) + (i & 3) * 2;
-          if (i == 0) mma_f16_ts<false>(tmem_base + acc * 32, t_a, b_lo, hi, idesc);
-          else mma_f16_ts<true>(tmem_base + acc * 32, t_a + i * 8, b_lo, hi, idesc);
+          if (i == 0) mma_f16_ts<false>(t_d, t_a, b_lo, hi, idesc);
+          else mma_f16_ts<true>(t_d, t_a + i * 8, b_lo, hi, idesc);
         }
         mma_commit(empty + ab);
         mma_commit(tfull + acc);
@@ -400,48 +408,33 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_ts_kernel(const Conv1
     }
     __syncwarp();
   } else {
+    // ================= epilogue warpgroups: tiles round-robin =========================================
+    const int wg = warp >> 2, trow = threadIdx.x & 127;
     float bias[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) bias[i] = __ldg(args.bias + i);
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-      const uint32_t acc = j & 1;
-      const int m = tile * 128 + threadIdx.x;
-      mbar_wait(tfull + acc, (j >> 1) & 1);
+      if ((int)(j % kC1tEpiWG) != wg) continue;
+      const uint32_t acc = j % kC1tNACC;
+      const int m = tile * 128 + trow;
+      mbar_wait(tfull + acc, (j / kC1tNACC) & 1);
       tc_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 32, r);
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ACC_COL + acc * 32, r);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(tempty + acc);
-      if (m < M) {
-        uint4* o = reinterpret_cast<uint4*>(args.out + (int64_t)m * 32);
-        uint32_t bits = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            f[i] = fmaxf(fmaf(__uint_as_float(r[8 * q + i]), args.scale, bias[8 * q + i]), 0.f);
-            bits |= (f[i] > 0.f ? 1u : 0u) << (8 * q + i);
-          }
-          o[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        }
-        args.mask_bits[m] = bits;
-      }
+      if (m < M) c1_store_row(r, bias, args.scale, args.out + (int64_t)m * 32, args.mask_bits + m);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
-
-}  // namespace drl
-
-namespace drl {
 
 // ---------------------------------------------------------------------------------------------------------
 // weight gradient:  dW1^T[kp=256 x co=32] += P[m x 256]^T * dY1[m x 32]   (both operands MN-major)
@@ -538,7 +531,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
         mbar_arrive(raw_empty + buf);
       }
     } else if (warp == 4) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, 32, 1, 1);   // bf16, MN-major A and B
         constexpr uint32_t a_hi = desc_hi(1024, LAYOUT_SW128), b_hi = desc_hi(512, LAYOUT_SW64);
         const uint32_t st_lo0 = desc_lo(smem_u32(sSt), 0);

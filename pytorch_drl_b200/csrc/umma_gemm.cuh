@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
       for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; ++j) mbar_arrive(full + (j % S));
     }
   } else if (warp == 4) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (all lanes stay converged; the mma_* wrappers elect one) =================
+    {
       constexpr uint32_t idesc = make_idesc_f16(SRC == SRC_U8 ? 0u : 1u, 128, N, 0, 0);
       constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
       const uint32_t a_lo0 = desc_lo(smem_u32(sA), 0), b_lo0 = desc_lo(smem_u32(sB), 0);
@@ -478,8 +478,8 @@ __global__ void __launch_bounds__(288, (MB == 1 ? 2 : 1)) wgrad_gemm_kernel(cons
       fence_proxy_async_smem();
       for (uint32_t j = it >= LAG ? it - LAG : 0; j < it; ++j) mbar_arrive(full + (j & (S - 1)));
     } else if (warp == 4) {
-      // ================= MMA issuer =================
-      if (lane == 0) {
+      // ================= MMA issuer (all lanes stay converged; the mma_* wrappers elect one) =================
+      {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);       // bf16, both operands MN-major
         constexpr uint32_t a_hi = desc_hi(1024, LAYOUT_SW128);
         constexpr uint32_t b_hi = NT >= 64 ? desc_hi(1024, LAYOUT_SW128) : desc_hi(512, LAYOUT_SW64);

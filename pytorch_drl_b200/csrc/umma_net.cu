@@ -325,7 +325,8 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   a.raw_buf_bytes = a.plane_bytes * a.planes;
   const int window = (a.MT * 128 + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
   a.slack_bytes = window > a.plane_bytes ? (window - a.plane_bytes + 1023) / 1024 * 1024 : 0;
-  a.use_base_offset = g_debug_flags[0];
+  if (a.MT != 1) return DRL_ERR_BAD_ARG;                // one 128-row tile per sample (all NatureCNN layers)
+  a.use_base_offset = 0;
   auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI>;
   const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
   if (smem > 227 * 1024) return DRL_ERR_BAD_ARG;
@@ -424,7 +425,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     }
     const int tiles = (nb * 400 + 127) / 128;
     if (g_debug_flags[3])   // A operand staged in tensor memory (tcgen05.st + TS-form MMA)
-      conv1_fwd_ts_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdTsSmem, st>>>(a1);
+      conv1_fwd_ts_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1tThreads, kC1FwdTsSmem, st>>>(a1);
     else
       conv1_fwd_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdSmem, st>>>(a1);
     DRL_LAUNCH_CHECK();

@@ -46,7 +46,7 @@ struct TmaConvArgs {
   void* out; const float* bias; float scale; const __nv_bfloat16* mask_src;
   int64_t out_sample_pitch; int out_row_pitch; int out_C; int osy, osx; int classes;
   int use_base_offset;    // debug switch for the descriptor base-offset field
-  uint32_t* bits_out;     // EPI_BIAS_RELU: bit (e & 31) of word (e >> 5) = (out[e] > 0) for output element index e
+  uint32_t* bits_out;     // EPI_BIAS_RELU: ReLU mask words (umma.cuh relu_bit_pos), word e >> 5 for output element index e
   const uint32_t* bits_in; // EPI_MASK: the same bit layout for the tensor shaped like `out` (replaces mask_src reads)
   float* bias_grad;       // EPI_MASK: += column sums of the produced gradient, index = column % bias_mod (or nullptr)
   int bias_mod;
@@ -115,39 +115,51 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
     }
     __syncwarp();
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_f16(1u, 128, N, 0, 0);
       constexpr uint32_t hi0 = desc_hi(1024, LAYOUT_SW128);
       const uint32_t b_lo0 = desc_lo(smem_u32(sB), 0);
       mbar_wait(b_full, 0);
-      uint32_t j = 0, it = 0;
-      for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
-        const uint32_t buf = j % NR;
-        mbar_wait(raw_full + buf, (j / NR) & 1);
-        const uint32_t raw_addr = smem_u32(sRaw + buf * args.raw_buf_bytes);
-        for (int mt = 0; mt < args.MT; ++mt, ++it) {
-          const uint32_t acc = it % NACC;
-          mbar_wait(tempty + acc, ((it / NACC) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * N;
-          int ty = 0, tx = 0;
-          for (int kb = 0; kb < args.KB; ++kb) {
-            const uint32_t a_addr = args.planes == 2
-                ? raw_addr + (uint32_t)((ty & 1) * args.plane_bytes) + (uint32_t)(mt * 128 + (ty >> 1) * args.SHIFT_RW + tx) * 128u
-                : raw_addr + (uint32_t)(mt * 128 + ty * args.SHIFT_RW + tx) * 128u;
-            const uint32_t a_hi = args.use_base_offset ? (hi0 | (((a_addr >> 7) & 7u) << 17)) : hi0;
-            const uint32_t a_lo = desc_lo(a_addr, 0);
-            const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
-            if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, a_hi, b_lo, hi0, idesc);
-            else mma_f16_lohi<true>(tmem_d, a_lo, a_hi, b_lo, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d, a_lo + 2, a_hi, b_lo + 2, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d, a_lo + 4, a_hi, b_lo + 4, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d, a_lo + 6, a_hi, b_lo + 6, hi0, idesc);
-            if (++tx == args.KBX) { tx = 0; ++ty; }
-          }
-          mma_commit(tfull + acc);
+      // Two samples are issued interleaved (k-block by k-block) into two accumulators: back-to-back MMAs into
+      // ONE accumulator do not overlap their operand fetch with the previous MMA, two independent chains do.
+      const int n_mine = (args.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      for (int j = 0; j < n_mine; j += 2) {
+        const int np = min(2, n_mine - j);
+        uint32_t raw_addr[2], tmem_d[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t jj = (uint32_t)(j + (t < np ? t : 0)), buf = jj % NR, acc = jj % NACC;
+          mbar_wait(raw_full + buf, (jj / NR) & 1);
+          mbar_wait(tempty + acc, ((jj / NACC) & 1) ^ 1);
+          raw_addr[t] = smem_u32(sRaw + buf * args.raw_buf_bytes);
+          tmem_d[t] = tmem_base + acc * N;
         }
-        mma_commit(raw_empty + buf);           // staged sample free once every MMA reading it has retired
+        tc_fence_after();
+        int ty = 0, tx = 0;
+        for (int kb = 0; kb < args.KB; ++kb) {
+          const uint32_t shift = args.planes == 2 ? (uint32_t)((ty & 1) * args.plane_bytes) + (uint32_t)((ty >> 1) * args.SHIFT_RW + tx) * 128u
+                                                  : (uint32_t)(ty * args.SHIFT_RW + tx) * 128u;
+          const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
+          const uint32_t a_lo0 = desc_lo(raw_addr[0] + shift, 0), a_lo1 = desc_lo(raw_addr[1] + shift, 0);
+          if (kb == 0) mma_f16_lohi<false>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
+          else mma_f16_lohi<true>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
+          mma_f16_lohi<true>(tmem_d[0], a_lo0 + 2, hi0, b_lo + 2, hi0, idesc);
+          mma_f16_lohi<true>(tmem_d[0], a_lo0 + 4, hi0, b_lo + 4, hi0, idesc);
+          mma_f16_lohi<true>(tmem_d[0], a_lo0 + 6, hi0, b_lo + 6, hi0, idesc);
+          if (np == 2) {
+            if (kb == 0) mma_f16_lohi<false>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
+            else mma_f16_lohi<true>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d[1], a_lo1 + 2, hi0, b_lo + 2, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d[1], a_lo1 + 4, hi0, b_lo + 4, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d[1], a_lo1 + 6, hi0, b_lo + 6, hi0, idesc);
+          }
+          if (++tx == args.KBX) { tx = 0; ++ty; }
+        }
+        for (int t = 0; t < np; ++t) {
+          const uint32_t jj = (uint32_t)(j + t);
+          mma_commit(tfull + jj % NACC);
+          mma_commit(raw_empty + jj % NR);         // staged sample free once every MMA reading it has retired
+        }
       }
     }
     __syncwarp();
@@ -188,18 +200,14 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
           if (ok) {
             if (EPI == EPI_BIAS_RELU_BF16) {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
-              uint32_t bits = 0;
+              uint32_t pk[16];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float f[8];
+              for (int i = 0; i < 16; ++i)
+                pk[i] = pack_bf16x2_relu(fmaf(__uint_as_float(rr[2 * i]), args.scale, sBias[ch * 32 + 2 * i]),
+                                         fmaf(__uint_as_float(rr[2 * i + 1]), args.scale, sBias[ch * 32 + 2 * i + 1]));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  f[i] = fmaxf(fmaf(__uint_as_float(rr[8 * q + i]), args.scale, sBias[ch * 32 + 8 * q + i]), 0.f);
-                  bits |= (f[i] > 0.f ? 1u : 0u) << (8 * q + i);
-                }
-                reinterpret_cast<uint4*>(o)[q] =
-                    make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-              }
+              for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              const uint32_t bits = relu_bits_from_pairs(pk);
               if (args.bits_out) args.bits_out[(ooff + ch * 32) >> 5] = bits;
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
@@ -208,8 +216,8 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
                 uint32_t pk[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float lo = (mbits[ch] >> (8 * q + 2 * i)) & 1u ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
-                  const float hi2 = (mbits[ch] >> (8 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
+                  const float lo = (mbits[ch] >> relu_bit_pos(8 * q + 2 * i)) & 1u ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
+                  const float hi2 = (mbits[ch] >> relu_bit_pos(8 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
                   pk[i] = pack_bf16x2(lo, hi2);
                   rr[8 * q + 2 * i] = __float_as_uint(lo);
                   rr[8 * q + 2 * i + 1] = __float_as_uint(hi2);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_conv_tma_kernel(const __grid_con
       }
       __syncwarp();
     } else if (warp == 4) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);       // bf16, MN-major A and B
         constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
         uint32_t j = 0;

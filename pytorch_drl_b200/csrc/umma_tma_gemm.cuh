@@ -34,7 +34,7 @@ struct TmaGemmArgs {
   int out_ld;
   const float* bias;           // EPI_BIAS_RELU_F32
   const __nv_bfloat16* mask_src;   // EPI_MASK_BF16 (same layout as out)
-  const uint32_t* bits_in;     // EPI_MASK_BF16: bit (e & 31) of word (e >> 5) = (act[e] > 0), e = m*out_ld + n
+  const uint32_t* bits_in;     // EPI_MASK_BF16: ReLU mask words (umma.cuh relu_bit_pos) of act, element e = m*out_ld + n
   float* bias_grad;            // EPI_MASK_BF16: += column sums of the produced gradient at index column % bias_mod
   int bias_mod;
 };
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
     }
     __syncwarp();
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_f16(1u, 128, BN, 0, 0);
       constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
       const uint32_t a_lo0 = desc_lo(smem_u32(smem), 0), b_lo0 = desc_lo(smem_u32(smem) + Cf::kABytes, 0);
@@ -174,23 +174,21 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
             if (args.bits_in) {
               mb = __ldg(args.bits_in + (off >> 5));
             } else {                                       // fallback: derive it from the bf16 activation itself
-              mb = 0;
+              uint32_t mw[16];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint4 mv = ldg_v4(args.mask_src + off + 8 * q);
-                const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  mb |= ((mw[i] & 0x00007fffu) ? 1u : 0u) << (8 * q + 2 * i) | ((mw[i] & 0x7fff0000u) ? 1u : 0u) << (8 * q + 2 * i + 1);
+                mw[4 * q] = mv.x; mw[4 * q + 1] = mv.y; mw[4 * q + 2] = mv.z; mw[4 * q + 3] = mv.w;
               }
+              mb = relu_bits_from_pairs(mw);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint32_t pk[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float lo = (mb >> (8 * q + 2 * i)) & 1u ? __uint_as_float(r[8 * q + 2 * i]) : 0.f;
-                const float hi2 = (mb >> (8 * q + 2 * i + 1)) & 1u ? __uint_as_float(r[8 * q + 2 * i + 1]) : 0.f;
+                const float lo = (mb >> relu_bit_pos(8 * q + 2 * i)) & 1u ? __uint_as_float(r[8 * q + 2 * i]) : 0.f;
+                const float hi2 = (mb >> relu_bit_pos(8 * q + 2 * i + 1)) & 1u ? __uint_as_float(r[8 * q + 2 * i + 1]) : 0.f;
                 pk[i] = pack_bf16x2(lo, hi2);
                 r[8 * q + 2 * i] = __float_as_uint(lo);
                 r[8 * q + 2 * i + 1] = __float_as_uint(hi2);
@@ -292,7 +290,7 @@ __global__ void __launch_bounds__(192, 2) wgrad_tma_kernel(const __grid_constant
       }
       __syncwarp();
     } else if (warp == 4) {
-      if (lane == 0) {
+      {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);
         constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
         const uint32_t a_lo0 = desc_lo(smem_u32(smem), Cf::kAtom);
