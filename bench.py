@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--debug-flags', default='', help='kernel-variant experiments, e.g. "2=1,3=0" (drl_debug_set)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -182,6 +183,9 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     L = _lib.lib()
+    for kv in filter(None, args.debug_flags.split(',')):
+        k, v = kv.split('=')
+        L.drl_debug_set(int(k), int(v))
     n_envs = args.envs
     nb = n_envs * B
 

@@ -96,7 +96,7 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// WARP-COLLECTIVE (all 32 lanes converged; one elected lane issues) — see elect_one() below.
+// Issued by ONE thread: call inside `if (elect_one()) { ... }` — see elect_one() below.
 // Split descriptor form for the issue loop: the high word (SBO, version, swizzle) is a constant of the
 // kernel, the low word is (address >> 4) | LBO << 16 and advances by plain 32-bit adds, so one MMA
 // costs ~4 instructions of the single issuing thread instead of ~20.
@@ -111,20 +111,18 @@ __device__ __forceinline__ void mma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uin
                                              uint32_t idesc) {
   if (ACC) {
     asm volatile(
-        "{\n\t.reg .b64 da, db;\n\t.reg .pred p, e;\n\t"
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
         "setp.eq.b32 p, 0, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .b64 da, db;\n\t.reg .pred p, e;\n\t"
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
         "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
         "setp.ne.b32 p, 0, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
         "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   }
@@ -136,20 +134,18 @@ template <bool ACC>
 __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
   if (ACC) {
     asm volatile(
-        "{\n\t.reg .b64 db;\n\t.reg .pred p, e;\n\t"
+        "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
         "mov.b64 db, {%2, %3};\n\t"
         "setp.eq.b32 p, 0, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .b64 db;\n\t.reg .pred p, e;\n\t"
+        "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
         "mov.b64 db, {%2, %3};\n\t"
         "setp.ne.b32 p, 0, 0;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc)
         : "memory");
   }
@@ -169,8 +165,8 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// One lane of the (converged) warp.  MMA-issuing warps keep ALL lanes in the loop and elect only around the
-// tcgen05 instructions (inside mma_f16_lohi / mma_f16_ts / mma_commit): addresses and descriptors then stay warp-uniform for the compiler
+// One lane of the (converged) warp.  MMA-issuing warps keep ALL lanes in the loop (waits, address math) and wrap
+// each unrolled BATCH of tcgen05 instructions in `if (elect_one()) { ... }`: addresses and descriptors then stay warp-uniform for the compiler
 // (uniform registers feed UTCHMMA directly); a loop run under `if (lane == 0)` instead makes every operand a
 // per-thread value and costs an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall per MMA.
 __device__ __forceinline__ bool elect_one() {
@@ -179,13 +175,9 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// All previously issued MMAs of the elected lane arrive on `bar` when complete (implies fence::before).
-// WARP-COLLECTIVE like the mma_* wrappers: call with all 32 lanes converged.
+// All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
-      : "memory");
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive columns (one fp32 row chunk per thread).

@@ -231,18 +231,21 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_fwd_kernel(const Conv1Arg
         mbar_wait(full + ab, (j >> 1) & 1);
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + ab * (65536 >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+          for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (kb == 0 && k == 0)
-              mma_f16_lohi<false>(tmem_base + acc * 32, a_lo, hi, b_lo0, hi, idesc);
-            else
-              mma_f16_lohi<true>(tmem_base + acc * 32, a_lo + kb * (16384 >> 4) + k * 2, hi, b_lo0 + kb * (4096 >> 4) + k * 2, hi, idesc);
+            for (int k = 0; k < 4; ++k) {
+              if (kb == 0 && k == 0)
+                mma_f16_lohi<false>(tmem_base + acc * 32, a_lo, hi, b_lo0, hi, idesc);
+              else
+                mma_f16_lohi<true>(tmem_base + acc * 32, a_lo + kb * (16384 >> 4) + k * 2, hi, b_lo0 + kb * (4096 >> 4) + k * 2, hi, idesc);
+            }
           }
+          mma_commit(empty + ab);
+          mma_commit(tfull + acc);
         }
-        mma_commit(empty + ab);
-        mma_commit(tfull + acc);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -396,14 +399,17 @@ __global__ void __launch_bounds__(kC1tThreads, 1) conv1_fwd_ts_kernel(const Conv
         mbar_wait(full + ab, (j / kC1tNA) & 1);
         tc_fence_after();
         const uint32_t t_a = tmem_base + A_COL + ab * 128, t_d = tmem_base + ACC_COL + acc * 32;
+        if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t b_lo = b_lo0 + (i >> 2) * (4096 >> 4) + (i & 3) * 2;
-          if (i == 0) mma_f16_ts<false>(t_d, t_a, b_lo, hi, idesc);
-          else mma_f16_ts<true>(t_d, t_a + i * 8, b_lo, hi, idesc);
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t b_lo = b_lo0 + (i >> 2) * (4096 >> 4) + (i & 3) * 2;
+            if (i == 0) mma_f16_ts<false>(t_d, t_a, b_lo, hi, idesc);
+            else mma_f16_ts<true>(t_d, t_a + i * 8, b_lo, hi, idesc);
+          }
+          mma_commit(empty + ab);
+          mma_commit(tfull + acc);
         }
-        mma_commit(empty + ab);
-        mma_commit(tfull + acc);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -540,6 +546,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
           const uint32_t tb = j & 1;
           mbar_wait(full + tb, (j >> 1) & 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
           for (int ss = 0; ss < 4; ++ss) {
             const uint32_t p_lo = st_lo0 + (tb * 4 + ss) * (kC1wStage >> 4), d_lo = p_lo + ((4 * 4096) >> 4);
@@ -558,8 +565,11 @@ __global__ void __launch_bounds__(kC1Threads, 1) conv1_wgrad_kernel(const Conv1A
               }
           }
           mma_commit(empty + tb);
+          }
+          __syncwarp();
         }
-        mma_commit(done);
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
       }
       __syncwarp();
     } else {

@@ -210,13 +210,16 @@ __global__ void __launch_bounds__(288, 2) rowgather_gemm_kernel(const RowGatherA
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * (L::kABytes >> 4), b_lo = b_lo0 + stage * (L::kBBytes >> 4);
-          if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, hi, b_lo, hi, idesc);
-          else mma_f16_lohi<true>(tmem_d, a_lo, hi, b_lo, hi, idesc);
-          mma_f16_lohi<true>(tmem_d, a_lo + 2, hi, b_lo + 2, hi, idesc);
-          mma_f16_lohi<true>(tmem_d, a_lo + 4, hi, b_lo + 4, hi, idesc);
-          mma_f16_lohi<true>(tmem_d, a_lo + 6, hi, b_lo + 6, hi, idesc);
-          mma_commit(empty + stage);
-          if (kb == args.KB - 1) mma_commit(tfull + acc);
+          if (elect_one()) {
+            if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, hi, b_lo, hi, idesc);
+            else mma_f16_lohi<true>(tmem_d, a_lo, hi, b_lo, hi, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 2, hi, b_lo + 2, hi, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 4, hi, b_lo + 4, hi, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 6, hi, b_lo + 6, hi, idesc);
+            mma_commit(empty + stage);
+            if (kb == args.KB - 1) mma_commit(tfull + acc);
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -493,26 +496,30 @@ __global__ void __launch_bounds__(288, (MB == 1 ? 2 : 1)) wgrad_gemm_kernel(cons
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * (STAGE >> 4), b_lo = b_lo0 + stage * (STAGE >> 4);
-          if (it == 0) {
+          if (elect_one()) {
+            if (it == 0) {
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              mma_f16_lohi<false>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4), a_hi, b_lo, b_hi, idesc);
+              for (int mb = 0; mb < MB; ++mb) {
+                mma_f16_lohi<false>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4), a_hi, b_lo, b_hi, idesc);
 #pragma unroll
-              for (int k = 1; k < ROWS / 16; ++k)
-                mma_f16_lohi<true>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4) + k * ((16 * 128) >> 4), a_hi,
-                                   b_lo + k * b_kstep, b_hi, idesc);
+                for (int k = 1; k < ROWS / 16; ++k)
+                  mma_f16_lohi<true>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4) + k * ((16 * 128) >> 4), a_hi,
+                                     b_lo + k * b_kstep, b_hi, idesc);
+              }
+            } else {
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int k = 0; k < ROWS / 16; ++k)
+                  mma_f16_lohi<true>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4) + k * ((16 * 128) >> 4), a_hi,
+                                     b_lo + k * b_kstep, b_hi, idesc);
             }
-          } else {
-#pragma unroll
-            for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-              for (int k = 0; k < ROWS / 16; ++k)
-                mma_f16_lohi<true>(tmem_base + mb * NT, a_lo + mb * ((2 * Cf::kAtomBytes) >> 4) + k * ((16 * 128) >> 4), a_hi,
-                                   b_lo + k * b_kstep, b_hi, idesc);
+            mma_commit(empty + stage);
           }
-          mma_commit(empty + stage);
+          __syncwarp();
         }
-        mma_commit(done);
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
       }
       __syncwarp();
     } else {

@@ -295,7 +295,7 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
 // [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
 // [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
-int g_debug_flags[8] = {0, 1, 0, 1, 0, 0, 0, 0};
+int g_debug_flags[8] = {0, 1, 1, 1, 0, 0, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -326,6 +326,7 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   const int window = (a.MT * 128 + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
   a.slack_bytes = window > a.plane_bytes ? (window - a.plane_bytes + 1023) / 1024 * 1024 : 0;
   if (a.MT != 1) return DRL_ERR_BAD_ARG;                // one 128-row tile per sample (all NatureCNN layers)
+  if (a.bias_grad && a.bias_mod != (N == 64 ? 64 : 32)) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   a.use_base_offset = 0;
   auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI>;
   const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
@@ -351,7 +352,7 @@ static TmaConvArgs tma_conv_args(int KB, int KBX, int RW, int SHIFT_RW, int pad,
   return a;
 }
 
-template <int NT, int MB, int NR>
+template <int NT, int MB, int NR, int KSTEPS>
 static int launch_wgrad_conv(const char* site, const void* p_src, int pH, int pW, int pBW, int pBH, const void* dy_src, int dH,
                              int dW, int dBW, int dBH, int nb, WgradConvArgs a, cudaStream_t st) {
   ProfileScope prof(site, st);
@@ -364,7 +365,8 @@ static int launch_wgrad_conv(const char* site, const void* p_src, int pH, int pW
   a.p_buf_bytes = a.p_plane_bytes * a.p_planes;
   a.dy_buf_bytes = (a.dy_box_bytes + 1023) / 1024 * 1024;
   if (a.dy_buf_bytes < a.ksteps * 16 * 128) a.dy_buf_bytes = (a.ksteps * 16 * 128 + 1023) / 1024 * 1024;
-  auto kern = wgrad_conv_tma_kernel<NT, MB, NR>;
+  if (a.ksteps != KSTEPS) return DRL_ERR_BAD_ARG;
+  auto kern = wgrad_conv_tma_kernel<NT, MB, NR, KSTEPS>;
   const int smem = NR * (a.p_buf_bytes + a.dy_buf_bytes) + 256 + 1024;
   static int configured = 0;
   if (configured < smem) {
@@ -383,6 +385,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
   CUtensorMap ta, tb;
   DRL_TRY(make_tmap_bf16(&ta, a, (uint64_t)M, (uint64_t)K, 128));
   DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, BN));
+  if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   auto kern = tma_gemm_kernel<BN, EPI>;
   constexpr int smem = TmaGemmCfg<BN>::kSmem;
   static bool configured = false;
@@ -517,7 +520,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     for (int mb = 0; mb < 5; ++mb) { w.a_off[mb] = sh[2 * mb] * 128; w.a_lbo[mb] = (sh[2 * mb + 1] - sh[2 * mb]) * 128; }
     w.p_plane_bytes = 11264;                         // 88 rows >= 63 + 21 + 1
     w.gw = g + o[4]; w.Cin = 64; w.KH = 3; w.KW = 3; w.kp_valid = 576;
-    DRL_TRY((launch_wgrad_conv<64, 5, 4>("conv3_wgrad", n->act[1], 9, 9, 9, 9, n->dact[2], 7, 7, 9, 8, nb, w, st)));
+    DRL_TRY((launch_wgrad_conv<64, 5, 4, 4>("conv3_wgrad", n->act[1], 9, 9, 9, 9, n->dact[2], 7, 7, 9, 8, nb, w, st)));
   } else {
     DRL_TRY((launch_wgrad<64, SRC_BF16, 5>("conv3_wgrad", w3, splits(nb * 49, 1), 1, st)));
   }
@@ -548,7 +551,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     w.p_plane_bytes = 14336;                         // 112 rows >= 95 + 11 + 1
     for (int ky = 0; ky < 4; ++ky) { w.a_off[ky] = (ky & 1) * w.p_plane_bytes + (ky >> 1) * 10 * 128; w.a_lbo[ky] = 128; }
     w.gw = g + o[2]; w.Cin = 32; w.KH = 4; w.KW = 4; w.kp_valid = 512;
-    DRL_TRY((launch_wgrad_conv<64, 4, 4>("conv2_wgrad", n->act[0], 20, 10, 10, 20, n->dact[1], 9, 9, 10, 10, nb, w, st)));
+    DRL_TRY((launch_wgrad_conv<64, 4, 4, 6>("conv2_wgrad", n->act[0], 20, 10, 10, 20, n->dact[1], 9, 9, 10, 10, nb, w, st)));
   } else {
     DRL_TRY((launch_wgrad<64, SRC_BF16, 4>("conv2_wgrad", w2, splits(nb * 81, 1), 1, st)));
   }

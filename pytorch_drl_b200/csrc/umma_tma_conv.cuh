@@ -14,6 +14,7 @@
 // No producer warps, no generic-proxy writes, no proxy fences: warps 0-3 epilogue, 4 MMA, 5 TMA.
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include "umma_tma_gemm.cuh"
 
 namespace drl {
@@ -141,25 +142,31 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
                                                   : (uint32_t)(ty * args.SHIFT_RW + tx) * 128u;
           const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
           const uint32_t a_lo0 = desc_lo(raw_addr[0] + shift, 0), a_lo1 = desc_lo(raw_addr[1] + shift, 0);
-          if (kb == 0) mma_f16_lohi<false>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
-          else mma_f16_lohi<true>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
-          mma_f16_lohi<true>(tmem_d[0], a_lo0 + 2, hi0, b_lo + 2, hi0, idesc);
-          mma_f16_lohi<true>(tmem_d[0], a_lo0 + 4, hi0, b_lo + 4, hi0, idesc);
-          mma_f16_lohi<true>(tmem_d[0], a_lo0 + 6, hi0, b_lo + 6, hi0, idesc);
-          if (np == 2) {
-            if (kb == 0) mma_f16_lohi<false>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
-            else mma_f16_lohi<true>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d[1], a_lo1 + 2, hi0, b_lo + 2, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d[1], a_lo1 + 4, hi0, b_lo + 4, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d[1], a_lo1 + 6, hi0, b_lo + 6, hi0, idesc);
+          if (elect_one()) {
+            if (kb == 0) mma_f16_lohi<false>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
+            else mma_f16_lohi<true>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d[0], a_lo0 + 2, hi0, b_lo + 2, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d[0], a_lo0 + 4, hi0, b_lo + 4, hi0, idesc);
+            mma_f16_lohi<true>(tmem_d[0], a_lo0 + 6, hi0, b_lo + 6, hi0, idesc);
+            if (np == 2) {
+              if (kb == 0) mma_f16_lohi<false>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
+              else mma_f16_lohi<true>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
+              mma_f16_lohi<true>(tmem_d[1], a_lo1 + 2, hi0, b_lo + 2, hi0, idesc);
+              mma_f16_lohi<true>(tmem_d[1], a_lo1 + 4, hi0, b_lo + 4, hi0, idesc);
+              mma_f16_lohi<true>(tmem_d[1], a_lo1 + 6, hi0, b_lo + 6, hi0, idesc);
+            }
           }
+          __syncwarp();
           if (++tx == args.KBX) { tx = 0; ++ty; }
         }
-        for (int t = 0; t < np; ++t) {
-          const uint32_t jj = (uint32_t)(j + t);
-          mma_commit(tfull + jj % NACC);
-          mma_commit(raw_empty + jj % NR);         // staged sample free once every MMA reading it has retired
+        if (elect_one()) {
+          for (int t = 0; t < np; ++t) {
+            const uint32_t jj = (uint32_t)(j + t);
+            mma_commit(tfull + jj % NACC);
+            mma_commit(raw_empty + jj % NR);       // staged sample free once every MMA reading it has retired
+          }
         }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -167,9 +174,12 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
     auto coff = [&](int ch) -> int64_t {
       return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
     };
-    float colacc[N / 32];
+    // fused bias gradient: every thread keeps running column sums of ITS rows (32 adds per chunk and tile);
+    // the cross-lane reduction happens once, after the last tile.  Column chunk ch feeds bias group ch % BG.
+    constexpr int BG = N == 64 ? 2 : 1;               // bias_mod / 32 (checked by the launcher)
+    float cs[EPI == EPI_MASK_BF16 ? 32 * BG : 1];
 #pragma unroll
-    for (int ch = 0; ch < N / 32; ++ch) colacc[ch] = 0.f;
+    for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
     const int wg = warp >> 2, trow = threadIdx.x & 127;
     uint32_t it = 0;
     for (int b = blockIdx.x; b < args.nb; b += gridDim.x) {
@@ -226,18 +236,21 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
               }
             }
           }
-          if (EPI == EPI_MASK_BF16 && args.bias_grad) {      // fused bias gradient of the layer below
-            float v[32];
+          if (EPI == EPI_MASK_BF16 && ok) {                 // fused bias gradient of the layer below
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ok ? __uint_as_float(rr[i]) : 0.f;
-            colacc[ch] += warp_colsum32(v, lane);
+            for (int i = 0; i < 32; ++i) cs[(ch % BG) * 32 + i] += __uint_as_float(rr[i]);
           }
         }
       }
     }
     if (EPI == EPI_MASK_BF16 && args.bias_grad) {
 #pragma unroll
-      for (int ch = 0; ch < N / 32; ++ch) atomicAdd(args.bias_grad + (ch * 32 + lane) % args.bias_mod, colacc[ch]);
+      for (int g = 0; g < BG; ++g) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = cs[g * 32 + i];
+        atomicAdd(args.bias_grad + g * 32 + lane, warp_colsum32(v, lane));
+      }
     }
   }
   tc_fence_before();
@@ -273,7 +286,7 @@ struct WgradConvArgs {
   float* gw; int Cin, KH, KW, kp_valid;
 };
 
-template <int NT, int MB, int NR>
+template <int NT, int MB, int NR, int KSTEPS>
 __global__ void __launch_bounds__(192, 1) wgrad_conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
                                                                 const __grid_constant__ CUtensorMap tmap_dy,
                                                                 const WgradConvArgs args) {
@@ -324,24 +337,37 @@ __global__ void __launch_bounds__(192, 1) wgrad_conv_tma_kernel(const __grid_con
       {
         constexpr uint32_t idesc = make_idesc_f16(1u, 128, NT, 1, 1);       // bf16, MN-major A and B
         constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
+        // descriptor low words of stage 0, per accumulator block: everything the loop adds is warp-uniform
+        uint32_t a_base[MB];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) a_base[mb] = desc_lo(smem_u32(smem) + args.a_off[mb], args.a_lbo[mb]);
+        const uint32_t b_base = desc_lo(smem_u32(smem) + (uint32_t)args.p_buf_bytes, 0);
+        const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+        auto issue = [&](uint32_t so, auto first) {
+          constexpr bool FIRST = decltype(first)::value;
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              const uint32_t al = a_base[mb] + so + k * ((16 * 128) >> 4), bl = b_base + so + k * ((16 * 128) >> 4);
+              if (FIRST && k == 0) mma_f16_lohi<false>(tmem_base + mb * NT, al, hi, bl, hi, idesc);
+              else mma_f16_lohi<true>(tmem_base + mb * NT, al, hi, bl, hi, idesc);
+            }
+        };
         uint32_t j = 0;
         for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
           const uint32_t buf = j % NR;
           mbar_wait(full + buf, (j / NR) & 1);
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + buf * stage_bytes), d_addr = p_addr + args.p_buf_bytes;
-          const uint32_t b_lo0 = desc_lo(d_addr, 0);
-#pragma unroll
-          for (int mb = 0; mb < MB; ++mb) {
-            const uint32_t a_lo0 = desc_lo(p_addr + args.a_off[mb], args.a_lbo[mb]);
-            for (int k = 0; k < args.ksteps; ++k) {
-              if (j == 0 && k == 0) mma_f16_lohi<false>(tmem_base + mb * NT, a_lo0, hi, b_lo0, hi, idesc);
-              else mma_f16_lohi<true>(tmem_base + mb * NT, a_lo0 + k * ((16 * 128) >> 4), hi, b_lo0 + k * ((16 * 128) >> 4), hi, idesc);
-            }
+          if (elect_one()) {
+            if (j == 0) issue(buf * stage16, std::true_type{});
+            else issue(buf * stage16, std::false_type{});
+            mma_commit(empty + buf);
           }
-          mma_commit(empty + buf);
+          __syncwarp();
         }
-        mma_commit(done);
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
       }
       __syncwarp();
     } else {

@@ -114,13 +114,16 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * (Cf::kStage >> 4), b_lo = b_lo0 + stage * (Cf::kStage >> 4);
-          if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, hi, b_lo, hi, idesc);
-          else mma_f16_lohi<true>(tmem_d, a_lo, hi, b_lo, hi, idesc);
-          mma_f16_lohi<true>(tmem_d, a_lo + 2, hi, b_lo + 2, hi, idesc);
-          mma_f16_lohi<true>(tmem_d, a_lo + 4, hi, b_lo + 4, hi, idesc);
-          mma_f16_lohi<true>(tmem_d, a_lo + 6, hi, b_lo + 6, hi, idesc);
-          mma_commit(empty + stage);
-          if (kb == args.KB - 1) mma_commit(tfull + acc);
+          if (elect_one()) {
+            if (kb == 0) mma_f16_lohi<false>(tmem_d, a_lo, hi, b_lo, hi, idesc);
+            else mma_f16_lohi<true>(tmem_d, a_lo, hi, b_lo, hi, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 2, hi, b_lo + 2, hi, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 4, hi, b_lo + 4, hi, idesc);
+            mma_f16_lohi<true>(tmem_d, a_lo + 6, hi, b_lo + 6, hi, idesc);
+            mma_commit(empty + stage);
+            if (kb == args.KB - 1) mma_commit(tfull + acc);
+          }
+          __syncwarp();
         }
       }
     }
@@ -128,9 +131,12 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
   } else {
     uint32_t j = 0;
     int last_nt = -1;
-    float colacc[BN / 32];
+    // fused bias gradient: per-thread running column sums (bias index = column % 64, two 32-column groups);
+    // one cross-lane reduction after the last tile
+    constexpr int BG = 2;
+    float cs[EPI == EPI_MASK_BF16 ? 32 * BG : 1];
 #pragma unroll
-    for (int ch = 0; ch < BN / 32; ++ch) colacc[ch] = 0.f;
+    for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
       const uint32_t acc = j & 1;
@@ -197,18 +203,20 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
             }
           }
         }
-        if (EPI == EPI_MASK_BF16 && args.bias_grad) {        // fused bias gradient of the layer below
-          float v[32];
-          const bool live = m < args.M && n < args.N_total;
+        if (EPI == EPI_MASK_BF16 && m < args.M && n < args.N_total) {   // fused bias gradient of the layer below
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = live ? __uint_as_float(r[i]) : 0.f;
-          colacc[ch] += warp_colsum32(v, lane);
+          for (int i = 0; i < 32; ++i) cs[(ch % BG) * 32 + i] += __uint_as_float(r[i]);
         }
       }
     }
     if (EPI == EPI_MASK_BF16 && args.bias_grad) {
 #pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) atomicAdd(args.bias_grad + (ch * 32 + lane) % args.bias_mod, colacc[ch]);
+      for (int g = 0; g < BG; ++g) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = cs[g * 32 + i];
+        atomicAdd(args.bias_grad + g * 32 + lane, warp_colsum32(v, lane));
+      }
     }
   }
   tc_fence_before();
@@ -301,18 +309,22 @@ __global__ void __launch_bounds__(192, 2) wgrad_tma_kernel(const __grid_constant
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * (Cf::kStage >> 4), b_lo = b_lo0 + stage * (Cf::kStage >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb)
+            for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-            for (int k = 0; k < ROWS / 16; ++k) {
-              const uint32_t al = a_lo + mb * ((2 * Cf::kAtom) >> 4) + k * ((16 * 128) >> 4);
-              const uint32_t bl = b_lo + k * ((16 * 128) >> 4);
-              if (k == 0 && it == 0) mma_f16_lohi<false>(tmem_base + mb * NT, al, hi, bl, hi, idesc);
-              else mma_f16_lohi<true>(tmem_base + mb * NT, al, hi, bl, hi, idesc);
-            }
-          mma_commit(empty + stage);
+              for (int k = 0; k < ROWS / 16; ++k) {
+                const uint32_t al = a_lo + mb * ((2 * Cf::kAtom) >> 4) + k * ((16 * 128) >> 4);
+                const uint32_t bl = b_lo + k * ((16 * 128) >> 4);
+                if (k == 0 && it == 0) mma_f16_lohi<false>(tmem_base + mb * NT, al, hi, bl, hi, idesc);
+                else mma_f16_lohi<true>(tmem_base + mb * NT, al, hi, bl, hi, idesc);
+              }
+            mma_commit(empty + stage);
+          }
+          __syncwarp();
         }
-        mma_commit(done);
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
       }
       __syncwarp();
     } else {

@@ -1,5 +1,5 @@
 """Runs a few full-size learner steps (32 768 samples) on cuda:0 — the target of the ncu captures
-whose summaries live under profiles/.  Usage: python scripts/one_step.py [steps] [precision]"""
+whose summaries live under profiles/.  Usage: python scripts/one_step.py [steps] [precision] [debug flags "2=1,3=0"]"""
 import os
 import sys
 
@@ -15,6 +15,10 @@ from pytorch_drl_b200.engine import LearnerEngine  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 precision = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 n_envs, T, B, A = 1024, 32, 32, 6
+if len(sys.argv) > 3:
+    from pytorch_drl_b200 import _lib
+    for kv in filter(None, sys.argv[3].split(',')):
+        _lib.lib().drl_debug_set(int(kv.split('=')[0]), int(kv.split('=')[1]))
 dev = tc.device('cuda', 0)
 eng = LearnerEngine(A, ['value_extrinsic'], n_envs * B, precision)
 g = tc.Generator(device=dev)
