@@ -13,6 +13,7 @@
 #include "umma_conv1.cuh"
 #include "umma_tma_gemm.cuh"
 #include "umma_tma_conv.cuh"
+#include "umma_conv1_s2d.cuh"
 
 namespace drl {
 
@@ -295,7 +296,8 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
 // [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
 // [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
-int g_debug_flags[8] = {0, 1, 1, 1, 0, 0, 0, 0};
+// [4] conv1 weight gradient on the space-to-depth block image (1) or the im2col kernel (0)
+int g_debug_flags[8] = {0, 1, 1, 1, 1, 0, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -308,6 +310,20 @@ static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64
   const cuuint32_t estr[4] = {1, 1, h_stride, 1};   // h_stride 2: every other map row (box BH spans BH/2 rows)
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
+}
+
+// dY1 [nb, 20, 20, 32] bf16 -> per sample a (32, 21, 20, 1) box: rows y*21 + x of 64 B, 64B swizzle; x = 20 is zero fill
+static int make_tmap_dy1(CUtensorMap* m, const void* base, uint64_t nb) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return DRL_ERR_CUDA;
+  const cuuint64_t dims[4] = {32, 20, 20, nb};
+  const cuuint64_t strides[3] = {64, 20 * 64, 400 * 64};
+  const cuuint32_t box[4] = {32, 21, 20, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
 }
@@ -576,7 +592,20 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   }
   // ---- conv1 (no data gradient: observations need none, agent.py:66-67)
   if (!g_debug_flags[1]) DRL_TRY(colsum(n->dact[0], (int64_t)nb * 400, 32, g + o[1], st));
-  {
+  if (g_debug_flags[4]) {
+    ProfileScope prof("conv1_wgrad", st);
+    CUtensorMap tdy;
+    DRL_TRY(make_tmap_dy1(&tdy, n->dact[0], (uint64_t)nb));
+    Conv1S2dArgs a{};
+    a.obs = obs; a.row_idx = row_idx; a.nb = nb; a.scale = kInv255; a.gw = g + o[0];
+    static bool configured = false;
+    if (!configured) {
+      DRL_CUDA(cudaFuncSetAttribute(conv1_wgrad_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS2dWgradSmem));
+      configured = true;
+    }
+    conv1_wgrad_s2d_kernel<<<nb < sms ? nb : sms, kS2dThreads, kS2dWgradSmem, st>>>(tdy, a);
+    DRL_LAUNCH_CHECK();
+  } else {
     ProfileScope prof("conv1_wgrad", st);
     Conv1Args a1{};
     a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.scale = kInv255;
