@@ -22,6 +22,7 @@ static const float kInv255 = [] { const uint32_t u = 0x3b808081u; float f; memcp
 struct Bf16Engine {
   // packed B operands (tile images)
   void* w1f = nullptr;   // conv1 fwd   fp16 [4][32x64]
+  void* w1s = nullptr;   // conv1 fwd   fp16 [4 taps][32x64] in space-to-depth block order (PK_CONV1_S2D)
   void* w2f = nullptr;   // conv2 fwd   bf16 [8][64x64]
   void* w3f = nullptr;   // conv3 fwd   bf16 [9][64x64]
   void* wff = nullptr;   // fc fwd      bf16 row-major [512][3136], k = (hw, c)  (TMA tensor map)
@@ -33,7 +34,7 @@ struct Bf16Engine {
 };
 
 // ---- packing -----------------------------------------------------------------------------------------
-enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4 };
+enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_CONV1_S2D = 5 };
 
 // fc weights as plain row-major bf16 matrices in the NHWC feature order k = hw*64 + c (TMA operands)
 __global__ void __launch_bounds__(256) pack_fc_plain_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
@@ -75,6 +76,11 @@ __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n,
     case PK_CONV3_DGRAD: {         // B[n=ci][k=(ty,tx,co)] = W3[co,ci,2-ty,2-tx]
       const int t = k / 64, co = k - t * 64, ty = t / 3, tx = t - ty * 3;
       return a.w[((size_t)(co * 64 + n) * 3 + (2 - ty)) * 3 + (2 - tx)];
+    }
+    case PK_CONV1_S2D: {           // B[n=co][k = tap*64 + e], tap = (ty,tx), e = dy*16 + px*4 + ci: W1[co,ci,4ty+dy,4tx+px]
+      const int tap = k >> 6, e = k & 63, ty = tap >> 1, tx = tap & 1;
+      const int dy = e >> 4, px = (e >> 2) & 3, ci = e & 3;
+      return a.w[((size_t)(n * 4 + ci) * 8 + (4 * ty + dy)) * 8 + (4 * tx + px)];
     }
     default: {                     // PK_CONV2_DGRAD: row n = (class (py,px), ci); B[n][k=(ty,tx,co)] = W2[co,ci,py+2(1-ty),px+2(1-tx)]
       const int cls = n >> 5, ci = n & 31, py = cls >> 1, px = cls & 1;
@@ -188,6 +194,7 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&n->feat, nb * 512 * 4));
   DRL_CUDA(cudaMalloc(&n->dpre, nb * 512 * 2));
   DRL_CUDA(cudaMalloc(&e->w1f, 4 * 32 * 128));
+  DRL_CUDA(cudaMalloc(&e->w1s, 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->w2f, 8 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w3f, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->wff, (size_t)512 * 3136 * 2));
@@ -204,7 +211,7 @@ int bf16_alloc(drl_net* n) {
 void bf16_free(drl_net* n) {
   Bf16Engine* e = n->bf16;
   if (!e) return;
-  cudaFree(e->w1f); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
+  cudaFree(e->w1f); cudaFree(e->w1s); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
   delete e;
   n->bf16 = nullptr;
 }
@@ -215,6 +222,7 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   const float* p = n->params;
   const int64_t* o = n->off;
   DRL_TRY(pack_one(p + o[0], e->w1f, PK_CONV_FWD, 1, 1, 4, 32, 4, 8, 8, 32, st));
+  DRL_TRY(pack_one(p + o[0], e->w1s, PK_CONV1_S2D, 1, 1, 4, 32, 4, 8, 8, 32, st));
   conv1_bias_eff_kernel<<<1, 32, 0, st>>>(p + o[0], p + o[1], kInv255, e->b1eff);
   DRL_LAUNCH_CHECK();
   DRL_TRY(pack_one(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64, st));
@@ -297,7 +305,8 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
 // [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
 // [4] conv1 weight gradient on the space-to-depth block image (1) or the im2col kernel (0)
-int g_debug_flags[8] = {0, 1, 1, 1, 1, 0, 0, 0};
+// [5] conv1 forward on the space-to-depth block image (1), else the kernel flag [3] selects
+int g_debug_flags[8] = {0, 1, 1, 1, 1, 1, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -440,10 +449,14 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     if (!configured) {
       DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1FwdSmem));
       DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kC1FwdTsSmem));
+      DRL_CUDA(cudaFuncSetAttribute(conv1_fwd_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS2dFwdSmem));
       configured = true;
     }
     const int tiles = (nb * 400 + 127) / 128;
-    if (g_debug_flags[3])   // A operand staged in tensor memory (tcgen05.st + TS-form MMA)
+    if (g_debug_flags[5]) { // space-to-depth block image, every pixel converted once
+      a1.bpack = e->w1s;
+      conv1_fwd_s2d_kernel<<<nb < sm_count() ? nb : sm_count(), kS2dFThreads, kS2dFwdSmem, st>>>(a1);
+    } else if (g_debug_flags[3])   // A operand staged in tensor memory (tcgen05.st + TS-form MMA)
       conv1_fwd_ts_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1tThreads, kC1FwdTsSmem, st>>>(a1);
     else
       conv1_fwd_kernel<<<tiles < sm_count() ? tiles : sm_count(), kC1Threads, kC1FwdSmem, st>>>(a1);
