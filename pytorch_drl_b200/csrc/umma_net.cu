@@ -337,7 +337,7 @@ static int make_tmap_dy1(CUtensorMap* m, const void* base, uint64_t nb) {
   return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
 }
 
-template <int N, int EPI, int NR, int NACC, int NEPI>
+template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS = 128>
 static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st) {
   ProfileScope prof(site, st);
   CUtensorMap tm;
@@ -348,12 +348,13 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   const int max_shift = (a.planes == 2 ? tap_rows / 2 : tap_rows) * a.SHIFT_RW + (a.KBX - 1);
   a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
   a.raw_buf_bytes = a.plane_bytes * a.planes;
-  const int window = (a.MT * 128 + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
+  const int window = (MROWS + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
   a.slack_bytes = window > a.plane_bytes ? (window - a.plane_bytes + 1023) / 1024 * 1024 : 0;
   if (a.MT != 1) return DRL_ERR_BAD_ARG;                // one 128-row tile per sample (all NatureCNN layers)
   if (a.bias_grad && a.bias_mod != (N == 64 ? 64 : 32)) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   a.use_base_offset = 0;
-  auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI>;
+  if (a.OH * a.RW > MROWS) return DRL_ERR_BAD_ARG;       // every output row must fall inside the tile
+  auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI, MROWS>;
   const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
   if (smem > 227 * 1024) return DRL_ERR_BAD_ARG;
   static int configured = 0;
@@ -476,7 +477,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   if (g_debug_flags[1]) {
     TmaConvArgs c3 = tma_conv_args(9, 3, 9, 9, 0, 1, 7, 7, e->w3f, n->act[2], p + o[5], nullptr, 3136, 7 * 64, 64, 1, 0);
     c3.bits_out = e->bits[2];
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 6, 4, 2>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 6, 4, 2, 64>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
   }

@@ -62,7 +62,7 @@ constexpr int tma_conv_smem(int KB, int raw_buf_bytes, int NR, int slack) {
   return KB * N * 128 + NR * raw_buf_bytes + slack + 1280 + 1024;
 }
 
-template <int N, int EPI, int NR, int NACC, int NEPI>
+template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS = 128>
 __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                            const TmaConvArgs args) {
   using namespace umma;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
     __syncwarp();
   } else if (warp == W_MMA) {
     {
-      constexpr uint32_t idesc = make_idesc_f16(1u, 128, N, 0, 0);
+      constexpr uint32_t idesc = make_idesc_f16(1u, MROWS, N, 0, 0);
       constexpr uint32_t hi0 = desc_hi(1024, LAYOUT_SW128);
       const uint32_t b_lo0 = desc_lo(smem_u32(sB), 0);
       mbar_wait(b_full, 0);
@@ -180,7 +180,9 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
     float cs[EPI == EPI_MASK_BF16 ? 32 * BG : 1];
 #pragma unroll
     for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
-    const int wg = warp >> 2, trow = threadIdx.x & 127;
+    // MROWS = 64: the accumulator rows live in lanes 0-15 of each 32-lane quarter (row = 16*quarter + lane)
+    const int wg = warp >> 2;
+    const int trow = MROWS == 128 ? (int)(threadIdx.x & 127) : (lane < 16 ? 16 * (warp & 3) + lane : 1 << 20);
     uint32_t it = 0;
     for (int b = blockIdx.x; b < args.nb; b += gridDim.x) {
       for (int mt = 0; mt < args.MT; ++mt, ++it) {
