@@ -122,9 +122,10 @@ __device__ __forceinline__ void c1_store_row(const uint32_t (&r)[32], const floa
   for (int i = 0; i < 16; ++i)
     pk[i] = umma::pack_bf16x2_relu(fmaf(__uint_as_float(r[2 * i]), scale, bias[2 * i]),
                                    fmaf(__uint_as_float(r[2 * i + 1]), scale, bias[2 * i + 1]));
-  uint4* o = reinterpret_cast<uint4*>(out_row);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) o[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  for (int q = 0; q < 2; ++q)
+    umma::stg_v8(out_row + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4], pk[8 * q + 5],
+                 pk[8 * q + 6], pk[8 * q + 7]);
   *bits_dst = umma::relu_bits_from_pairs(pk);
 }
 

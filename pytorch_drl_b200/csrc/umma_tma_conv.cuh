@@ -218,23 +218,25 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
                 pk[i] = pack_bf16x2_relu(fmaf(__uint_as_float(rr[2 * i]), args.scale, sBias[ch * 32 + 2 * i]),
                                          fmaf(__uint_as_float(rr[2 * i + 1]), args.scale, sBias[ch * 32 + 2 * i + 1]));
 #pragma unroll
-              for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              for (int q = 0; q < 2; ++q)
+                stg_v8(o + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4], pk[8 * q + 5], pk[8 * q + 6],
+                       pk[8 * q + 7]);
               const uint32_t bits = relu_bits_from_pairs(pk);
               if (args.bits_out) args.bits_out[(ooff + ch * 32) >> 5] = bits;
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t pk[4];
+              for (int q = 0; q < 2; ++q) {
+                uint32_t pk[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float lo = (mbits[ch] >> relu_bit_pos(8 * q + 2 * i)) & 1u ? __uint_as_float(rr[8 * q + 2 * i]) : 0.f;
-                  const float hi2 = (mbits[ch] >> relu_bit_pos(8 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[8 * q + 2 * i + 1]) : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                  const float lo = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i)) & 1u ? __uint_as_float(rr[16 * q + 2 * i]) : 0.f;
+                  const float hi2 = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[16 * q + 2 * i + 1]) : 0.f;
                   pk[i] = pack_bf16x2(lo, hi2);
-                  rr[8 * q + 2 * i] = __float_as_uint(lo);
-                  rr[8 * q + 2 * i + 1] = __float_as_uint(hi2);
+                  rr[16 * q + 2 * i] = __float_as_uint(lo);
+                  rr[16 * q + 2 * i + 1] = __float_as_uint(hi2);
                 }
-                reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
               }
             }
           }

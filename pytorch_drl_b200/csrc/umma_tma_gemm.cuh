@@ -164,14 +164,11 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
           if (EPI == EPI_BIAS_RELU_F32) {
             float* o = reinterpret_cast<float*>(args.out) + (int64_t)m * args.out_ld + n;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 bb = *reinterpret_cast<const float4*>(sBias + ch * 32 + 4 * q);
-              float4 v;
-              v.x = fmaxf(__uint_as_float(r[4 * q + 0]) + bb.x, 0.f);
-              v.y = fmaxf(__uint_as_float(r[4 * q + 1]) + bb.y, 0.f);
-              v.z = fmaxf(__uint_as_float(r[4 * q + 2]) + bb.z, 0.f);
-              v.w = fmaxf(__uint_as_float(r[4 * q + 3]) + bb.w, 0.f);
-              reinterpret_cast<float4*>(o)[q] = v;
+            for (int q = 0; q < 4; ++q) {
+              uint32_t v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(r[8 * q + i]) + sBias[ch * 32 + 8 * q + i], 0.f));
+              stg_v8(o + 8 * q, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
             }
           } else {
             const int64_t off = (int64_t)m * args.out_ld + n;
@@ -189,17 +186,17 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
               mb = relu_bits_from_pairs(mw);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t pk[4];
+            for (int q = 0; q < 2; ++q) {
+              uint32_t pk[8];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float lo = (mb >> relu_bit_pos(8 * q + 2 * i)) & 1u ? __uint_as_float(r[8 * q + 2 * i]) : 0.f;
-                const float hi2 = (mb >> relu_bit_pos(8 * q + 2 * i + 1)) & 1u ? __uint_as_float(r[8 * q + 2 * i + 1]) : 0.f;
+              for (int i = 0; i < 8; ++i) {
+                const float lo = (mb >> relu_bit_pos(16 * q + 2 * i)) & 1u ? __uint_as_float(r[16 * q + 2 * i]) : 0.f;
+                const float hi2 = (mb >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? __uint_as_float(r[16 * q + 2 * i + 1]) : 0.f;
                 pk[i] = pack_bf16x2(lo, hi2);
-                r[8 * q + 2 * i] = __float_as_uint(lo);
-                r[8 * q + 2 * i + 1] = __float_as_uint(hi2);
+                r[16 * q + 2 * i] = __float_as_uint(lo);
+                r[16 * q + 2 * i + 1] = __float_as_uint(hi2);
               }
-              reinterpret_cast<uint4*>(o)[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             }
           }
         }
