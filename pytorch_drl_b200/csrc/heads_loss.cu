@@ -19,10 +19,14 @@ constexpr int kFeat = 512;
 constexpr int kWarps = 8;
 
 
-template <typename T> __device__ __forceinline__ void store_act(T* p, float v);
-template <> __device__ __forceinline__ void store_act<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void store_act<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-  *p = __float2bfloat16_rn(v);
+// a lane owns the column PAIRS (64q + 2*lane, +1), q = 0..7: features load as float2, d(feat) stores as one
+// 4-byte bf16x2 (or float2) per pair
+template <typename T> __device__ __forceinline__ void store_act2(T* p, float a, float b);
+template <> __device__ __forceinline__ void store_act2<float>(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <> __device__ __forceinline__ void store_act2<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
 // MODE 0: forward only (logits/values/logp/entropy);  MODE 1: + losses;  MODE 2: + backward.
@@ -63,7 +67,10 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
     float f[16];
     if (live) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) f[q] = feat[(size_t)i * kFeat + lane + 32 * q];
+      for (int q = 0; q < 8; ++q) {
+        const float2 v = *reinterpret_cast<const float2*>(feat + (size_t)i * kFeat + 64 * q + 2 * lane);
+        f[2 * q] = v.x; f[2 * q + 1] = v.y;
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < 16; ++q) f[q] = 0.f;
@@ -74,7 +81,10 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
       if (o < O) {
         float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) s = fmaf(f[q], Ws[o * kFeat + lane + 32 * q], s);
+        for (int q = 0; q < 8; ++q) {
+          const float2 w = *reinterpret_cast<const float2*>(Ws + o * kFeat + 64 * q + 2 * lane);
+          s = fmaf(f[2 * q], w.x, fmaf(f[2 * q + 1], w.y, s));
+        }
         out[o] = warp_sum(s) + bs[o];
       } else {
         out[o] = 0.f;
@@ -153,15 +163,23 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
         for (int o = 0; o < MAXO; ++o) sd[warp * MAXO + o] = dout[o];
       }
 #pragma unroll
-      for (int q = 0; q < 16; ++q) sf[warp * kFeat + lane + 32 * q] = f[q];
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float2*>(sf + warp * kFeat + 64 * q + 2 * lane) = make_float2(f[2 * q], f[2 * q + 1]);
       if (live) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float d = 0.f;
+        for (int q = 0; q < 8; ++q) {
+          float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-          for (int o = 0; o < MAXO; ++o) if (o < O) d = fmaf(dout[o], Ws[o * kFeat + lane + 32 * q], d);
-          d = f[q] > 0.f ? d : 0.f;                       // ReLU of the fc layer (nature_cnn.py:36)
-          store_act<TD>(dpre + (size_t)i * kFeat + lane + 32 * q, d);
+          for (int o = 0; o < MAXO; ++o) {
+            if (o < O) {
+              const float2 w = *reinterpret_cast<const float2*>(Ws + o * kFeat + 64 * q + 2 * lane);
+              d0 = fmaf(dout[o], w.x, d0);
+              d1 = fmaf(dout[o], w.y, d1);
+            }
+          }
+          d0 = f[2 * q] > 0.f ? d0 : 0.f;                 // ReLU of the fc layer (nature_cnn.py:36)
+          d1 = f[2 * q + 1] > 0.f ? d1 : 0.f;
+          store_act2<TD>(dpre + (size_t)i * kFeat + 64 * q + 2 * lane, d0, d1);
         }
       }
       __syncthreads();
@@ -214,7 +232,7 @@ static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t*
   auto kern = heads_loss_kernel<MAXA, MODE, TD>;
   DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntiles = (nb + kWarps - 1) / kWarps;
-  int blocks = ntiles < sm_count() * 2 ? ntiles : sm_count() * 2;
+  int blocks = ntiles < sm_count() * 4 ? ntiles : sm_count() * 4;   // latency-bound: as many CTAs as the registers allow
   kern<<<blocks, kWarps * 32, smem, st>>>(feat, hpp, row_idx, nb, batch, hp, 1.0f / (float)nb,
                                           losses_out, logits_out, values_out, logp_out, ent_out, dpre);
   DRL_LAUNCH_CHECK();
