@@ -337,7 +337,7 @@ static int make_tmap_dy1(CUtensorMap* m, const void* base, uint64_t nb) {
   return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
 }
 
-template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS = 128>
+template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS, int KB, int KBX, int SHIFT_RW, int PLANES>
 static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st) {
   ProfileScope prof(site, st);
   CUtensorMap tm;
@@ -354,7 +354,8 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   if (a.bias_grad && a.bias_mod != (N == 64 ? 64 : 32)) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   a.use_base_offset = 0;
   if (a.OH * a.RW > MROWS) return DRL_ERR_BAD_ARG;       // every output row must fall inside the tile
-  auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI, MROWS>;
+  if (a.KB != KB || a.KBX != KBX || a.SHIFT_RW != SHIFT_RW || a.planes != PLANES) return DRL_ERR_BAD_ARG;
+  auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI, MROWS, KB, KBX, SHIFT_RW, PLANES>;
   const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
   if (smem > 227 * 1024) return DRL_ERR_BAD_ARG;
   static int configured = 0;
@@ -469,7 +470,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     // stride 2), so tap row ky reads plane ky&1 shifted by (ky>>1)*10 + half and the GEMM rows are oy*10 + ox
     TmaConvArgs c2 = tma_conv_args(8, 2, 10, 10, 0, 1, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
     c2.planes = 2; c2.bits_out = e->bits[1];
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 4, 4, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 4, 4, 2, 128, 8, 2, 10, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
   }
@@ -477,7 +478,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   if (g_debug_flags[1]) {
     TmaConvArgs c3 = tma_conv_args(9, 3, 9, 9, 0, 1, 7, 7, e->w3f, n->act[2], p + o[5], nullptr, 3136, 7 * 64, 64, 1, 0);
     c3.bits_out = e->bits[2];
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 6, 4, 2, 64>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 6, 4, 2, 64, 9, 3, 9, 1>("conv3_fwd", n->act[1], nb, 9, 9, 9, 9, c3, st)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv3_fwd", a3, 1, st)));
   }
@@ -566,7 +567,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
       c.bias_grad = g + o[3]; c.bias_mod = 64;       // conv2 bias gradient
       c.bits_in = e->bits[1];
-      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
+      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2, 128, 9, 3, 11, 1>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
     }
@@ -599,7 +600,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
       c.bias_grad = g + o[1]; c.bias_mod = 32;       // conv1 bias gradient
       c.bits_in = e->bits[0];
-      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 2>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
+      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 2, 128, 4, 2, 11, 1>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
     } else {
       DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
     }

@@ -62,7 +62,9 @@ constexpr int tma_conv_smem(int KB, int raw_buf_bytes, int NR, int slack) {
   return KB * N * 128 + NR * raw_buf_bytes + slack + 1280 + 1024;
 }
 
-template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS = 128>
+// KB / KBX / SHIFT_RW / PLANES (the tap geometry) are compile-time so the whole tap loop of a sample pair unrolls
+// under ONE election and every descriptor is `base + immediate`.
+template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS, int KB, int KBX, int SHIFT_RW, int PLANES>
 __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                            const TmaConvArgs args) {
   using namespace umma;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                         // KB weight tiles, resident
-  uint8_t* sRaw = smem + args.KB * B_BYTES;                   // NR staged samples
+  uint8_t* sRaw = smem + KB * B_BYTES;                        // NR staged samples
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + NR * args.raw_buf_bytes + args.slack_bytes);
   uint64_t* raw_full = bars;                    // [NR]
   uint64_t* raw_empty = bars + NR;              // [NR]
@@ -102,15 +104,15 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
   if (warp == W_TMA) {
     if (lane == 0) {
       // weights: resident for the whole kernel
-      mbar_arrive_expect_tx(b_full, (uint32_t)(args.KB * B_BYTES));
-      for (int kb = 0; kb < args.KB; ++kb)
+      mbar_arrive_expect_tx(b_full, (uint32_t)(KB * B_BYTES));
+      for (int kb = 0; kb < KB; ++kb)
         tma_bulk_g2s(sB + kb * B_BYTES, reinterpret_cast<const uint8_t*>(args.bpack) + (int64_t)kb * B_BYTES, B_BYTES, b_full);
       uint32_t j = 0;
       for (int b = blockIdx.x; b < args.nb; b += gridDim.x, ++j) {
         const uint32_t buf = j % NR;
         mbar_wait(raw_empty + buf, ((j / NR) & 1) ^ 1);
-        mbar_arrive_expect_tx(raw_full + buf, (uint32_t)(args.box_bytes * args.planes));
-        for (int pl = 0; pl < args.planes; ++pl)
+        mbar_arrive_expect_tx(raw_full + buf, (uint32_t)(args.box_bytes * PLANES));
+        for (int pl = 0; pl < PLANES; ++pl)
           tma_load_4d(sRaw + buf * args.raw_buf_bytes + pl * args.plane_bytes, &tmap, 0, -args.pad, -args.pad + pl, b, raw_full + buf);
       }
     }
@@ -136,35 +138,38 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
           tmem_d[t] = tmem_base + acc * N;
         }
         tc_fence_after();
-        int ty = 0, tx = 0;
-        for (int kb = 0; kb < args.KB; ++kb) {
-          const uint32_t shift = args.planes == 2 ? (uint32_t)((ty & 1) * args.plane_bytes) + (uint32_t)((ty >> 1) * args.SHIFT_RW + tx) * 128u
-                                                  : (uint32_t)(ty * args.SHIFT_RW + tx) * 128u;
-          const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
-          const uint32_t a_lo0 = desc_lo(raw_addr[0] + shift, 0), a_lo1 = desc_lo(raw_addr[1] + shift, 0);
-          if (elect_one()) {
-            if (kb == 0) mma_f16_lohi<false>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
-            else mma_f16_lohi<true>(tmem_d[0], a_lo0, hi0, b_lo, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d[0], a_lo0 + 2, hi0, b_lo + 2, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d[0], a_lo0 + 4, hi0, b_lo + 4, hi0, idesc);
-            mma_f16_lohi<true>(tmem_d[0], a_lo0 + 6, hi0, b_lo + 6, hi0, idesc);
-            if (np == 2) {
-              if (kb == 0) mma_f16_lohi<false>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
-              else mma_f16_lohi<true>(tmem_d[1], a_lo1, hi0, b_lo, hi0, idesc);
-              mma_f16_lohi<true>(tmem_d[1], a_lo1 + 2, hi0, b_lo + 2, hi0, idesc);
-              mma_f16_lohi<true>(tmem_d[1], a_lo1 + 4, hi0, b_lo + 4, hi0, idesc);
-              mma_f16_lohi<true>(tmem_d[1], a_lo1 + 6, hi0, b_lo + 6, hi0, idesc);
+        const uint32_t ab0 = desc_lo(raw_addr[0], 0), ab1 = desc_lo(raw_addr[1], 0), pl16 = (uint32_t)args.plane_bytes >> 4;
+        auto issue = [&](auto two) {
+          constexpr bool TWO = decltype(two)::value;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const int ty = kb / KBX, tx = kb % KBX;
+            const uint32_t shift16 = PLANES == 2 ? (uint32_t)(((ty >> 1) * SHIFT_RW + tx) * 8) + ((ty & 1) ? pl16 : 0u)
+                                                 : (uint32_t)((ty * SHIFT_RW + tx) * 8);
+            const uint32_t b_lo = b_lo0 + kb * (B_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (kb == 0 && k == 0) mma_f16_lohi<false>(tmem_d[0], ab0 + shift16, hi0, b_lo, hi0, idesc);
+              else mma_f16_lohi<true>(tmem_d[0], ab0 + shift16 + 2 * k, hi0, b_lo + 2 * k, hi0, idesc);
+            }
+            if (TWO) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (kb == 0 && k == 0) mma_f16_lohi<false>(tmem_d[1], ab1 + shift16, hi0, b_lo, hi0, idesc);
+                else mma_f16_lohi<true>(tmem_d[1], ab1 + shift16 + 2 * k, hi0, b_lo + 2 * k, hi0, idesc);
+              }
             }
           }
-          __syncwarp();
-          if (++tx == args.KBX) { tx = 0; ++ty; }
-        }
-        if (elect_one()) {
-          for (int t = 0; t < np; ++t) {
-            const uint32_t jj = (uint32_t)(j + t);
-            mma_commit(tfull + jj % NACC);
-            mma_commit(raw_empty + jj % NR);       // staged sample free once every MMA reading it has retired
+          mma_commit(tfull + (uint32_t)j % NACC);
+          mma_commit(raw_empty + (uint32_t)j % NR);       // staged sample free once every MMA reading it has retired
+          if (TWO) {
+            mma_commit(tfull + (uint32_t)(j + 1) % NACC);
+            mma_commit(raw_empty + (uint32_t)(j + 1) % NR);
           }
+        };
+        if (elect_one()) {
+          if (np == 2) issue(std::true_type{});
+          else issue(std::false_type{});
         }
         __syncwarp();
       }
