@@ -30,13 +30,16 @@ template <> __device__ __forceinline__ void store_act2<__nv_bfloat16>(__nv_bfloa
 }
 
 // MODE 0: forward only (logits/values/logp/entropy);  MODE 1: + losses;  MODE 2: + backward.
-template <int MAXA, int MODE, typename TD>
+// OX = A + K when the launcher knows it at compile time (the Atari cases), else 0: the three O x 512 loops then
+// run exactly O iterations; with OX = 0 their iterations o >= O are predicated off but still take issue slots.
+template <int MAXA, int MODE, typename TD, int OX = 0>
 __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
     const float* __restrict__ feat, HeadParams hp_ptrs, const int64_t* __restrict__ row_idx, int nb,
     drl_ppo_batch_t batch, drl_ppo_hyper_t hp, float inv_nb, float* __restrict__ losses_out,
     float* __restrict__ logits_out, float* __restrict__ values_out, float* __restrict__ logp_out,
     float* __restrict__ ent_out, TD* __restrict__ dpre) {
   constexpr int MAXO = MAXA + DRL_MAX_REWARD_STREAMS;
+  constexpr int OLOOP = OX ? OX : MAXO;
   extern __shared__ float smem[];
   const int A = hp.num_actions, K = hp.num_streams, O = A + K;
   float* Ws = smem;                              // [O][512]
@@ -77,8 +80,10 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
     }
     float out[MAXO];
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o) {
-      if (o < O) {
+    for (int o = OLOOP; o < MAXO; ++o) out[o] = 0.f;
+#pragma unroll
+    for (int o = 0; o < OLOOP; ++o) {
+      if (OX || o < O) {
         float s = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -170,8 +175,8 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
         for (int q = 0; q < 8; ++q) {
           float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-          for (int o = 0; o < MAXO; ++o) {
-            if (o < O) {
+          for (int o = 0; o < OLOOP; ++o) {
+            if (OX || o < O) {
               const float2 w = *reinterpret_cast<const float2*>(Ws + o * kFeat + 64 * q + 2 * lane);
               d0 = fmaf(dout[o], w.x, d0);
               d1 = fmaf(dout[o], w.y, d1);
@@ -188,8 +193,8 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
       for (int s = 0; s < kWarps; ++s) {
         const float f0 = sf[s * kFeat + c0], f1 = sf[s * kFeat + c1];
 #pragma unroll
-        for (int o = 0; o < MAXO; ++o) {
-          if (o < O) {
+        for (int o = 0; o < OLOOP; ++o) {
+          if (OX || o < O) {
             const float d = sd[s * MAXO + o];
             gw[o][0] = fmaf(d, f0, gw[o][0]);
             gw[o][1] = fmaf(d, f1, gw[o][1]);
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
   }
 }
 
-template <int MAXA, int MODE, typename TD>
+template <int MAXA, int MODE, typename TD, int OX = 0>
 static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t* row_idx, int nb,
                         const drl_ppo_batch_t& batch, const drl_ppo_hyper_t& hp, float* losses_out,
                         float* logits_out, float* values_out, float* logp_out, float* ent_out,
@@ -229,7 +234,7 @@ static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t*
   constexpr int MAXO = MAXA + DRL_MAX_REWARD_STREAMS;
   const int O = hp.num_actions + hp.num_streams;
   const size_t smem = sizeof(float) * ((size_t)O * kFeat + MAXO + kWarps * kFeat + kWarps * MAXO + 128);
-  auto kern = heads_loss_kernel<MAXA, MODE, TD>;
+  auto kern = heads_loss_kernel<MAXA, MODE, TD, OX>;
   DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ntiles = (nb + kWarps - 1) / kWarps;
   int blocks = ntiles < sm_count() * 4 ? ntiles : sm_count() * 4;   // latency-bound: as many CTAs as the registers allow
@@ -256,6 +261,22 @@ int heads_loss_dispatch(int mode, bool dpre_is_bf16, const float* feat, const He
     if (dpre_is_bf16) GO(MAXA, 2, __nv_bfloat16);                  \
     GO(MAXA, 2, float);                                            \
   } while (0)
+  // training step of the common Atari heads: exact output count known at compile time
+#define GOX(MAXA, OXV)                                                                                              \
+  do {                                                                                                              \
+    if (dpre_is_bf16)                                                                                               \
+      return launch_heads<MAXA, 2, __nv_bfloat16, OXV>(feat, hpp, row_idx, nb, batch, hp, losses_out, logits_out,    \
+                                                       values_out, logp_out, ent_out, (__nv_bfloat16*)dpre, st);    \
+    return launch_heads<MAXA, 2, float, OXV>(feat, hpp, row_idx, nb, batch, hp, losses_out, logits_out, values_out, \
+                                             logp_out, ent_out, (float*)dpre, st);                                  \
+  } while (0)
+  if (mode == 2 && hp.num_streams == 1) {
+    if (A == 4) GOX(8, 5);
+    if (A == 6) GOX(8, 7);
+    if (A == 9) GOX(18, 10);
+    if (A == 18) GOX(18, 19);
+  }
+#undef GOX
   if (A <= 8) BY_MODE(8);
   if (A <= 18) BY_MODE(18);
   BY_MODE(32);
