@@ -87,7 +87,7 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
 
 // 8 uint8 -> 8 fp16 holding 1024 + b (bytes become the mantissa of 0x6400 = 1024.0): one PRMT per pair.
 // The constant 1024 * sum_k W[n][k] this adds to every accumulator is folded into the bias
-// (conv1_bias_eff_kernel), so the forward conversion costs 4 instructions per 8 pixels.
+// (last block of pack_all_kernel), so the forward conversion costs 4 instructions per 8 pixels.
 __device__ __forceinline__ uint4 u8x8_to_f16x8_biased(uint2 w) {
   const uint32_t magic = 0x64006400u;
   return make_uint4(__byte_perm(w.x, magic, 0x7170), __byte_perm(w.x, magic, 0x7372),

@@ -29,25 +29,12 @@ struct Bf16Engine {
   void* wfd = nullptr;   // fc dgrad    bf16 row-major [3136][512] = the transpose      (TMA tensor map)
   void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
   uint32_t* bits[3] = {nullptr, nullptr, nullptr};   // ReLU masks of act1/act2/act3, 1 bit per element
-  float* b1eff = nullptr; // conv1 effective bias (see conv1_bias_eff_kernel)
+  float* b1eff = nullptr; // conv1 effective bias (last block of pack_all_kernel)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
 };
 
 // ---- packing -----------------------------------------------------------------------------------------
 enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_CONV1_S2D = 5 };
-
-// fc weights as plain row-major bf16 matrices in the NHWC feature order k = hw*64 + c (TMA operands)
-__global__ void __launch_bounds__(256) pack_fc_plain_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
-                                                            __nv_bfloat16* __restrict__ dgrad) {
-  const int total = 512 * 3136;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int n = e / 3136, k = e - n * 3136;
-    const int hw = k >> 6, c = k & 63;
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[(size_t)n * 3136 + c * 49 + hw]);
-    fwd[e] = v;
-    dgrad[(size_t)k * 512 + n] = v;
-  }
-}
 
 struct PackArgs {
   const float* w;      // reference-layout fp32 weights of the layer
@@ -90,42 +77,73 @@ __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n,
   }
 }
 
-__global__ void __launch_bounds__(256) pack_tiles_kernel(const PackArgs a) {
-  const int64_t total = (int64_t)a.variants * a.KB * a.N * 64;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(e & 63);
-    const int n = (int)((e >> 6) % a.N);
-    const int64_t t = (e >> 6) / a.N;
-    const int kb = (int)(t % a.KB), variant = (int)(t / a.KB);
-    const float v = pack_src(a, variant, n, kb * 64 + kk);
-    const int64_t tile_bytes = (int64_t)a.N * 128;
-    const int64_t off = t * tile_bytes + umma::swz_off<128>((uint32_t)n, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
-    if (a.fp16) *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(a.out) + off) = __float2half_rn(v);
-    else *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(a.out) + off) = __float2bfloat16_rn(v);
+// ---- all operand layouts of one Adam step in ONE launch ---------------------------------------------------
+// Block ranges: [0, fc_blocks) the two plain fc matrices, then one range per tile-image job, the last block
+// computes conv1's effective bias.
+struct PackAllArgs {
+  PackArgs job[8];
+  int first_block[9];     // job j owns blocks [first_block[j], first_block[j+1])
+  int n_jobs;
+  const float* wfc; __nv_bfloat16* fc_fwd; __nv_bfloat16* fc_dgrad; int fc_blocks;
+  const float* w1; const float* b1; float scale; float* b1eff;
+};
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackAllArgs a) {
+  const int blk = blockIdx.x;
+  if (blk < a.fc_blocks) {
+    // fc weights [512][c*49+hw] -> forward [n][k = hw*64+c] and its transpose [k][n]; 32x32 tiles through shared
+    // memory so both writes are coalesced
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int tiles_k = 3136 / 32, n_tiles = 16 * tiles_k;
+    for (int t = blk; t < n_tiles; t += a.fc_blocks) {
+      const int tn = t / tiles_k, tk = t - tn * tiles_k;
+      const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = tn * 32 + ty + 8 * r, k = tk * 32 + tx;
+        const int hw = k >> 6, c = k & 63;
+        const __nv_bfloat16 v = __float2bfloat16_rn(a.wfc[(size_t)n * 3136 + c * 49 + hw]);
+        a.fc_fwd[(size_t)n * 3136 + k] = v;
+        tile[ty + 8 * r][tx] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = tk * 32 + ty + 8 * r, n = tn * 32 + tx;
+        a.fc_dgrad[(size_t)k * 512 + n] = tile[tx][ty + 8 * r];
+      }
+      __syncthreads();
+    }
+    return;
   }
-}
-
-static int pack_one(const float* w, void* out, int mode, int fp16, int variants, int KB, int N, int Cin, int KH,
-                    int KW, int Cout, cudaStream_t st) {
-  PackArgs a{w, out, mode, fp16, variants, KB, N, Cin, KH, KW, Cout};
-  const int64_t total = (int64_t)variants * KB * N * 64;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  pack_tiles_kernel<<<blocks, 256, 0, st>>>(a);
-  DRL_LAUNCH_CHECK();
-  return DRL_OK;
-}
-
-// conv1 forward feeds the tensor core fp16 operands holding 1024 + pixel; the resulting constant
-// 1024 * sum_k fp16(W1[n][k]) per output channel is removed through the bias:
-//   y = acc * s + b_eff,  b_eff[n] = b[n] - 1024 * s * sum_k fp16(W1[n][k])      (s = float32(1/255))
-__global__ void conv1_bias_eff_kernel(const float* __restrict__ w, const float* __restrict__ b, float scale,
-                                      float* __restrict__ out) {
-  const int n = threadIdx.x;
-  if (n >= 32) return;
-  double s = 0.0;
-  for (int k = 0; k < 256; ++k) s += (double)__half2float(__float2half_rn(w[n * 256 + k]));
-  out[n] = (float)((double)b[n] - 1024.0 * (double)scale * s);
+  const int jb = blk - a.fc_blocks;
+  if (jb >= a.first_block[a.n_jobs]) {          // last block: conv1 effective bias, one warp per 4 output channels
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = warp; n < 32; n += 8) {
+      double s = 0.0;
+      for (int k = lane; k < 256; k += 32) s += (double)__half2float(__float2half_rn(a.w1[n * 256 + k]));
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) a.b1eff[n] = (float)((double)a.b1[n] - 1024.0 * (double)a.scale * s);
+    }
+    return;
+  }
+  int j = 0;
+  while (j + 1 < a.n_jobs && jb >= a.first_block[j + 1]) ++j;
+  const PackArgs& pa = a.job[j];
+  const int nblk = a.first_block[j + 1] - a.first_block[j], lb = jb - a.first_block[j];
+  const int64_t total = (int64_t)pa.variants * pa.KB * pa.N * 64;
+  for (int64_t e = (int64_t)lb * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
+    const int kk = (int)(e & 63);
+    const int n = (int)((e >> 6) % pa.N);
+    const int64_t t = (e >> 6) / pa.N;
+    const int kb = (int)(t % pa.KB), variant = (int)(t / pa.KB);
+    const float v = pack_src(pa, variant, n, kb * 64 + kk);
+    const int64_t tile_bytes = (int64_t)pa.N * 128;
+    const int64_t off = t * tile_bytes + umma::swz_off<128>((uint32_t)n, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
+    if (pa.fp16) *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(pa.out) + off) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(pa.out) + off) = __float2bfloat16_rn(v);
+  }
 }
 
 // ---- bias gradients: column sums of a bf16 [R, C] matrix, C in {32, 64, 512} -----------------------------
@@ -221,16 +239,28 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   Bf16Engine* e = n->bf16;
   const float* p = n->params;
   const int64_t* o = n->off;
-  DRL_TRY(pack_one(p + o[0], e->w1f, PK_CONV_FWD, 1, 1, 4, 32, 4, 8, 8, 32, st));
-  DRL_TRY(pack_one(p + o[0], e->w1s, PK_CONV1_S2D, 1, 1, 4, 32, 4, 8, 8, 32, st));
-  conv1_bias_eff_kernel<<<1, 32, 0, st>>>(p + o[0], p + o[1], kInv255, e->b1eff);
+  PackAllArgs a{};
+  int nj = 0, blocks = 0;
+  auto add = [&](const float* w, void* out, int mode, int fp16, int variants, int KB, int N, int Cin, int KH, int KW, int Cout) {
+    a.job[nj] = PackArgs{w, out, mode, fp16, variants, KB, N, Cin, KH, KW, Cout};
+    a.first_block[nj] = blocks;
+    const int64_t total = (int64_t)variants * KB * N * 64;
+    int b = (int)((total + 1023) / 1024);               // ~4 elements per thread
+    blocks += b < 1 ? 1 : b;
+    ++nj;
+  };
+  add(p + o[0], e->w1f, PK_CONV_FWD, 1, 1, 4, 32, 4, 8, 8, 32);
+  add(p + o[0], e->w1s, PK_CONV1_S2D, 1, 1, 4, 32, 4, 8, 8, 32);
+  add(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64);
+  add(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64);
+  add(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64);
+  add(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 1, 4, 128, 32, 4, 4, 64);
+  a.first_block[nj] = blocks;
+  a.n_jobs = nj;
+  a.wfc = p + o[6]; a.fc_fwd = (__nv_bfloat16*)e->wff; a.fc_dgrad = (__nv_bfloat16*)e->wfd; a.fc_blocks = sm_count() * 2;
+  a.w1 = p + o[0]; a.b1 = p + o[1]; a.scale = kInv255; a.b1eff = e->b1eff;
+  pack_all_kernel<<<a.fc_blocks + blocks + 1, 256, 0, st>>>(a);
   DRL_LAUNCH_CHECK();
-  DRL_TRY(pack_one(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64, st));
-  DRL_TRY(pack_one(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64, st));
-  pack_fc_plain_kernel<<<sm_count() * 4, 256, 0, st>>>(p + o[6], (__nv_bfloat16*)e->wff, (__nv_bfloat16*)e->wfd);
-  DRL_LAUNCH_CHECK();
-  DRL_TRY(pack_one(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64, st));
-  DRL_TRY(pack_one(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 1, 4, 128, 32, 4, 4, 64, st));
   return DRL_OK;
 }
 
