@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
 
   float gw[MAXO][2];
   float gb = 0.f;
+  float gfc[16];                                  // running column sums of this lane's d(feat) columns
+#pragma unroll
+  for (int q = 0; q < 16; ++q) gfc[q] = 0.f;
   if (MODE == 2) {
 #pragma unroll
     for (int o = 0; o < MAXO; ++o) { gw[o][0] = 0.f; gw[o][1] = 0.f; }
@@ -184,6 +187,8 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
           }
           d0 = f[2 * q] > 0.f ? d0 : 0.f;                 // ReLU of the fc layer (nature_cnn.py:36)
           d1 = f[2 * q + 1] > 0.f ? d1 : 0.f;
+          gfc[2 * q] += d0;
+          gfc[2 * q + 1] += d1;
           store_act2<TD>(dpre + (size_t)i * kFeat + 64 * q + 2 * lane, d0, d1);
         }
       }
@@ -222,6 +227,18 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
     if (threadIdx.x < O) {
       float* g = threadIdx.x < A ? hp_ptrs.gbp + threadIdx.x : hp_ptrs.gbv[threadIdx.x - A];
       atomicAdd(g, gb);
+    }
+    if (hp_ptrs.gfc_bias) {                       // fc bias gradient: sum the 8 warps' column sums through smem
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float2*>(sf + warp * kFeat + 64 * q + 2 * lane) = make_float2(gfc[2 * q], gfc[2 * q + 1]);
+      __syncthreads();
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { t0 += sf[w * kFeat + c0]; t1 += sf[w * kFeat + c1]; }
+      atomicAdd(hp_ptrs.gfc_bias + c0, t0);
+      atomicAdd(hp_ptrs.gfc_bias + c1, t1);
     }
   }
 }

@@ -30,6 +30,8 @@ static void head_params(const drl_net* net, const float* params, float* grads, H
   const int64_t* o = net->off;
   hp.wp = params + o[8]; hp.bp = params + o[9];
   hp.gwp = grads ? grads + o[8] : nullptr; hp.gbp = grads ? grads + o[9] : nullptr;
+  // the bf16 engine takes the fc bias gradient from the heads kernel (the fp32 engine computes its own)
+  hp.gfc_bias = (grads && net->precision == DRL_PRECISION_BF16) ? grads + o[7] : nullptr;
   for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) {
     const bool on = k < net->K;
     hp.wv[k] = on ? params + o[10 + 2 * k] : nullptr;

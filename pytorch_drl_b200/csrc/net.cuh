@@ -29,6 +29,7 @@ struct HeadParams {            // pointers into the flat parameter / gradient bu
   const float* wv[DRL_MAX_REWARD_STREAMS]; const float* bv[DRL_MAX_REWARD_STREAMS];
   float* gwp; float* gbp;
   float* gwv[DRL_MAX_REWARD_STREAMS]; float* gbv[DRL_MAX_REWARD_STREAMS];
+  float* gfc_bias;               // if set: += column sums of d(feat) (the fc layer's bias gradient), fused
 };
 
 int64_t net_param_offsets(int A, int K, int64_t* off);

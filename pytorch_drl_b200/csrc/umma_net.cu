@@ -537,12 +537,8 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
   const int sms = sm_count();
   auto splits = [&](int M, int gy) { int s = (M + 31) / 32; int gx = (sms + gy - 1) / gy; return s < gx ? s : gx; };
 
-  // ---- fc: bias, weight gradient (3136 x 512, split over the batch), data gradient (masked by act3 > 0)
-  {
-    ProfileScope prof("bias_grad", st);
-    colsum512_bf16_kernel<<<sms * 2 < nb ? sms * 2 : nb, 256, 0, st>>>((const __nv_bfloat16*)n->dpre, nb, g + o[7]);
-    DRL_LAUNCH_CHECK();
-  }
+  // ---- fc: weight gradient (3136 x 512, split over the batch), data gradient (masked by act3 > 0); the fc bias
+  //      gradient was accumulated by the heads kernel (HeadParams::gfc_bias)
   {
     ProfileScope prof("fc_wgrad", st);
     using Cf = WgradTmaCfg<256, 1>;
