@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);     // [0,256) 8 accumulators, [256,512) tap-(0,0) A operand of 2 samples x 4 tiles
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -271,15 +271,23 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
     __syncwarp();
   } else if (warp >= W_CONV) {
     // ================= converters: raw uint8 frame -> 1024-biased fp16 block image ======================
-    const int t = threadIdx.x - 32 * W_CONV;
+    // Thread (quarter = warp & 3, lane) converts blocks q = tile*128 + quarter*32 + lane for two tiles.  For tap
+    // (0,0) the A row of GEMM row r IS image row r, and tile row q % 128 lives in this thread's own TMEM lane: the
+    // 32 registers it just produced also go to tensor memory (tcgen05.st), so that tap is issued in TS form and a
+    // quarter of the A operand never crosses the shared-memory port.
+    const int quarter = warp & 3, half = (warp - W_CONV) >> 2;
+    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
     for (int j = 0; j < n_mine; ++j) {
       const uint32_t s = j & 1, ph = (j >> 1) & 1;
       mbar_wait(raw_full + s, ph);
       mbar_wait(img_empty + s, ph ^ 1);
+      tc_fence_after();
       const uint32_t raw = smem_u32(sRaw + s * kS2dRawBytes), img = smem_u32(sImg + s * kS2dFImgBytes);
 #pragma unroll
       for (int rep = 0; rep < 2; ++rep) {
-        const int q = t + rep * NCONV;                     // block index by*21 + bx
+        const int tile = 2 * half + rep;
+        const int q = tile * 128 + quarter * 32 + lane;    // block index by*21 + bx
+        uint32_t r[32];
         if (q < 441) {
           const int by = (q * 3121) >> 16;                 // q / 21
           const int bx = q - by * 21;
@@ -290,11 +298,20 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
           const uint32_t dst = img + (uint32_t)q * 128u;
 #pragma unroll
           for (int dy = 0; dy < 4; ++dy) {
-            st_shared_v4(dst + (((uint32_t)(2 * dy) ^ ((uint32_t)q & 7u)) << 4), u8x8_to_f16x8_biased(make_uint2(v[dy].x, v[dy].y)));
-            st_shared_v4(dst + (((uint32_t)(2 * dy + 1) ^ ((uint32_t)q & 7u)) << 4), u8x8_to_f16x8_biased(make_uint2(v[dy].z, v[dy].w)));
+            const uint4 a = u8x8_to_f16x8_biased(make_uint2(v[dy].x, v[dy].y)), b = u8x8_to_f16x8_biased(make_uint2(v[dy].z, v[dy].w));
+            st_shared_v4(dst + (((uint32_t)(2 * dy) ^ ((uint32_t)q & 7u)) << 4), a);
+            st_shared_v4(dst + (((uint32_t)(2 * dy + 1) ^ ((uint32_t)q & 7u)) << 4), b);
+            r[8 * dy] = a.x; r[8 * dy + 1] = a.y; r[8 * dy + 2] = a.z; r[8 * dy + 3] = a.w;
+            r[8 * dy + 4] = b.x; r[8 * dy + 5] = b.y; r[8 * dy + 6] = b.z; r[8 * dy + 7] = b.w;
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
+        tmem_st_32x32b_x32(tmem_base + t_lane + 256 + s * 128 + tile * 32, r);
       }
+      tmem_st_wait();
+      tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(img_full + s);
       mbar_arrive(raw_empty + s);
@@ -316,15 +333,19 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
         tc_fence_after();
         const uint32_t a_tile = a_lo0 + s * (kS2dFImgBytes >> 4) + tile * ((128 * 128) >> 4);
         const uint32_t t_d = tmem_base + acc * 32;
+        const uint32_t t_a = tmem_base + 256 + s * 128 + tile * 32;      // tap (0,0): A rows straight from the converters
         if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < 4; ++tap) {
+          for (int k = 0; k < 4; ++k) {
+            if (k == 0) mma_f16_ts<false>(t_d, t_a, b_lo0, hi, idesc);
+            else mma_f16_ts<true>(t_d, t_a + k * 8, b_lo0 + k * 2, hi, idesc);
+          }
+#pragma unroll
+          for (int tap = 1; tap < 4; ++tap) {
             const uint32_t a_lo = a_tile + (((tap >> 1) * 21 + (tap & 1)) * 128 >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (tap == 0 && k == 0) mma_f16_lohi<false>(t_d, a_lo, hi, b_lo0, hi, idesc);
-              else mma_f16_lohi<true>(t_d, a_lo + k * 2, hi, b_lo0 + tap * (4096 >> 4) + k * 2, hi, idesc);
-            }
+            for (int k = 0; k < 4; ++k)
+              mma_f16_lohi<true>(t_d, a_lo + k * 2, hi, b_lo0 + tap * (4096 >> 4) + k * 2, hi, idesc);
           }
           mma_commit(tfull + acc);
           if (tile == 3) mma_commit(img_empty + s);
@@ -365,7 +386,7 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
   __syncthreads();
   if (warp == W_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
