@@ -259,6 +259,13 @@ int drl_comm_create(drl_comm_t** out, const uint8_t* id_host, int rank, int worl
 int drl_comm_destroy(drl_comm_t* comm);
 /* In-place SUM allreduce of a flat fp32 buffer in `n_buckets` buckets given by bucket_offsets
  * [n_buckets+1] (host, elements), issued in order on `stream`. */
+/* Attach (or detach, comm = NULL) a communicator to a network handle: drl_net_ppo_step then returns gradients
+ * that are already SUMMED over the ranks — what DistributedDataParallel's backward hooks do in the reference
+ * (drl/utils/launch.py:310, drl/algos/ppo.py:233) — and overlaps the exchange with the backward pass: the
+ * fc + heads range (95 % of the parameters) is all-reduced on a side stream as soon as its gradients are final
+ * (after the fc weight-gradient kernel), while the convolution gradients are still being computed; the small
+ * convolution range follows after the last kernel.  The caller's stream waits for both before returning work. */
+int drl_net_set_comm(drl_net_t* net, drl_comm_t* comm);
 int drl_grad_allreduce_bucketed(drl_comm_t* comm, float* flat, const int64_t* bucket_offsets_host,
                                 int n_buckets, void* stream);
 

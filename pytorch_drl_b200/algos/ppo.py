@@ -116,6 +116,8 @@ class PPO:
         self._vf_loss_clipping, self._vf_simple_weighting = vf_loss_clipping, vf_simple_weighting
         self._envs_per_rank, self._comm = envs_per_rank, comm
         self._engine = self._policy_net._require_engine()
+        if comm is not None and hasattr(comm, 'attach'):
+            comm.attach(self._engine)                # gradient exchange overlapped with the backward pass
         self._samplers = []
         for e in range(envs_per_rank):
             rng = None
@@ -234,8 +236,8 @@ class PPO:
             raise ValueError('minibatch larger than the engine max_batch')
         losses = eng.ppo_step(minibatch['observations'], rows, self._batch(minibatch), self._hyper(), grads=True)
         world = self._world_size if self._comm is not None else 1
-        if self._comm is not None:
-            self._comm.allreduce_grads(eng)
+        if self._comm is not None and getattr(eng, 'comm_attached', None) is not self._comm:
+            self._comm.allreduce_grads(eng)          # not attached: exchange after the backward pass
         lr, betas, eps = self._optimizer_hparams()
         eng.adam_step(lr, betas, eps, grad_scale=1.0 / world)
         return losses

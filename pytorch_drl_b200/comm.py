@@ -68,6 +68,13 @@ class Communicator:
     def allreduce_grads(self, engine) -> None:
         self.allreduce_(engine.grads, self.grad_buckets(engine.offsets))
 
+    def attach(self, engine) -> None:
+        """Let the engine's ppo_step exchange its gradients itself, overlapped with the backward pass (the
+        role of DDP's bucket hooks, launch.py:310): the fc + heads bucket starts as soon as the fc weight
+        gradient is done, the conv bucket follows the last kernel."""
+        check(self._L.drl_net_set_comm(engine._h, self._h), 'net_set_comm')
+        engine.comm_attached = self
+
     def mean_(self, vec: tc.Tensor) -> tc.Tensor:
         """global_mean of a small fp32 CUDA vector (metrics.py:8-26), one collective."""
         v = vec.contiguous()

@@ -49,6 +49,8 @@ static NcclApi* nccl_api() {
 struct drl_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, device = 0;
+  cudaStream_t side = nullptr;          // overlapped gradient exchange (drl_net_set_comm)
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
 };
 
 using namespace drl;
@@ -78,6 +80,13 @@ extern "C" int drl_comm_create(drl_comm_t** out, const uint8_t* id_host, int ran
   ncclUniqueId id;
   memcpy(&id, id_host, sizeof(id));
   if (api->CommInitRank(&c->comm, world, id, rank) != ncclSuccess) { delete c; return DRL_ERR_NCCL; }
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+    api->CommDestroy(c->comm);
+    delete c;
+    return DRL_ERR_CUDA;
+  }
   *out = c;
   return DRL_OK;
 }
@@ -86,6 +95,9 @@ extern "C" int drl_comm_destroy(drl_comm_t* c) {
   if (!c) return DRL_OK;
   NcclApi* api = nccl_api();
   if (api && c->comm) api->CommDestroy(c->comm);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
   delete c;
   return DRL_OK;
 }
@@ -106,3 +118,30 @@ extern "C" int drl_grad_allreduce_bucketed(drl_comm_t* c, float* flat, const int
   }
   return DRL_OK;
 }
+
+// ---- overlapped exchange used by the network handle (net.cu / umma_net.cu) ---------------------------------
+namespace drl {
+
+// SUM all-reduce of flat[lo, hi) on the communicator's side stream, ordered after everything `producer` has queued
+int comm_allreduce_after(drl_comm* c, float* flat, int64_t lo, int64_t hi, cudaStream_t producer) {
+  if (!c || hi <= lo) return DRL_OK;
+  NcclApi* api = nccl_api();
+  if (!api) return DRL_ERR_NCCL;
+  DRL_CUDA(cudaEventRecord(c->ev_ready, producer));
+  DRL_CUDA(cudaStreamWaitEvent(c->side, c->ev_ready, 0));
+  if (api->AllReduce(flat + lo, flat + lo, (size_t)(hi - lo), ncclFloat, ncclSum, c->comm, c->side) != ncclSuccess)
+    return DRL_ERR_NCCL;
+  return DRL_OK;
+}
+
+// `consumer` waits for everything queued on the side stream so far
+int comm_join(drl_comm* c, cudaStream_t consumer) {
+  if (!c) return DRL_OK;
+  DRL_CUDA(cudaEventRecord(c->ev_done, c->side));
+  DRL_CUDA(cudaStreamWaitEvent(consumer, c->ev_done, 0));
+  return DRL_OK;
+}
+
+int comm_world(const drl_comm* c) { return c ? c->world : 1; }
+
+}  // namespace drl

@@ -10,8 +10,10 @@ struct Bf16Engine;
 
 }  // namespace drl
 
+struct drl_comm;
 struct drl_net {
   int device = 0, max_batch = 0, A = 0, K = 0, precision = 0;
+  drl_comm* comm = nullptr;            // if attached: ppo_step all-reduces the gradients, overlapped with the backward
   int64_t nparams = 0;
   int64_t off[8 + 2 + 2 * DRL_MAX_REWARD_STREAMS + 1] = {0};
   const float* params = nullptr;       // caller-owned flat fp32 parameters (reference layouts)
@@ -49,6 +51,9 @@ int bf16_alloc(drl_net* n);
 void bf16_free(drl_net* n);
 int bf16_pack_params(drl_net* n, cudaStream_t st);
 int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, cudaStream_t st);
+int comm_allreduce_after(drl_comm* c, float* flat, int64_t lo, int64_t hi, cudaStream_t producer);
+int comm_join(drl_comm* c, cudaStream_t consumer);
+int comm_world(const drl_comm* c);
 int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, float* grads, cudaStream_t st);
 
 }  // namespace drl

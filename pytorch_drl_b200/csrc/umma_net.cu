@@ -559,6 +559,9 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     kern<<<dim3(gx, 50), 192, Cf::kSmem, st>>>(tp, td, w);
     DRL_LAUNCH_CHECK();
   }
+  // fc weights, fc bias and the heads (everything from the fc weight on = 95 % of the gradient) are final: start
+  // their all-reduce on the side stream while the convolution gradients are computed
+  if (n->comm && comm_world(n->comm) > 1) DRL_TRY(comm_allreduce_after(n->comm, g, o[6], n->nparams, st));
   {
     TmaGemmArgs a{};
     a.M = nb; a.N_total = 3136; a.KB = 8; a.out = n->dact[2]; a.out_ld = 3136; a.bias = nullptr;
