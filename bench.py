@@ -162,6 +162,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--debug-flags', default='', help='kernel-variant experiments, e.g. "2=1,3=0" (drl_debug_set)')
+    ap.add_argument('--comm', default='nccl', choices=['p2p-overlap', 'p2p', 'p2p-1', 'nccl-overlap', 'nccl', 'nccl-1'],
+                    help='gradient exchange variant at N > 1: NCCL or NVLink peer-memory kernels, after the backward pass (2 buckets / -1: one) or overlapped with it')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -198,7 +200,11 @@ def main():
          'value_extrinsic': agents.SimpleValueHead(512, w_init=lambda w: tc.nn.init.orthogonal_(w, gain=0.01), b_init=tc.nn.init.zeros_)})
     agent.fuse(max_batch=nb, precision=args.precision, device=dev)
     opt = tc.optim.Adam(agent.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5)
-    comm = Communicator(rank, world, local_rank) if world > 1 else None
+    comm = None
+    if world > 1:
+        comm = Communicator(rank, world, local_rank, p2p_elems=(1 << 22) if args.comm.startswith('p2p') else 0)
+        comm.overlap = args.comm.endswith('overlap')
+        comm.single_bucket = args.comm.endswith('-1')
     algo = algos.PPO(rank=rank, world_size=world, rollout_len=T, extra_steps=0,
                      credit_assignment_ops={'extrinsic': algos.GAE(gamma=0.99, use_dones=True, lambda_=0.95)},
                      global_step=1, max_steps=10 ** 7, policy_net=agent, policy_optimizer=opt, standardize_adv=True,

@@ -257,6 +257,17 @@ typedef struct drl_comm drl_comm_t;
 int drl_comm_unique_id(uint8_t* id_host /* [128] */);
 int drl_comm_create(drl_comm_t** out, const uint8_t* id_host, int rank, int world, int device);
 int drl_comm_destroy(drl_comm_t* comm);
+/* All-reduce over NVLink PEER MEMORY instead of NCCL (one node, <= 8 ranks): every rank exports an exchange buffer
+ * (cudaIpc handle, 64 bytes) sized for `max_elems` floats, the caller all-gathers the handles (e.g. through
+ * torch.distributed) and hands all of them to every rank; from then on every gradient all-reduce of at most
+ * max_elems floats issued through this communicator (drl_net_set_comm, drl_grad_allreduce_bucketed) runs as a
+ * two-shot reduce-scatter / all-gather in three small kernels: each GPU reads its 1/N slice from all peers,
+ * writes the sums back to all of them.  The result is bit-identical on every rank.  All ranks must call
+ * export, exchange, import, and then synchronise (a barrier) before the first collective. */
+#define DRL_IPC_HANDLE_BYTES 64
+#define DRL_MAX_P2P_RANKS 8
+int drl_comm_p2p_export(drl_comm_t* comm, int64_t max_elems, uint8_t* handle_out /* [64] */);
+int drl_comm_p2p_import(drl_comm_t* comm, const uint8_t* handles_all /* [world][64], rank order; NULL = back to NCCL */);
 /* In-place SUM allreduce of a flat fp32 buffer in `n_buckets` buckets given by bucket_offsets
  * [n_buckets+1] (host, elements), issued in order on `stream`. */
 /* Attach (or detach, comm = NULL) a communicator to a network handle: drl_net_ppo_step then returns gradients

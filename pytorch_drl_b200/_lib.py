@@ -17,6 +17,8 @@ MAX_STREAMS = 4
 MAX_ACTIONS = 32
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
+MAX_P2P_RANKS = 8
 
 
 class PpoHyper(Structure):
@@ -84,6 +86,8 @@ PROTOTYPES = {
     'drl_comm_unique_id': (c_int, [POINTER(c_uint8)]),
     'drl_comm_create': (c_int, [POINTER(c_void_p), POINTER(c_uint8), c_int, c_int, c_int]),
     'drl_comm_destroy': (c_int, [c_void_p]),
+    'drl_comm_p2p_export': (c_int, [c_void_p, c_int64, POINTER(c_uint8)]),
+    'drl_comm_p2p_import': (c_int, [c_void_p, POINTER(c_uint8)]),
     'drl_grad_allreduce_bucketed': (c_int, [c_void_p, c_void_p, POINTER(c_int64), c_int, c_void_p]),
 }
 

@@ -116,8 +116,8 @@ class PPO:
         self._vf_loss_clipping, self._vf_simple_weighting = vf_loss_clipping, vf_simple_weighting
         self._envs_per_rank, self._comm = envs_per_rank, comm
         self._engine = self._policy_net._require_engine()
-        if comm is not None and hasattr(comm, 'attach'):
-            comm.attach(self._engine)                # gradient exchange overlapped with the backward pass
+        if comm is not None and hasattr(comm, 'attach') and getattr(comm, 'overlap', False):
+            comm.attach(self._engine)                # opt-in: gradient exchange overlapped with the backward pass
         self._samplers = []
         for e in range(envs_per_rank):
             rng = None

@@ -32,7 +32,8 @@ def _worker(rank, world, port, out_dir):
     tc.cuda.set_device(rank)
     dev = tc.device('cuda', rank)
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
-    comm = Communicator(rank, world, rank)
+    comm = Communicator(rank, world, rank, p2p_elems=1 << 21)   # NVLink peer-memory all-reduce
+    comm_nccl = Communicator(rank, world, rank, p2p_elems=0)  # plain NCCL
     A, rk, n_envs, T, B = 6, ['extrinsic'], 2, 16, 8
     params = po.init_params(A, rk, seed=5)
     credit = {'extrinsic': dict(gamma=0.99, lambda_=0.95, use_dones=True)}
@@ -56,11 +57,14 @@ def _worker(rank, world, port, out_dir):
         eng.ppo_step(d['observations'], rows, batch, hyper)
         local = eng.grads.clone()
         plain = comm.allreduce_(local.clone(), Communicator.grad_buckets(eng.offsets))     # backward, then all-reduce
+        nccl = comm_nccl.allreduce_(local.clone(), Communicator.grad_buckets(eng.offsets))
+        small = comm.mean_(tc.arange(5, device=dev, dtype=tc.float32) + rank)              # 5-float metric vector
         comm.attach(eng)
         for _ in range(3):                                                                  # repeated: buffers are reused
             eng.ppo_step(d['observations'], rows, batch, hyper)
         tc.cuda.synchronize()
-        result[precision] = dict(local=local.cpu().numpy(), plain=plain.cpu().numpy(), fused=eng.grads.cpu().numpy())
+        result[precision] = dict(local=local.cpu().numpy(), plain=plain.cpu().numpy(), fused=eng.grads.cpu().numpy(),
+                                 nccl=nccl.cpu().numpy(), small=small.cpu().numpy(), p2p=np.array([int(comm.p2p)]))
         del eng
     np.savez(os.path.join(out_dir, f'rank{rank}.npz'), **{f'{p}_{k}': v for p, r in result.items() for k, v in r.items()})
     dist.barrier()
@@ -77,6 +81,9 @@ def test_overlapped_gradient_exchange_matches_plain_allreduce(tmp_path):
         total = r[0][f'{precision}_local'] + r[1][f'{precision}_local']
         for i in range(2):
             np.testing.assert_array_equal(r[i][f'{precision}_plain'], total)       # 2-rank fp32 sum is order-free
+            np.testing.assert_array_equal(r[i][f'{precision}_nccl'], total)        # NCCL and peer-memory paths agree
+            np.testing.assert_allclose(r[i][f'{precision}_small'], np.arange(5) + 0.5, rtol=0, atol=1e-6)
+            assert int(r[i][f'{precision}_p2p'][0]) == 1, 'peer-memory all-reduce was not enabled'
             # the fused result comes from a re-run of the step: its red.global.add partial sums arrive in a different
             # order, so compare as a whole (a missing or doubled range would show up as O(1))
             f, p = r[i][f'{precision}_fused'].astype(np.float64), r[i][f'{precision}_plain'].astype(np.float64)
