@@ -191,6 +191,22 @@ int drl_net_adam_step(drl_net_t* net, float* params, const float* grads, float* 
                       int64_t step, float grad_scale, void* stream);
 
 /* =============================================================================================
+ * Reward normaliser — replaces ReturnAcc and the per-step part of NormalizeRewardWrapper.step
+ * (drl/envs/wrappers/stateful/normalize_reward.py:20-100, 171-194) for n_envs environments at once.
+ * ============================================================================================= */
+/* Feed T new (reward, done) steps of every environment (rewards[e*r_ld + t], dones likewise, 0/1) into its
+ * un-synchronised accumulator.  State (caller-allocated, zero-initialised): win_r / win_d float[2*trace_len][n_envs]
+ * (time-major window of pending pairs), count int[n_envs], steps / m1 / m2 float[n_envs].
+ * trace_len = int(5 / (1 - gamma)) (normalize_reward.py:27). */
+int drl_return_acc_update_f32(const float* rewards, int64_t r_ld, const float* dones, int64_t d_ld, int n_envs, int T,
+                              float gamma, int use_dones, int trace_len, float* win_r, float* win_d, int* count,
+                              float* steps, float* m1, float* m2, void* stream);
+/* y[i] = 0 if steps == 0 else clip(x[i] * rsqrt(m2 - m1^2 + eps), lo, hi), (steps, m1, m2) = synced_moments[0..2]
+ * on the device (ReturnAcc.forward, shift = False: normalize_reward.py:97-100, normalize.py:150-162). */
+int drl_reward_norm_apply_f32(const float* x, int64_t n, const float* synced_moments, float eps, float clip_lo,
+                              float clip_hi, float* y, void* stream);
+
+/* =============================================================================================
  * Observation normaliser — replaces Normalizer.forward / update
  * (drl/envs/wrappers/stateful/normalize.py:129-162, 105-127).
  * ============================================================================================= */

@@ -12,6 +12,8 @@ What is pinned (all from reference code, never from the oracle):
   normalizer.npz Normalizer.update/forward  drl/envs/wrappers/stateful/normalize.py:105-162
   rnd.npz        RND teacher/student forward, predictor loss + grads
                  drl/envs/wrappers/stateful/intrinsic/random_network_distillation.py:22-87,225-233
+  reward_norm.npz ReturnAcc.update/forward (the reward normaliser's accumulator)
+                 drl/envs/wrappers/stateful/normalize_reward.py:20-100
 Large tensors are stored as (sum, l2, strided sample) summaries to keep fixtures small.
 """
 import os
@@ -309,6 +311,33 @@ def gen_rnd():
     np.savez_compressed(os.path.join(GOLD, 'rnd.npz'), **out)
 
 
+def gen_reward_norm():
+    """ReturnAcc driven step by step exactly as NormalizeRewardWrapper.step does (:186-188): reward as a 0-dim
+    float32 tensor, done as bool; moments and normalised probes recorded after every window update."""
+    from drl.envs.wrappers.stateful.normalize_reward import ReturnAcc
+    out = {}
+    cases = [(0.99, True, 2600), (0.99, False, 2100), (0.9, True, 700)]
+    rs = np.random.RandomState(77)
+    probes = np.array([-3.0, -1.0, -0.25, 0.0, 0.5, 1.0, 40.0], F32)
+    for i, (gamma, use_dones, steps) in enumerate(cases):
+        acc = ReturnAcc(gamma, -10., 10., use_dones)
+        r = (rs.randint(-1, 2, size=steps).astype(F32) + (rs.standard_normal(steps) * 0.05).astype(F32)).astype(F32)
+        d = rs.uniform(size=steps) < 0.01
+        trace, first = [], [float(acc(tc.tensor(1.0).unsqueeze(0)))]          # forward before any statistics -> 0
+        for t in range(steps):
+            before = float(acc.steps)
+            acc.update(tc.tensor(r[t]).float(), bool(d[t]))
+            if float(acc.steps) != before:
+                trace.append([t, float(acc.steps), float(acc.moment1), float(acc.moment2)] +
+                             [float(acc(tc.tensor(x).float().unsqueeze(0))) for x in probes])
+        out.update({f'c{i}_meta': np.array([gamma, float(use_dones), steps, acc.trace_length]), f'c{i}_r': r,
+                    f'c{i}_d': d.astype(F32), f'c{i}_trace': np.array(trace, np.float64),
+                    f'c{i}_first': np.array(first)})
+    out['probes'] = probes
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'reward_norm.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_loader.load()
@@ -317,6 +346,7 @@ def main():
     gen_losses()
     gen_normalizer()
     gen_rnd()
+    gen_reward_norm()
     gen_ppo('ppo_2rank', ['extrinsic'], {'extrinsic': 1.0}, False, 29611)
     gen_ppo('ppo_2rank_rnd', ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
             True, 29612)

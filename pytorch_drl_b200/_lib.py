@@ -83,6 +83,9 @@ PROTOTYPES = {
     'drl_sumtree_rebuild': (c_int, [c_void_p, c_int64, c_void_p]),
     'drl_sumtree_sample': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'drl_sumtree_stratified_u': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'drl_return_acc_update_f32': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'drl_reward_norm_apply_f32': (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),
     'drl_comm_unique_id': (c_int, [POINTER(c_uint8)]),
     'drl_comm_create': (c_int, [POINTER(c_void_p), POINTER(c_uint8), c_int, c_int, c_int]),
     'drl_comm_destroy': (c_int, [c_void_p]),

@@ -476,3 +476,56 @@ def test_alternative_bf16_engines_stay_in_parity():
         L.drl_debug_set(3, 1)
         L.drl_debug_set(4, 1)
         L.drl_debug_set(5, 1)
+
+
+# ---- reward normaliser -------------------------------------------------------------------
+def test_reward_normalizer_vs_reference_golden(golden_dir):
+    """One environment per golden case, fed in blocks of 128 steps like a rollout: the window updates must land
+    on the same steps and give the reference's moments and normalised probes (normalize_reward.py:20-100)."""
+    from pytorch_drl_b200.envs import BatchedRewardNormalizer
+    g = np.load(os.path.join(golden_dir, 'reward_norm.npz'))
+    probes = g['probes']
+    for i in range(int(g['ncases'])):
+        gamma, use_dones, steps, L = g[f'c{i}_meta']
+        rn = BatchedRewardNormalizer(1, float(gamma), bool(use_dones), device=dev())
+        assert rn.trace_length == int(L)
+        r, d, trace = g[f'c{i}_r'], g[f'c{i}_d'], g[f'c{i}_trace']
+        assert float(rn.normalize(cu(np.ones(1, np.float32)))[0]) == 0.0          # no statistics yet
+        got, t0 = [], 0
+        while t0 < int(steps):
+            n = min(128, int(steps) - t0)
+            for t in range(t0, t0 + n):                                              # step granularity to catch the update step
+                before = float(rn.steps[0])
+                rn.step_block(cu(r[None, t:t + 1]), cu(d[None, t:t + 1]))
+                if float(rn.steps[0]) != before:
+                    rn.synced.copy_(tc.stack([rn.steps[0], rn.moment1[0], rn.moment2[0]]))
+                    got.append([t, float(rn.steps[0]), float(rn.moment1[0]), float(rn.moment2[0])] +
+                               rn.normalize(cu(probes)).cpu().tolist())
+            t0 += n
+        got = np.array(got)
+        assert got.shape == trace.shape
+        np.testing.assert_array_equal(got[:, :2], trace[:, :2])
+        np.testing.assert_allclose(got[:, 2:], trace[:, 2:], rtol=2e-6, atol=1e-7)
+
+
+def test_reward_normalizer_blocks_vs_oracle():
+    """64 environments x 3 rollouts of 700 steps with a learn() between them, whole [N, T] blocks per call, against
+    the oracle's batched restatement (moments of every environment and every normalised reward)."""
+    from oracle import reward_norm_oracle as rno
+    from pytorch_drl_b200.envs import BatchedRewardNormalizer
+    N, T, gamma = 64, 700, 0.9
+    rs = np.random.RandomState(3)
+    ref = rno.BatchedRewardNormalizer(N, gamma, True)
+    rn = BatchedRewardNormalizer(N, gamma, True, device=dev())
+    for it in range(3):
+        r = (rs.randint(-1, 2, size=(N, T)) + rs.standard_normal((N, T)) * 0.05).astype(np.float32)
+        d = (rs.uniform(size=(N, T)) < 0.02).astype(np.float32)
+        want = ref.step_block(r, d)
+        got = rn.step_block(cu(r), cu(d)).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+        for name in ('steps', 'moment1', 'moment2'):
+            np.testing.assert_allclose(getattr(rn, name).cpu().numpy(), np.array([getattr(a, name) for a in ref.unsynced]),
+                                       rtol=2e-6, atol=1e-7, err_msg=name)
+        ref.learn()
+        rn.learn()
+        np.testing.assert_allclose(rn.synced.cpu().numpy(), [ref.synced.steps, ref.synced.moment1, ref.synced.moment2], rtol=2e-6)

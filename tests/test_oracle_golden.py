@@ -186,3 +186,27 @@ def test_rnd_vs_reference(golden_dir):
         gold = g[f'sgrad::{k}']
         s = summary(gk, 512) if gk.size > 1024 else np.asarray(gk, np.float64)
         np.testing.assert_allclose(s, gold, rtol=1e-4, atol=1e-7 + 1e-5 * np.abs(gold).max())
+
+
+def test_reward_normalizer_oracle_vs_reference_golden(golden_dir):
+    """ReturnAcc (normalize_reward.py:20-100): window updates land on the same steps, moments within float32
+    rounding of torch's mean (1e-6 rel), normalised probes likewise; forward() is 0 before any statistics."""
+    from oracle import reward_norm_oracle as ro
+    g = np.load(os.path.join(golden_dir, 'reward_norm.npz'))
+    probes = g['probes']
+    for i in range(int(g['ncases'])):
+        gamma, use_dones, steps, L = g[f'c{i}_meta']
+        acc = ro.ReturnAcc(float(gamma), -10.0, 10.0, bool(use_dones))
+        assert acc.trace_length == int(L)
+        assert float(acc.forward(1.0)) == float(g[f'c{i}_first'][0]) == 0.0
+        r, d, trace = g[f'c{i}_r'], g[f'c{i}_d'], g[f'c{i}_trace']
+        got = []
+        for t in range(int(steps)):
+            before = float(acc.steps)
+            acc.update(r[t], d[t] != 0)
+            if float(acc.steps) != before:
+                got.append([t, float(acc.steps), float(acc.moment1), float(acc.moment2)] + [float(acc.forward(x)) for x in probes])
+        got = np.array(got)
+        assert got.shape == trace.shape
+        np.testing.assert_array_equal(got[:, :2], trace[:, :2])
+        np.testing.assert_allclose(got[:, 2:], trace[:, 2:], rtol=2e-6, atol=1e-7)
