@@ -191,6 +191,22 @@ int drl_net_adam_step(drl_net_t* net, float* params, const float* grads, float* 
                       int64_t step, float grad_scale, void* stream);
 
 /* =============================================================================================
+ * n-step credit assignment — replaces NStepAdvantageEstimator.call and
+ * SimpleDiscreteBellmanOptimalityOperator.call (drl/algos/common/credit_assignment.py:225-249, 276-305).
+ * n = extra_steps + 1; rewards/dones [n_envs, >= T+n-1] with row stride ld_r, vpreds [n_envs, >= T+n] (ld_v),
+ * q tables [n_envs, >= T+n, A] with row stride ld_q (in time steps).  Bit-identical to the reference.
+ * ============================================================================================= */
+/* adv[e,t] = r_t + nt_t g r_{t+1} + ... + (prod nt) g^n V(s_{t+n}) - V(s_t) */
+int drl_nstep_advantages_f32(const float* rewards, const float* vpreds, const float* dones, int n_envs, int T,
+                             int extra_steps, int64_t ld_r, int64_t ld_v, int64_t ld_out, float gamma, int use_dones,
+                             float* adv_out, void* stream);
+/* out[e,t] = n-step return bootstrapped with Qtgt(s_{t+n}, argmax_a Q*(s_{t+n}, a)), Q* = qpreds if double_q else
+ * tgt_qpreds (first maximum on ties, like torch.argmax). */
+int drl_bellman_backups_f32(const float* rewards, const float* qpreds, const float* tgt_qpreds, const float* dones,
+                            int n_envs, int T, int extra_steps, int num_actions, int64_t ld_r, int64_t ld_q,
+                            int64_t ld_out, float gamma, int use_dones, int double_q, float* out, void* stream);
+
+/* =============================================================================================
  * Reward normaliser — replaces ReturnAcc and the per-step part of NormalizeRewardWrapper.step
  * (drl/envs/wrappers/stateful/normalize_reward.py:20-100, 171-194) for n_envs environments at once.
  * ============================================================================================= */

@@ -12,6 +12,8 @@ What is pinned (all from reference code, never from the oracle):
   normalizer.npz Normalizer.update/forward  drl/envs/wrappers/stateful/normalize.py:105-162
   rnd.npz        RND teacher/student forward, predictor loss + grads
                  drl/envs/wrappers/stateful/intrinsic/random_network_distillation.py:22-87,225-233
+  nstep_bellman.npz NStepAdvantageEstimator.call, SimpleDiscreteBellmanOptimalityOperator.call
+                 drl/algos/common/credit_assignment.py:225-249, 276-305
   reward_norm.npz ReturnAcc.update/forward (the reward normaliser's accumulator)
                  drl/envs/wrappers/stateful/normalize_reward.py:20-100
 Large tensors are stored as (sum, l2, strided sample) summaries to keep fixtures small.
@@ -311,6 +313,33 @@ def gen_rnd():
     np.savez_compressed(os.path.join(GOLD, 'rnd.npz'), **out)
 
 
+def gen_nstep_bellman():
+    from drl.algos.common.credit_assignment import NStepAdvantageEstimator, SimpleDiscreteBellmanOptimalityOperator
+    out = {}
+    rs = np.random.RandomState(4321)
+    cases = [(16, 0, 0.99, True, 4), (128, 2, 0.99, True, 6), (128, 4, 0.999, False, 18), (37, 1, 0.9, True, 3)]
+    for i, (T, extra, g, ud, A) in enumerate(cases):
+        n = extra + 1
+        r = (rs.randint(-1, 2, size=T + n - 1) + rs.standard_normal(T + n - 1) * 0.1).astype(F32)
+        v = rs.standard_normal(T + n).astype(F32)
+        d = (rs.uniform(size=T + n - 1) < 0.1).astype(F32)
+        q = rs.standard_normal((T + n, A)).astype(F32)
+        qt = rs.standard_normal((T + n, A)).astype(F32)
+        q[3] = q[3, 0]                                              # ties: argmax must take the first maximum
+        qt[5, 1:3] = qt[5].max() + 1.0
+        adv = NStepAdvantageEstimator(gamma=g, use_dones=ud)(
+            rollout_len=T, extra_steps=extra, rewards=tc.from_numpy(r), vpreds=tc.from_numpy(v), dones=tc.from_numpy(d)).numpy()
+        bb = {}
+        for dq in (False, True):
+            bb[dq] = SimpleDiscreteBellmanOptimalityOperator(gamma=g, use_dones=ud, double_q=dq)(
+                rollout_len=T, extra_steps=extra, rewards=tc.from_numpy(r), qpreds=tc.from_numpy(q),
+                tgt_qpreds=tc.from_numpy(qt), dones=tc.from_numpy(d)).numpy()
+        out.update({f'c{i}_meta': np.array([T, extra, g, float(ud), A]), f'c{i}_r': r, f'c{i}_v': v, f'c{i}_d': d,
+                    f'c{i}_q': q, f'c{i}_qt': qt, f'c{i}_adv': adv, f'c{i}_bb': bb[False], f'c{i}_bb_dq': bb[True]})
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'nstep_bellman.npz'), **out)
+
+
 def gen_reward_norm():
     """ReturnAcc driven step by step exactly as NormalizeRewardWrapper.step does (:186-188): reward as a 0-dim
     float32 tensor, done as bool; moments and normalised probes recorded after every window update."""
@@ -347,6 +376,7 @@ def main():
     gen_normalizer()
     gen_rnd()
     gen_reward_norm()
+    gen_nstep_bellman()
     gen_ppo('ppo_2rank', ['extrinsic'], {'extrinsic': 1.0}, False, 29611)
     gen_ppo('ppo_2rank_rnd', ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
             True, 29612)

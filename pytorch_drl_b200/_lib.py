@@ -83,6 +83,10 @@ PROTOTYPES = {
     'drl_sumtree_rebuild': (c_int, [c_void_p, c_int64, c_void_p]),
     'drl_sumtree_sample': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'drl_sumtree_stratified_u': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'drl_nstep_advantages_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64,
+                                         c_float, c_int, c_void_p, c_void_p]),
+    'drl_bellman_backups_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64,
+                                        c_int64, c_int64, c_float, c_int, c_int, c_void_p, c_void_p]),
     'drl_return_acc_update_f32': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'drl_reward_norm_apply_f32': (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),

@@ -529,3 +529,27 @@ def test_reward_normalizer_blocks_vs_oracle():
         ref.learn()
         rn.learn()
         np.testing.assert_allclose(rn.synced.cpu().numpy(), [ref.synced.steps, ref.synced.moment1, ref.synced.moment2], rtol=2e-6)
+
+
+# ---- n-step advantages / Bellman backups ----------------------------------------------------
+def test_nstep_and_bellman_vs_reference_golden(golden_dir):
+    """Bit-exact against the reference's NStepAdvantageEstimator / SimpleDiscreteBellmanOptimalityOperator, single
+    trajectory (the reference's call shape) and 3 identical envs per launch."""
+    from pytorch_drl_b200.algos.credit_assignment import NStepAdvantageEstimator, SimpleDiscreteBellmanOptimalityOperator
+    g = np.load(os.path.join(golden_dir, 'nstep_bellman.npz'))
+    for i in range(int(g['ncases'])):
+        T, extra, gam, ud, A = g[f'c{i}_meta']
+        T, extra = int(T), int(extra)
+        r, v, d, q, qt = (cu(g[f'c{i}_{k}']) for k in ('r', 'v', 'd', 'q', 'qt'))
+        op = NStepAdvantageEstimator(gamma=float(gam), use_dones=bool(ud))
+        np.testing.assert_array_equal(op(rollout_len=T, extra_steps=extra, rewards=r, vpreds=v, dones=d).cpu().numpy(), g[f'c{i}_adv'])
+        many = op(rollout_len=T, extra_steps=extra, rewards=r.repeat(3, 1), vpreds=v.repeat(3, 1), dones=d.repeat(3, 1)).cpu().numpy()
+        for e in range(3):
+            np.testing.assert_array_equal(many[e], g[f'c{i}_adv'])
+        for dq, key in ((False, 'bb'), (True, 'bb_dq')):
+            bop = SimpleDiscreteBellmanOptimalityOperator(gamma=float(gam), use_dones=bool(ud), double_q=dq)
+            got = bop(rollout_len=T, extra_steps=extra, rewards=r, qpreds=q, tgt_qpreds=qt, dones=d).cpu().numpy()
+            np.testing.assert_array_equal(got, g[f'c{i}_{key}'])
+            got3 = bop(rollout_len=T, extra_steps=extra, rewards=r.repeat(3, 1), qpreds=q.repeat(3, 1, 1),
+                       tgt_qpreds=qt.repeat(3, 1, 1), dones=d.repeat(3, 1)).cpu().numpy()
+            np.testing.assert_array_equal(got3[2], g[f'c{i}_{key}'])

@@ -210,3 +210,28 @@ def test_reward_normalizer_oracle_vs_reference_golden(golden_dir):
         assert got.shape == trace.shape
         np.testing.assert_array_equal(got[:, :2], trace[:, :2])
         np.testing.assert_allclose(got[:, 2:], trace[:, 2:], rtol=2e-6, atol=1e-7)
+
+
+def test_nstep_and_bellman_oracle_vs_reference_golden(golden_dir):
+    """credit_assignment.py:225-249, 276-305: bit-exact, plus the expected values of the reference's own tests
+    (test_credit_assignment.py:64-170)."""
+    from oracle import credit_oracle as co
+    g = np.load(os.path.join(golden_dir, 'nstep_bellman.npz'))
+    for i in range(int(g['ncases'])):
+        T, extra, gam, ud, A = g[f'c{i}_meta']
+        T, extra = int(T), int(extra)
+        np.testing.assert_array_equal(co.nstep_advantages(T, extra, g[f'c{i}_r'], g[f'c{i}_v'], g[f'c{i}_d'], float(gam), bool(ud)),
+                                      g[f'c{i}_adv'])
+        for dq, key in ((False, 'bb'), (True, 'bb_dq')):
+            np.testing.assert_array_equal(
+                co.bellman_backups(T, extra, g[f'c{i}_r'], g[f'c{i}_q'], g[f'c{i}_qt'], g[f'c{i}_d'], float(gam), bool(ud), dq),
+                g[f'c{i}_{key}'])
+    # reference test vectors
+    r, v = np.array([1., 2., 3., 4.], np.float32), np.array([0., 0., 0., 0., 5.], np.float32)
+    adv = co.nstep_advantages(2, 2, r, v, np.zeros(4, np.float32), 0.99, True)
+    np.testing.assert_allclose(adv, [1 + .99 * 2 + .99 ** 2 * 3, 2 + .99 * 3 + .99 ** 2 * 4 + .99 ** 3 * 5], rtol=1e-6)
+    q = np.array([[0., 0., 0.], [0., 0., 1.], [0., 0., 1.]], np.float32)
+    qt = np.array([[0., 0., 0.], [1., 0., 0.], [0., 1., 0.]], np.float32)
+    z = np.zeros(2, np.float32)
+    np.testing.assert_allclose(co.bellman_backups(2, 0, z, q, qt, z, 0.99, True, False), [0.99, 0.99], rtol=1e-6)
+    np.testing.assert_allclose(co.bellman_backups(2, 0, z, q, qt, z, 0.99, True, True), [0.0, 0.0], atol=1e-7)
