@@ -3,7 +3,7 @@
 Run here (the GPU box has no /root/reference):   python -m oracle.make_golden
 
 What is pinned (all from reference code, never from the oracle):
-  gae.npz        GAE.call               drl/algos/common/credit_assignment.py:195-214
+  gae.npz        GAE.call               drl/algos/common/credit_assignment.py:195-214 (gae_extra.npz: extra_steps > 0)
   standardize.npz standardize           drl/utils/stats.py:4-17
   losses.npz     ppo_* loss functions   drl/algos/ppo.py:310-417 (+ composite, ppo.py:195-200)
   ppo_2rank.npz  annotate + credit_assignment + PPO.optimize run as TWO gloo ranks with
@@ -58,6 +58,25 @@ def gen_gae():
                     f'c{i}_d': d, f'c{i}_adv': adv})
     out['ncases'] = np.array(len(cases))
     np.savez_compressed(os.path.join(GOLD, 'gae.npz'), **out)
+
+
+def gen_gae_extra():
+    """GAE.call with extra_steps > 0 (the scan runs over T + n - 1 steps and the first T are returned)."""
+    from drl.algos.common.credit_assignment import GAE
+    out = {}
+    cases = [(16, 2, 0.99, 0.95, True), (128, 4, 0.999, 0.9, False), (33, 1, 0.9, 0.5, True)]
+    rs = np.random.RandomState(99)
+    for i, (T, extra, g, l, ud) in enumerate(cases):
+        Tn = T + extra
+        r = (rs.randint(-1, 2, size=Tn) + rs.standard_normal(Tn) * 0.1).astype(F32)
+        v = rs.standard_normal(Tn + 1).astype(F32)
+        d = (rs.uniform(size=Tn) < 0.05).astype(F32)
+        adv = GAE(gamma=g, use_dones=ud, lambda_=l)(rollout_len=T, extra_steps=extra, rewards=tc.from_numpy(r),
+                                                    vpreds=tc.from_numpy(v), dones=tc.from_numpy(d)).numpy()
+        out.update({f'c{i}_meta': np.array([T, extra, g, l, float(ud)]), f'c{i}_r': r, f'c{i}_v': v, f'c{i}_d': d,
+                    f'c{i}_adv': adv})
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'gae_extra.npz'), **out)
 
 
 def gen_standardize():
@@ -371,6 +390,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_loader.load()
     gen_gae()
+    gen_gae_extra()
     gen_standardize()
     gen_losses()
     gen_normalizer()

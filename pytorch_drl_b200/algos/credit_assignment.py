@@ -36,17 +36,15 @@ class GAE(AdvantageEstimator):
 
     def call(self, rollout_len: int, extra_steps: int, rewards: tc.Tensor, vpreds: tc.Tensor,
              dones: tc.Tensor) -> tc.Tensor:
-        if extra_steps != 0:
-            # GAE ignores the extra steps' targets only through A_{T+n-1}=0; both shipped configs
-            # use extra_steps: 0 (models_dir/atari_ppo/config.yaml:10).
-            raise NotImplementedError('GAE with extra_steps > 0 is not built yet')
         single = rewards.dim() == 1
         r = rewards.unsqueeze(0) if single else rewards
         v = vpreds.unsqueeze(0) if single else vpreds
         d = dones.unsqueeze(0) if single else dones
         if single:
             r, v, d = r.contiguous(), v.contiguous(), d.contiguous()
-        adv, _ = ops.gae(r, v, d, self._gamma, self._lambda, self._use_dones, False, rollout_len)
+        # extra_steps = n - 1 > 0: the scan runs over T + n - 1 steps, the first T are returned (:204-214)
+        adv, _ = ops.gae(r, v, d, self._gamma, self._lambda, self._use_dones, False, rollout_len + extra_steps)
+        adv = adv[:, :rollout_len]
         return adv[0] if single else adv
 
     def call_fused(self, rollout_len, rewards, vpreds, dones, standardize, adv_out=None, vtarg_out=None):

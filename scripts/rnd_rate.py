@@ -1,0 +1,30 @@
+"""RND predictor throughput on cuda:0 (fp32 CUDA-core engine): learn steps and batched intrinsic reward.
+Usage: python scripts/rnd_rate.py [samples]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch as tc  # noqa: E402
+
+from pytorch_drl_b200.envs import RandomNetworkDistillation  # noqa: E402
+
+nb = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+dev = tc.device('cuda', 0)
+rnd = RandomNetworkDistillation({'lr': 1e-4, 'betas': (0.9, 0.999), 'eps': 1e-8}, world_size=1, max_batch=nb, device=dev)
+rnd._synced_normalizer.moment2.fill_(1.0)
+obs = tc.randint(0, 256, (nb, 84, 84, 4), device=dev, dtype=tc.uint8)
+rows = tc.arange(nb, device=dev, dtype=tc.int64)
+for name, fn in (('learn', lambda: rnd.learn_rows(obs, rows)), ('intrinsic_reward', lambda: rnd.intrinsic_reward(obs, rows))):
+    for _ in range(3):
+        fn()
+    tc.cuda.synchronize()
+    e0, e1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    tc.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f'rnd {name}: {nb} samples in {ms:.3f} ms = {nb / ms * 1e3 / 1e6:.2f} M samples/s')

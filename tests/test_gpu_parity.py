@@ -553,3 +553,15 @@ def test_nstep_and_bellman_vs_reference_golden(golden_dir):
             got3 = bop(rollout_len=T, extra_steps=extra, rewards=r.repeat(3, 1), qpreds=q.repeat(3, 1, 1),
                        tgt_qpreds=qt.repeat(3, 1, 1), dones=d.repeat(3, 1)).cpu().numpy()
             np.testing.assert_array_equal(got3[2], g[f'c{i}_{key}'])
+
+
+def test_gae_extra_steps_vs_reference_golden(golden_dir):
+    """GAE.call with extra_steps > 0 (credit_assignment.py:204-214); same fp32 tolerance as the T-step case (the
+    warp-parallel affine scan re-associates the recurrence)."""
+    from pytorch_drl_b200.algos.credit_assignment import GAE
+    g = np.load(os.path.join(golden_dir, 'gae_extra.npz'))
+    for i in range(int(g['ncases'])):
+        T, extra, gam, lam, ud = g[f'c{i}_meta']
+        op = GAE(gamma=float(gam), use_dones=bool(ud), lambda_=float(lam))
+        adv = op(rollout_len=int(T), extra_steps=int(extra), rewards=cu(g[f'c{i}_r']), vpreds=cu(g[f'c{i}_v']), dones=cu(g[f'c{i}_d']))
+        np.testing.assert_allclose(adv.cpu().numpy(), g[f'c{i}_adv'], rtol=2e-5, atol=2e-6)

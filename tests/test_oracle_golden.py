@@ -235,3 +235,11 @@ def test_nstep_and_bellman_oracle_vs_reference_golden(golden_dir):
     z = np.zeros(2, np.float32)
     np.testing.assert_allclose(co.bellman_backups(2, 0, z, q, qt, z, 0.99, True, False), [0.99, 0.99], rtol=1e-6)
     np.testing.assert_allclose(co.bellman_backups(2, 0, z, q, qt, z, 0.99, True, True), [0.0, 0.0], atol=1e-7)
+
+
+def test_gae_extra_steps_oracle_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'gae_extra.npz'))
+    for i in range(int(g['ncases'])):
+        T, extra, gam, lam, ud = g[f'c{i}_meta']
+        adv = po.gae(int(T), int(extra), g[f'c{i}_r'], g[f'c{i}_v'], g[f'c{i}_d'], float(gam), float(lam), bool(ud))
+        np.testing.assert_array_equal(adv, g[f'c{i}_adv'])
