@@ -451,7 +451,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
     configured = true;
   }
   const int tiles = ((M + 127) / 128) * ((N_total + BN - 1) / BN);
-  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, smem, st>>>(ta, tb, args);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), kTmaGemmThreads, smem, st>>>(ta, tb, args);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }

@@ -48,8 +48,11 @@ struct TmaGemmCfg {
   static constexpr int kSmem = kStages * kStage + 256 + 1024 + 1024;   // stages, barriers, bias, alignment slack
 };
 
+// Warps 0-7: two epilogue warpgroups, each drains HALF the columns of every tile (the epilogue of a 128 x 256 tile
+// costs about as much as its 32 MMAs, so one warpgroup was the critical path); warp 8: MMA; warp 9: TMA.
+constexpr int kTmaGemmThreads = 320;
 template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+__global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                           const __grid_constant__ CUtensorMap tmap_b,
                                                           const TmaGemmArgs args) {
   using namespace umma;
@@ -72,17 +75,17 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
-  if (warp == 5 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     {
       constexpr uint32_t idesc = make_idesc_f16(1u, 128, BN, 0, 0);
       constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
@@ -140,22 +143,24 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
       const uint32_t acc = j & 1;
-      const int m = mt * 128 + threadIdx.x;
+      const int m = mt * 128 + (int)(threadIdx.x & 127);
       const int n0 = nt * BN;
       if (EPI == EPI_BIAS_RELU_F32 && nt != last_nt) {     // (re)load the bias slice of this N tile
-        asm volatile("bar.sync 1, 128;");
-        for (int i = threadIdx.x; i < BN; i += 128) sBias[i] = n0 + i < args.N_total ? args.bias[n0 + i] : 0.f;
-        asm volatile("bar.sync 1, 128;");
+        asm volatile("bar.sync 1, 256;");
+        for (int i = threadIdx.x; i < BN; i += 256) sBias[i] = n0 + i < args.N_total ? args.bias[n0 + i] : 0.f;
+        asm volatile("bar.sync 1, 256;");
         last_nt = nt;
       }
       mbar_wait(tfull + acc, (j >> 1) & 1);
       tc_fence_after();
+      const int wg = warp >> 2;                             // warpgroup 0: columns [0, BN/2), warpgroup 1: the rest
 #pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int c2 = 0; c2 < BN / 64; ++c2) {
+        const int ch = wg * (BN / 64) + c2;
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN + ch * 32, r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * BN + ch * 32, r);
         tmem_ld_wait();
-        if (ch == BN / 32 - 1) {
+        if (c2 == BN / 64 - 1) {
           tc_fence_before();
           mbar_arrive(tempty + acc);
         }
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
         }
         if (EPI == EPI_MASK_BF16 && m < args.M && n < args.N_total) {   // fused bias gradient of the layer below
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cs[(ch % BG) * 32 + i] += __uint_as_float(r[i]);
+          for (int i = 0; i < 32; ++i) cs[(c2 % BG) * 32 + i] += __uint_as_float(r[i]);   // ch = wg * BN/64 + c2, BN/64 even
         }
       }
     }
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(192, 1) tma_gemm_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
