@@ -14,6 +14,7 @@
 #include "umma_tma_gemm.cuh"
 #include "umma_tma_conv.cuh"
 #include "umma_conv1_s2d.cuh"
+#include "umma_tma_gemm2.cuh"
 
 namespace drl {
 
@@ -336,7 +337,8 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
 // [4] conv1 weight gradient on the space-to-depth block image (1) or the im2col kernel (0)
 // [5] conv1 forward on the space-to-depth block image (1), else the kernel flag [3] selects
-int g_debug_flags[8] = {0, 1, 1, 1, 1, 1, 0, 0};
+// [6] fc GEMMs on CTA pairs (cta_group::2, 256 x 256 tiles): 0 none, 1 forward only (default), 2 forward + data gradient
+int g_debug_flags[8] = {0, 1, 1, 1, 1, 1, 1, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -441,6 +443,24 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
   ProfileScope prof(site, st);
   CUtensorMap ta, tb;
   DRL_TRY(make_tmap_bf16(&ta, a, (uint64_t)M, (uint64_t)K, 128));
+  // CTA pairs: each CTA stages 128 rows of A and 128 columns of B.  Measured: fc forward (49 k-blocks per tile)
+  // 0.106 -> 0.098 ms, fc data gradient (8 k-blocks per tile, heavy epilogue) 0.105 -> 0.113 ms => [6] = 1 pairs the
+  // forward only, [6] = 2 both.
+  if (BN == 256 && (g_debug_flags[6] == 2 || (g_debug_flags[6] == 1 && EPI == EPI_BIAS_RELU_F32))) {
+    DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, 128));
+    if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;
+    auto kern2 = tma_gemm2_kernel<EPI>;
+    static bool configured2 = false;
+    if (!configured2) {
+      DRL_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem));
+      configured2 = true;
+    }
+    const int pair_tiles = ((M + 255) / 256) * ((N_total + 255) / 256);
+    const int pairs = pair_tiles < sm_count() / 2 ? pair_tiles : sm_count() / 2;
+    kern2<<<2 * pairs, kG2Threads, kG2Smem, st>>>(ta, tb, args);
+    DRL_LAUNCH_CHECK();
+    return DRL_OK;
+  }
   DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, BN));
   if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   auto kern = tma_gemm_kernel<BN, EPI>;

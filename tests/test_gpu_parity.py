@@ -459,12 +459,13 @@ def test_alternative_bf16_engines_stay_in_parity():
                            [d['vtargs']['extrinsic']])
     try:
         # (tma conv fwd/dgrad kernels, tma conv wgrad kernels, conv1 forward A operand in TMEM)
-        for flags in ((0, 0, 0, 0, 0), (1, 1, 1, 1, 0), (1, 1, 1, 1, 1)):
+        for flags in ((0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 0, 2), (1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 0)):
             L.drl_debug_set(1, flags[0])
             L.drl_debug_set(2, flags[1])
             L.drl_debug_set(3, flags[2])
             L.drl_debug_set(4, flags[3])      # conv1 weight gradient on the space-to-depth block image
             L.drl_debug_set(5, flags[4])      # conv1 forward on the space-to-depth block image
+            L.drl_debug_set(6, flags[5])      # fc GEMMs on CTA pairs (cta_group::2): 0 none, 1 forward, 2 forward + data gradient
             eng, _ = _build('bf16', A, rk, n_envs * B)
             eng.ppo_step(d['observations'], rows, batch, hyper)
             gv = eng.named_views(eng.grads)
@@ -476,6 +477,7 @@ def test_alternative_bf16_engines_stay_in_parity():
         L.drl_debug_set(3, 1)
         L.drl_debug_set(4, 1)
         L.drl_debug_set(5, 1)
+        L.drl_debug_set(6, 1)
 
 
 # ---- reward normaliser -------------------------------------------------------------------
