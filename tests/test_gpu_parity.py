@@ -567,3 +567,36 @@ def test_gae_extra_steps_vs_reference_golden(golden_dir):
         op = GAE(gamma=float(gam), use_dones=bool(ud), lambda_=float(lam))
         adv = op(rollout_len=int(T), extra_steps=int(extra), rewards=cu(g[f'c{i}_r']), vpreds=cu(g[f'c{i}_v']), dones=cu(g[f'c{i}_d']))
         np.testing.assert_allclose(adv.cpu().numpy(), g[f'c{i}_adv'], rtol=2e-5, atol=2e-6)
+
+
+# ---- error behaviour at the boundary (ValueError for argument errors, RuntimeError otherwise) -----
+def test_error_behaviour_matches_reference_conventions():
+    import ctypes
+    from pytorch_drl_b200 import _lib, ops
+    from pytorch_drl_b200.algos import IndependentSampler
+    from pytorch_drl_b200.algos.credit_assignment import GAE, get_credit_assignment_op
+    from pytorch_drl_b200.engine import LearnerEngine
+    L = _lib.lib()
+    # shapes that do not fit: ValueError (credit_assignment.py:25 / samplers.py:51 style)
+    with pytest.raises(ValueError):
+        ops.gae(cu(np.zeros((2, 8), np.float32)), cu(np.zeros((2, 8), np.float32)), cu(np.zeros((2, 8), np.float32)),
+                0.99, 0.95, True, False, 8)                                      # vpreds needs T+1 entries
+    with pytest.raises(ValueError):
+        get_credit_assignment_op('NoSuchOp', {})
+    with pytest.raises((AssertionError, ValueError)):
+        IndependentSampler(10, 4)                                                 # T % B != 0 (samplers.py:51)
+    # C-ABI status codes, called raw
+    assert L.drl_gae_f32(None, None, None, 1, 8, 8, 9, 8, ctypes.c_float(0.99), ctypes.c_float(0.95), 1, 0, None, None, None) == 2
+    h = ctypes.c_void_p()
+    assert L.drl_net_create(ctypes.byref(h), 0, 0, 6, 1, 1) == 1                  # max_batch 0: bad shape
+    assert L.drl_net_create(ctypes.byref(h), 99, 64, 6, 1, 1) == 5                # no such device: NO_DEVICE, not a fallback
+    assert L.drl_rnd_create(ctypes.byref(h), 0, 64, 1, 1) == 6                    # bf16 RND: UNSUPPORTED, loudly
+    eng = LearnerEngine(6, ['value_extrinsic'], 8, 'bf16')
+    obs = tc.zeros((16, 84, 84, 4), dtype=tc.uint8, device=dev())
+    logits, values = tc.empty((16, 6), device=dev()), tc.empty((16, 1), device=dev())
+    # one C call may not exceed the handle's max_batch (the Python engine chunks for the caller)
+    assert L.drl_net_forward(eng._h, _lib.ptr(obs), None, 16, _lib.ptr(logits), _lib.ptr(values), None, None, None, None) == 1
+    assert L.drl_net_forward(eng._h, None, None, 8, _lib.ptr(logits), _lib.ptr(values), None, None, None, None) == 2
+    lg, vl, _, _ = eng.forward(obs)
+    assert lg.shape == (16, 6) and vl.shape == (16, 1)
+    assert L.drl_status_string(6).decode() != ''
