@@ -600,3 +600,71 @@ def test_error_behaviour_matches_reference_conventions():
     lg, vl, _, _ = eng.forward(obs)
     assert lg.shape == (16, 6) and vl.shape == (16, 1)
     assert L.drl_status_string(6).decode() != ''
+
+
+# ---- ragged / boundary batch sizes: the tcgen05 engine against the (oracle-checked) fp32 engine ------------------
+@pytest.mark.parametrize('nb', [1, 2, 3, 127, 129, 149, 257, 297, 300, 1000])
+def test_bf16_engine_ragged_batches_vs_fp32_engine(nb):
+    """Sizes around every tiling boundary of the tcgen05 kernels: fewer samples than SMs, one sample more than the
+    SM count (CTAs with 2 and with 1 samples; odd sample-pair tails), non-multiples of the 128- and 256-row GEMM
+    tiles of the fc layer and its CTA pairs.  Activations, logits, losses and every gradient tensor must agree
+    with the CUDA-core fp32 engine (itself checked against the oracle) within the bf16 bars."""
+    from pytorch_drl_b200 import ops
+    A, rk = 6, ['extrinsic']
+    g = tc.Generator(device=dev())
+    g.manual_seed(100 + nb)
+    obs = tc.randint(0, 256, (nb, 84, 84, 4), device=dev(), dtype=tc.uint8, generator=g)
+    rows = tc.randperm(nb, device=dev(), generator=g)
+    actions = tc.randint(0, A, (nb,), device=dev(), generator=g)
+    logp_old = tc.full((nb,), -float(np.log(A)), device=dev())
+    adv = tc.randn(nb, device=dev(), generator=g)
+    vold = tc.randn(nb, device=dev(), generator=g) * 0.1
+    vtarg = tc.randn(nb, device=dev(), generator=g)
+    hyper = ops.make_hyper(A, [1.0], 0.1, 0.01, 0.5, False, True)
+    batch = ops.make_batch(actions, logp_old, [adv], [vold], [vtarg])
+    out = {}
+    for precision in ('fp32', 'bf16'):
+        eng, _ = _build(precision, A, rk, nb)
+        losses = eng.ppo_step(obs, rows, batch, hyper).cpu().numpy()
+        grads = {k: v.cpu().numpy().copy() for k, v in eng.named_views(eng.grads).items()}
+        logits, values, _, _ = eng.forward(obs, rows)
+        out[precision] = (losses, grads, logits.cpu().numpy(), values.cpu().numpy())
+        del eng
+    (l32, g32, lg32, v32), (l16, g16, lg16, v16) = out['fp32'], out['bf16']
+    t = TOL['bf16']
+    assert np.isfinite(l16).all() and all(np.isfinite(v).all() for v in g16.values())
+    assert rel_l2(lg16, lg32) < t['act'] and rel_l2(v16, v32) < 2 * t['act']
+    np.testing.assert_allclose(l16[:4], l32[:4], rtol=5 * t['loss'], atol=5 * t['loss'])
+    for k in g32:
+        # single-digit batches make some gradient tensors tiny differences of large sums: direction + norm check
+        a, b = g16[k].ravel().astype(np.float64), g32[k].ravel().astype(np.float64)
+        if np.linalg.norm(b) > 0:
+            assert a @ b / (np.linalg.norm(a) * np.linalg.norm(b)) > 0.99, (nb, k)
+            assert rel_l2(g16[k], g32[k]) < 0.15, (nb, k, rel_l2(g16[k], g32[k]))
+
+
+def test_bf16_engine_reuse_across_batch_sizes():
+    """One network handle, learner steps of different sizes back to back (workspaces, ReLU-mask buffers and TMEM
+    are reused): each must equal what a fresh handle of exactly that size computes."""
+    from pytorch_drl_b200 import ops
+    A, rk = 6, ['extrinsic']
+    g = tc.Generator(device=dev())
+    g.manual_seed(7)
+    big = 300
+    obs = tc.randint(0, 256, (big, 84, 84, 4), device=dev(), dtype=tc.uint8, generator=g)
+    actions = tc.randint(0, A, (big,), device=dev(), generator=g)
+    logp_old = tc.full((big,), -float(np.log(A)), device=dev())
+    adv, vold, vtarg = (tc.randn(big, device=dev(), generator=g) for _ in range(3))
+    hyper = ops.make_hyper(A, [1.0], 0.1, 0.01, 0.5, False, True)
+    batch = ops.make_batch(actions, logp_old, [adv], [vold], [vtarg])
+    shared, _ = _build('bf16', A, rk, big)
+    for nb in (300, 1, 149, 300, 2):
+        rows = tc.arange(nb, device=dev(), dtype=tc.int64)
+        l_shared = shared.ppo_step(obs, rows, batch, hyper).cpu().numpy()
+        g_shared = shared.grads.cpu().numpy().copy()
+        fresh, _ = _build('bf16', A, rk, nb)
+        l_fresh = fresh.ppo_step(obs, rows, batch, hyper).cpu().numpy()
+        g_fresh = fresh.grads.cpu().numpy()
+        np.testing.assert_allclose(l_shared, l_fresh, rtol=1e-5, atol=1e-6)
+        assert np.linalg.norm(g_shared - g_fresh) <= 1e-4 * max(np.linalg.norm(g_fresh), 1e-30), nb   # atomics order only
+        del fresh
