@@ -668,3 +668,47 @@ def test_bf16_engine_reuse_across_batch_sizes():
         np.testing.assert_allclose(l_shared, l_fresh, rtol=1e-5, atol=1e-6)
         assert np.linalg.norm(g_shared - g_fresh) <= 1e-4 * max(np.linalg.norm(g_fresh), 1e-30), nb   # atomics order only
         del fresh
+
+
+def test_full_size_step_properties():
+    """BASELINE.json config[1] size (1024 envs x 32 samples = 32 768 per step), where the oracle is too slow:
+    size-independent properties of the learner step on the tcgen05 engine —
+      * permutation invariance: the same minibatch in another row order gives the same losses and gradients,
+      * additivity: every loss is a mean over samples, so grad(all) = (grad(first half) + grad(second half)) / 2,
+      * consistency with the oracle-checked fp32 engine on a 512-sample slice of the same data."""
+    from pytorch_drl_b200 import ops
+    A, rk, nb = 6, ['extrinsic'], 32768
+    g = tc.Generator(device=dev())
+    g.manual_seed(2024)
+    obs = tc.empty((nb, 84, 84, 4), device=dev(), dtype=tc.uint8)
+    for s in range(0, nb, 4096):
+        obs[s:s + 4096] = tc.randint(0, 256, (4096, 84, 84, 4), device=dev(), dtype=tc.uint8, generator=g)
+    actions = tc.randint(0, A, (nb,), device=dev(), generator=g)
+    logp_old = tc.full((nb,), -float(np.log(A)), device=dev())
+    adv, vold, vtarg = (tc.randn(nb, device=dev(), generator=g) for _ in range(3))
+    hyper = ops.make_hyper(A, [1.0], 0.1, 0.01, 0.5, False, True)
+    batch = ops.make_batch(actions, logp_old, [adv], [vold], [vtarg])
+    eng, _ = _build('bf16', A, rk, nb)
+
+    def step(rows):
+        losses = eng.ppo_step(obs, rows, batch, hyper).cpu().numpy().astype(np.float64)
+        return losses, eng.grads.cpu().numpy().astype(np.float64)
+
+    ident = tc.arange(nb, device=dev(), dtype=tc.int64)
+    l_all, g_all = step(ident)
+    assert np.isfinite(l_all).all() and np.isfinite(g_all).all() and np.linalg.norm(g_all) > 0
+    l_perm, g_perm = step(tc.randperm(nb, device=dev(), generator=g))
+    np.testing.assert_allclose(l_perm, l_all, rtol=1e-4, atol=1e-6)
+    assert np.linalg.norm(g_perm - g_all) <= 2e-4 * np.linalg.norm(g_all)
+    l_a, g_a = step(ident[:nb // 2])
+    l_b, g_b = step(ident[nb // 2:])
+    np.testing.assert_allclose(0.5 * (l_a + l_b)[:4], l_all[:4], rtol=1e-4, atol=1e-6)
+    assert np.linalg.norm(0.5 * (g_a + g_b) - g_all) <= 2e-4 * np.linalg.norm(g_all)
+    sub = ident[1000:1512]
+    l_sub, g_sub = step(sub)
+    del eng
+    ref, _ = _build('fp32', A, rk, 512)
+    l_ref = ref.ppo_step(obs, sub, batch, hyper).cpu().numpy()
+    g_ref = ref.grads.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(l_sub[:4], l_ref[:4], rtol=5 * TOL['bf16']['loss'], atol=5 * TOL['bf16']['loss'])
+    assert g_sub @ g_ref / (np.linalg.norm(g_sub) * np.linalg.norm(g_ref)) > 0.995
