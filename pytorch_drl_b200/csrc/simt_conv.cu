@@ -12,35 +12,53 @@ namespace drl {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
+// Operand functors are evaluated in two levels so that the per-element cost is two shared-memory reads, an add
+// and the load: `d0(i)` describes a row of the operand (computed once per tile for A rows / B columns), `d1(j)` a
+// position along the reduction (computed once per 16-wide k-step), `at(d0, d1)` fetches the element.  The index
+// arithmetic (divisions by the map geometry) therefore runs once per row / per k instead of once per element.
+struct Desc { long long a; int b; int c; };
+
 template <bool A_M_FAST, class AF, class BF, class EF>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int k_per_split, AF af,
                                                         BF bf, EF ef) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
+  __shared__ Desc dAm[BM], dBn[BN], dAk[BK], dBk[BK];
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;   // M tiles on x: up to 2^31-1 blocks
   const int kbeg = blockIdx.z * k_per_split;
   const int kend = min(K, kbeg + k_per_split);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (threadIdx.x < BM) {
+    if (m0 + (int)threadIdx.x < M) dAm[threadIdx.x] = af.d0(m0 + threadIdx.x);
+  } else if (threadIdx.x < BM + BN) {
+    const int nn = threadIdx.x - BM;
+    if (n0 + nn < N) dBn[nn] = bf.d1(n0 + nn);
+  }
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    if (threadIdx.x < BK) {
+      if (k0 + (int)threadIdx.x < kend) dAk[threadIdx.x] = af.d1(k0 + threadIdx.x);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + BK) {
+      const int kk = threadIdx.x - 32;
+      if (k0 + kk < kend) dBk[kk] = bf.d0(k0 + kk);
+    }
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = threadIdx.x + 256 * i;
       const int kk = A_M_FAST ? e / BM : e % BK;
       const int mm = A_M_FAST ? e % BM : e / BK;
-      const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < kend) ? af(m, k) : 0.f;
+      As[kk][mm] = (m0 + mm < M && k0 + kk < kend) ? af.at(dAm[mm], dAk[kk]) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = threadIdx.x + 256 * i;
       const int kk = e / BN, nn = e % BN;
-      const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < kend) ? bf(k, n) : 0.f;
+      Bs[kk][nn] = (n0 + nn < N && k0 + kk < kend) ? bf.at(dBk[kk], dBn[nn]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -80,26 +98,31 @@ template <> __device__ __forceinline__ float load_in<uint8_t>(const uint8_t* p, 
 template <typename TIn>
 struct PatchGather {
   const TIn* in; const int64_t* row_idx; ConvGeom g;
-  __device__ __forceinline__ float operator()(int r, int c) const {
+  __device__ __forceinline__ Desc d0(int r) const {          // offset of the patch's first element
     const int pos = g.OH * g.OW;
     const int b = r / pos, rem = r - b * pos;
     const int oy = rem / g.OW, ox = rem - oy * g.OW;
+    const long long row = row_idx ? (long long)row_idx[b] : (long long)b;
+    return Desc{((row * g.H + oy * g.S) * g.W + ox * g.S) * g.Cin, 0, 0};
+  }
+  __device__ __forceinline__ Desc d1(int c) const {          // offset of tap (ky, kx, ci) inside the patch
     const int kc = g.KW * g.Cin;
     const int ky = c / kc, r2 = c - ky * kc;
-    const int kx = r2 / g.Cin, ci = r2 - kx * g.Cin;
-    const size_t row = row_idx ? (size_t)row_idx[b] : (size_t)b;
-    return load_in<TIn>(in, ((row * g.H + (oy * g.S + ky)) * g.W + (ox * g.S + kx)) * g.Cin + ci);
+    return Desc{0, ky * g.W * g.Cin + r2, 0};
   }
+  __device__ __forceinline__ float at(const Desc& r, const Desc& c) const { return load_in<TIn>(in, (size_t)(r.a + c.b)); }
 };
 
 struct WeightFwd {            // B(k=(ky,kx,ci), n=co) = W[co, ci, ky, kx]
   const float* w; ConvGeom g;
-  __device__ __forceinline__ float operator()(int k, int n) const {
+  __device__ __forceinline__ Desc d0(int k) const {
     const int kc = g.KW * g.Cin;
     const int ky = k / kc, r2 = k - ky * kc;
     const int kx = r2 / g.Cin, ci = r2 - kx * g.Cin;
-    return __ldg(w + ((size_t)(n * g.Cin + ci) * g.KH + ky) * g.KW + kx);
+    return Desc{0, (ci * g.KH + ky) * g.KW + kx, 0};
   }
+  __device__ __forceinline__ Desc d1(int n) const { return Desc{(long long)n * g.Cin * g.KH * g.KW, 0, 0}; }
+  __device__ __forceinline__ float at(const Desc& k, const Desc& n) const { return __ldg(w + n.a + k.b); }
 };
 
 // act: 0 identity, 1 ReLU, 2 LeakyReLU(0.2)
@@ -115,29 +138,37 @@ struct EpiBiasRelu {
 // dgrad: A(m=(b,iy,ix), k=(ky,kx,co)) = dY[b,(iy-ky)/S,(ix-kx)/S,co] when that lands on the grid
 struct DyGather {
   const float* dy; ConvGeom g;
-  __device__ __forceinline__ float operator()(int m, int k) const {
+  __device__ __forceinline__ Desc d0(int m) const {
     const int pos = g.H * g.W;
     const int b = m / pos, rem = m - b * pos;
     const int iy = rem / g.W, ix = rem - iy * g.W;
+    return Desc{(long long)b * g.OH * g.OW * g.Cout, iy, ix};
+  }
+  __device__ __forceinline__ Desc d1(int k) const {
     const int kc = g.KW * g.Cout;
     const int ky = k / kc, r2 = k - ky * kc;
     const int kx = r2 / g.Cout, co = r2 - kx * g.Cout;
-    const int ty = iy - ky, tx = ix - kx;
+    return Desc{co, ky, kx};
+  }
+  __device__ __forceinline__ float at(const Desc& r, const Desc& c) const {
+    const int ty = r.b - c.b, tx = r.c - c.c;
     if (ty < 0 || tx < 0) return 0.f;
     const int oy = ty / g.S, ox = tx / g.S;
     if (oy * g.S != ty || ox * g.S != tx || oy >= g.OH || ox >= g.OW) return 0.f;
-    return __ldg(dy + (((size_t)b * g.OH + oy) * g.OW + ox) * g.Cout + co);
+    return __ldg(dy + r.a + (size_t)(oy * g.OW + ox) * g.Cout + c.a);
   }
 };
 
 struct WeightDgrad {          // B(k=(ky,kx,co), n=ci) = W[co, ci, ky, kx]
   const float* w; ConvGeom g;
-  __device__ __forceinline__ float operator()(int k, int n) const {
+  __device__ __forceinline__ Desc d0(int k) const {
     const int kc = g.KW * g.Cout;
     const int ky = k / kc, r2 = k - ky * kc;
     const int kx = r2 / g.Cout, co = r2 - kx * g.Cout;
-    return __ldg(w + ((size_t)(co * g.Cin + n) * g.KH + ky) * g.KW + kx);
+    return Desc{(long long)co * g.Cin * g.KH * g.KW + ky * g.KW + kx, 0, 0};
   }
+  __device__ __forceinline__ Desc d1(int n) const { return Desc{0, n * g.KH * g.KW, 0}; }
+  __device__ __forceinline__ float at(const Desc& k, const Desc& n) const { return __ldg(w + k.a + n.b); }
 };
 
 struct EpiReluMask {          // dX = acc * act'(X): activation of the producing layer (1 ReLU, 2 LeakyReLU 0.2)
@@ -150,13 +181,17 @@ struct EpiReluMask {          // dX = acc * act'(X): activation of the producing
 
 struct DyT {                  // wgrad A'(m=co, k=r) = dY[r, co]
   const float* dy; int Cout;
-  __device__ __forceinline__ float operator()(int m, int k) const { return __ldg(dy + (size_t)k * Cout + m); }
+  __device__ __forceinline__ Desc d0(int m) const { return Desc{0, m, 0}; }
+  __device__ __forceinline__ Desc d1(int k) const { return Desc{(long long)k * Cout, 0, 0}; }
+  __device__ __forceinline__ float at(const Desc& m, const Desc& k) const { return __ldg(dy + k.a + m.b); }
 };
 
 template <typename TIn>
 struct PatchGatherT {         // wgrad B'(k=r, n=(ky,kx,ci)) plus a ones column (n == Kp) for the bias
   PatchGather<TIn> pg; int Kp;
-  __device__ __forceinline__ float operator()(int k, int n) const { return n < Kp ? pg(k, n) : 1.f; }
+  __device__ __forceinline__ Desc d0(int k) const { return pg.d0(k); }
+  __device__ __forceinline__ Desc d1(int n) const { Desc d = pg.d1(n < Kp ? n : 0); d.c = n < Kp ? 0 : 1; return d; }
+  __device__ __forceinline__ float at(const Desc& k, const Desc& n) const { return n.c ? 1.f : pg.at(k, n); }
 };
 
 struct EpiWgrad {             // scatter-add into the OIHW gradient (+ bias gradient)
@@ -178,23 +213,32 @@ struct EpiWgrad {             // scatter-add into the OIHW gradient (+ bias grad
 // fused into the im2col gather.  Cin = 1.
 struct NormPatchGather {
   const uint8_t* obs; const int64_t* row_idx; const float* m1; const float* m2; ConvGeom g;
-  __device__ __forceinline__ float operator()(int r, int c) const {
+  __device__ __forceinline__ Desc d0(int r) const {          // frame offset and pixel index of the patch origin
     const int pos = g.OH * g.OW;
     const int b = r / pos, rem = r - b * pos;
     const int oy = rem / g.OW, ox = rem - oy * g.OW;
+    const long long row = row_idx ? (long long)row_idx[b] : (long long)b;
+    const int pix = (oy * g.S) * 84 + ox * g.S;
+    return Desc{(row * 7056 + pix) * 4 + 3, pix, 0};
+  }
+  __device__ __forceinline__ Desc d1(int c) const {
     const int ky = c / g.KW, kx = c - ky * g.KW;
-    const int y = oy * g.S + ky, x = ox * g.S + kx;
-    const size_t row = row_idx ? (size_t)row_idx[b] : (size_t)b;
-    const float v = __fmul_rn((float)__ldg(obs + ((row * 84 + y) * 84 + x) * 4 + 3), __uint_as_float(0x3b808081u));
-    const float mu = __ldg(m1 + y * 84 + x);
-    const float var = __fsub_rn(__ldg(m2 + y * 84 + x), __fmul_rn(mu, mu));
+    return Desc{0, ky * 84 + kx, 0};
+  }
+  __device__ __forceinline__ float at(const Desc& r, const Desc& c) const {
+    const int pix = r.b + c.b;
+    const float v = __fmul_rn((float)__ldg(obs + r.a + (size_t)c.b * 4), __uint_as_float(0x3b808081u));
+    const float mu = __ldg(m1 + pix);
+    const float var = __fsub_rn(__ldg(m2 + pix), __fmul_rn(mu, mu));
     const float z = __fmul_rn(__fsub_rn(v, mu), rsqrtf(__fadd_rn(var, 1e-8f)));
     return fminf(fmaxf(z, -5.f), 5.f);
   }
 };
 struct NormPatchGatherT {
   NormPatchGather pg; int Kp;
-  __device__ __forceinline__ float operator()(int k, int n) const { return n < Kp ? pg(k, n) : 1.f; }
+  __device__ __forceinline__ Desc d0(int k) const { return pg.d0(k); }
+  __device__ __forceinline__ Desc d1(int n) const { Desc d = pg.d1(n < Kp ? n : 0); d.c = n < Kp ? 0 : 1; return d; }
+  __device__ __forceinline__ float at(const Desc& k, const Desc& n) const { return n.c ? 1.f : pg.at(k, n); }
 };
 
 static inline dim3 tiles(int M, int N, int z = 1) { return dim3((M + BM - 1) / BM, (N + BN - 1) / BN, z); }
