@@ -28,3 +28,17 @@ for name, fn in (('learn', lambda: rnd.learn_rows(obs, rows)), ('intrinsic_rewar
     tc.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f'rnd {name}: {nb} samples in {ms:.3f} ms = {nb / ms * 1e3 / 1e6:.2f} M samples/s')
+    # per-launch-site breakdown (CUDA events recorded by the library)
+    import ctypes
+    from pytorch_drl_b200 import _lib
+    L = _lib.lib()
+    L.drl_profile_enable(1)
+    nbuf = ctypes.create_string_buffer(48 * 64)
+    msb, cnt, ns = (ctypes.c_float * 64)(), (ctypes.c_int * 64)(), ctypes.c_int()
+    L.drl_profile_read(64, nbuf, msb, cnt, ctypes.byref(ns))
+    fn()
+    tc.cuda.synchronize()
+    L.drl_profile_read(64, nbuf, msb, cnt, ctypes.byref(ns))
+    L.drl_profile_enable(0)
+    sites = {nbuf.raw[48 * i:48 * i + 48].split(b'\0')[0].decode(): (round(msb[i], 3), cnt[i]) for i in range(ns.value)}
+    print('   sites (total ms, launches):', sites)
