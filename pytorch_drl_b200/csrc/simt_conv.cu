@@ -10,7 +10,7 @@
 
 namespace drl {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 64, BK = 16;     // BN (64 / 32 / 16) is a template parameter: the RND layers have 16 / 32 columns
 
 // Operand functors are evaluated in two levels so that the per-element cost is two shared-memory reads, an add
 // and the load: `d0(i)` describes a row of the operand (computed once per tile for A rows / B columns), `d1(j)` a
@@ -18,9 +18,10 @@ constexpr int BM = 64, BN = 64, BK = 16;
 // arithmetic (divisions by the map geometry) therefore runs once per row / per k instead of once per element.
 struct Desc { long long a; int b; int c; };
 
-template <bool A_M_FAST, class AF, class BF, class EF>
+template <bool A_M_FAST, int BN, class AF, class BF, class EF>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int k_per_split, AF af,
                                                         BF bf, EF ef) {
+  constexpr int TN = BN / 16;                        // columns per thread
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   __shared__ Desc dAm[BM], dBn[BN], dAk[BK], dBk[BK];
@@ -34,11 +35,11 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int
     const int nn = threadIdx.x - BM;
     if (n0 + nn < N) dBn[nn] = bf.d1(n0 + nn);
   }
-  float acc[4][4];
+  float acc[4][TN];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
     if (threadIdx.x < BK) {
       if (k0 + (int)threadIdx.x < kend) dAk[threadIdx.x] = af.d1(k0 + threadIdx.x);
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int
       As[kk][mm] = (m0 + mm < M && k0 + kk < kend) ? af.at(dAm[mm], dAk[kk]) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < BK * BN / 256; ++i) {
       const int e = threadIdx.x + 256 * i;
       const int kk = e / BN, nn = e % BN;
       Bs[kk][nn] = (n0 + nn < N && k0 + kk < kend) ? bf.at(dBk[kk], dBn[nn]) : 0.f;
@@ -63,15 +64,15 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+      float a[4], b[TN];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -80,8 +81,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(int M, int N, int K, int
     const int m = m0 + ty * 4 + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
       if (n < N) ef(m, n, acc[i][j]);
     }
   }
@@ -179,6 +180,52 @@ struct EpiReluMask {          // dX = acc * act'(X): activation of the producing
   }
 };
 
+// ---- strided data gradient by output-parity classes ---------------------------------------------------------
+// For stride S > 1 only the taps ky = py + S*a, kx = px + S*b reach input pixel (iy, ix) = (S*u + py, S*v + px), so
+// each of the S*S classes is a dense stride-1 correlation over dY with a (KH/S x KW/S) sub-kernel: no tap is
+// fetched to be multiplied by zero.  m' = (b, u, v) over the class's Hc x Wc pixels, k' = (a, b', co).
+struct DyGatherCls {
+  const float* dy; ConvGeom g; int py, px, Hc, Wc;
+  __device__ __forceinline__ Desc d0(int m) const {
+    const int pos = Hc * Wc;
+    const int b = m / pos, rem = m - b * pos;
+    const int u = rem / Wc, v = rem - u * Wc;
+    return Desc{(long long)b * g.OH * g.OW * g.Cout, u, v};
+  }
+  __device__ __forceinline__ Desc d1(int k) const {
+    const int kc = (g.KW / g.S) * g.Cout;
+    const int a = k / kc, r2 = k - a * kc;
+    const int bb = r2 / g.Cout, co = r2 - bb * g.Cout;
+    return Desc{co, a, bb};
+  }
+  __device__ __forceinline__ float at(const Desc& r, const Desc& c) const {
+    const int oy = r.b - c.b, ox = r.c - c.c;
+    if (oy < 0 || ox < 0 || oy >= g.OH || ox >= g.OW) return 0.f;
+    return __ldg(dy + r.a + (size_t)(oy * g.OW + ox) * g.Cout + c.a);
+  }
+};
+struct WeightDgradCls {       // B(k'=(a,b',co), n=ci) = W[co, ci, py + S*a, px + S*b']
+  const float* w; ConvGeom g; int py, px;
+  __device__ __forceinline__ Desc d0(int k) const {
+    const int kc = (g.KW / g.S) * g.Cout;
+    const int a = k / kc, r2 = k - a * kc;
+    const int bb = r2 / g.Cout, co = r2 - bb * g.Cout;
+    return Desc{(long long)co * g.Cin * g.KH * g.KW + (py + g.S * a) * g.KW + (px + g.S * bb), 0, 0};
+  }
+  __device__ __forceinline__ Desc d1(int n) const { return Desc{0, n * g.KH * g.KW, 0}; }
+  __device__ __forceinline__ float at(const Desc& k, const Desc& n) const { return __ldg(w + k.a + n.b); }
+};
+struct EpiReluMaskCls {       // class row m' = (b, u, v) -> input pixel (S*u + py, S*v + px)
+  const float* x_act; float* dx; ConvGeom g; int py, px, Hc, Wc, act;
+  __device__ __forceinline__ void operator()(int m, int n, float acc) const {
+    const int pos = Hc * Wc;
+    const int b = m / pos, rem = m - b * pos;
+    const int u = rem / Wc, v = rem - u * Wc;
+    const size_t i = (((size_t)b * g.H + (g.S * u + py)) * g.W + (g.S * v + px)) * g.Cin + n;
+    dx[i] = __ldg(x_act + i) > 0.f ? acc : (act == 2 ? 0.2f * acc : 0.f);
+  }
+};
+
 struct DyT {                  // wgrad A'(m=co, k=r) = dY[r, co]
   const float* dy; int Cout;
   __device__ __forceinline__ Desc d0(int m) const { return Desc{0, m, 0}; }
@@ -241,7 +288,19 @@ struct NormPatchGatherT {
   __device__ __forceinline__ float at(const Desc& k, const Desc& n) const { return n.c ? 1.f : pg.at(k, n); }
 };
 
-static inline dim3 tiles(int M, int N, int z = 1) { return dim3((M + BM - 1) / BM, (N + BN - 1) / BN, z); }
+static inline int pick_bn(int N) { return N <= 16 ? 16 : N <= 32 ? 32 : 64; }
+static inline dim3 tiles(int M, int N, int z = 1) {
+  const int bn = pick_bn(N);
+  return dim3((M + BM - 1) / BM, (N + bn - 1) / bn, z);
+}
+// launch with the column-tile width that fits N
+#define SIMT_LAUNCH(A_M_FAST, grid, st, M, N, K, kper, af, bf, ef)                                              \
+  do {                                                                                                          \
+    const int bn_ = pick_bn(N);                                                                                 \
+    if (bn_ == 16) simt_gemm_kernel<A_M_FAST, 16><<<grid, 256, 0, st>>>(M, N, K, kper, af, bf, ef);             \
+    else if (bn_ == 32) simt_gemm_kernel<A_M_FAST, 32><<<grid, 256, 0, st>>>(M, N, K, kper, af, bf, ef);        \
+    else simt_gemm_kernel<A_M_FAST, 64><<<grid, 256, 0, st>>>(M, N, K, kper, af, bf, ef);                       \
+  } while (0)
 
 template <typename TIn>
 int simt_conv_forward(const TIn* in, const int64_t* row_idx, int nb, const ConvGeom& g, const float* w,
@@ -251,7 +310,7 @@ int simt_conv_forward(const TIn* in, const int64_t* row_idx, int nb, const ConvG
   WeightFwd bf{w, g};
   EpiBiasRelu<float> ef{bias, out, N, act};
   ProfileScope prof("simt_fwd", st);
-  simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
+  SIMT_LAUNCH(false, tiles(M, N), st, M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -262,12 +321,28 @@ template int simt_conv_forward<uint8_t>(const uint8_t*, const int64_t*, int, con
 
 int simt_conv_dgrad(const float* dy, int nb, const ConvGeom& g, const float* w, const float* x_act,
                     float* dx, cudaStream_t st, int act) {
-  const int M = nb * g.H * g.W, N = g.Cin, K = g.KH * g.KW * g.Cout;
+  const int N = g.Cin;
+  ProfileScope prof("simt_dgrad", st);
+  if (g.S > 1 && g.KH % g.S == 0 && g.KW % g.S == 0) {
+    // one dense stride-1 problem per output-parity class; pixels no tap reaches (none in NatureCNN / RND) keep the
+    // zero the class sum would give them because every input pixel belongs to exactly one class
+    for (int py = 0; py < g.S; ++py)
+      for (int px = 0; px < g.S; ++px) {
+        const int Hc = (g.H - py + g.S - 1) / g.S, Wc = (g.W - px + g.S - 1) / g.S;
+        const int M = nb * Hc * Wc, K = (g.KH / g.S) * (g.KW / g.S) * g.Cout;
+        DyGatherCls af{dy, g, py, px, Hc, Wc};
+        WeightDgradCls bf{w, g, py, px};
+        EpiReluMaskCls ef{x_act, dx, g, py, px, Hc, Wc, act};
+        SIMT_LAUNCH(false, tiles(M, N), st, M, N, K, K, af, bf, ef);
+        DRL_LAUNCH_CHECK();
+      }
+    return DRL_OK;
+  }
+  const int M = nb * g.H * g.W, K = g.KH * g.KW * g.Cout;
   DyGather af{dy, g};
   WeightDgrad bf{w, g};
   EpiReluMask ef{x_act, dx, N, act};
-  ProfileScope prof("simt_dgrad", st);
-  simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
+  SIMT_LAUNCH(false, tiles(M, N), st, M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -287,7 +362,7 @@ int simt_conv_wgrad(const float* dy, const TIn* in, const int64_t* row_idx, int 
   PatchGatherT<TIn> bf{PatchGather<TIn>{in, row_idx, g}, Kp};
   EpiWgrad ef{gw, gb, g, Kp};
   ProfileScope prof("simt_wgrad", st);
-  simt_gemm_kernel<true><<<tiles(M, N, splits), 256, 0, st>>>(M, N, K, k_per, af, bf, ef);
+  SIMT_LAUNCH(true, tiles(M, N, splits), st, M, N, K, k_per, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -307,7 +382,7 @@ int simt_rnd_conv1_forward(const uint8_t* obs, const int64_t* row_idx, int nb, c
   WeightFwd bf{w, g};
   EpiBiasRelu<float> ef{bias, out, N, 2};
   ProfileScope prof("rnd_simt_fwd", st);
-  simt_gemm_kernel<false><<<tiles(M, N), 256, 0, st>>>(M, N, K, K, af, bf, ef);
+  SIMT_LAUNCH(false, tiles(M, N), st, M, N, K, K, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -325,7 +400,7 @@ int simt_rnd_conv1_wgrad(const float* dy, const uint8_t* obs, const int64_t* row
   NormPatchGatherT bf{NormPatchGather{obs, row_idx, m1, m2, g}, Kp};
   EpiWgrad ef{gw, gb, g, Kp};
   ProfileScope prof("rnd_simt_wgrad", st);
-  simt_gemm_kernel<true><<<tiles(M, N, splits), 256, 0, st>>>(M, N, K, k_per, af, bf, ef);
+  SIMT_LAUNCH(true, tiles(M, N, splits), st, M, N, K, k_per, af, bf, ef);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
