@@ -302,6 +302,12 @@ int drl_comm_p2p_export(drl_comm_t* comm, int64_t max_elems, uint8_t* handle_out
 int drl_comm_p2p_import(drl_comm_t* comm, const uint8_t* handles_all /* [world][64], rank order; NULL = back to NCCL */);
 /* In-place SUM allreduce of a flat fp32 buffer in `n_buckets` buckets given by bucket_offsets
  * [n_buckets+1] (host, elements), issued in order on `stream`. */
+/* Vector-Jacobian product of the network (trunk + heads): grads[p] = d( sum(dlogits * logits) + sum(dvalues * values) ) / dp
+ * for the minibatch (obs, row_idx), dlogits [nb, A], dvalues [nb, K] fp32 on the device.  For callers that put their
+ * own loss on top of drl_net_forward — what autograd does behind the reference's Agent.forward (agent.py:53-75).
+ * Activations are recomputed; `grads` is overwritten. */
+int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dlogits,
+                     const float* dvalues, float* grads, void* stream);
 /* Attach (or detach, comm = NULL) a communicator to a network handle: drl_net_ppo_step then returns gradients
  * that are already SUMMED over the ranks — what DistributedDataParallel's backward hooks do in the reference
  * (drl/utils/launch.py:310, drl/algos/ppo.py:233) — and overlaps the exchange with the backward pass: the

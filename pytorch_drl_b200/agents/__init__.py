@@ -97,6 +97,33 @@ class SimpleValueHead(tc.nn.Module):
                                                  b_init=b_init, **(head_architecture_cls_args or {}))
 
 
+class _FusedForward(tc.autograd.Function):
+    """logits, values = f(parameters; frames) with the backward pass delegated to the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, anchor, agent, obs):
+        eng = agent.engine
+        eng.sync_params()                      # parameters may have been changed through torch since the last call
+        logits, values, _, _ = eng.forward(obs)
+        ctx.agent, ctx.obs = agent, obs
+        return logits, values
+
+    @staticmethod
+    def backward(ctx, dlogits, dvalues):
+        eng = ctx.agent.engine
+        nb = ctx.obs.shape[0]
+        dl = dlogits if dlogits is not None else tc.zeros((nb, eng.A), device=eng.device)
+        dv = dvalues if dvalues is not None else tc.zeros((nb, eng.K), device=eng.device)
+        params = dict(ctx.agent.named_parameters())
+        if any(p.grad is None for p in params.values()):        # optimizer.zero_grad(set_to_none=True): start from zero
+            eng.grads.zero_()
+            gviews = eng.named_views(eng.grads)
+            for k, p in params.items():
+                p.grad = gviews[k]
+        eng.backward(ctx.obs, None, dl.contiguous(), dv.contiguous(), out=eng.grads)    # accumulate, like autograd
+        return None, None, None
+
+
 class Agent(tc.nn.Module):
     """drl/agents/integration/agent.py:10-75 with the whole forward fused on the GPU.
 
@@ -167,6 +194,13 @@ class Agent(tc.nn.Module):
         self.sync()
         return tc.nn.modules.module._IncompatibleKeys([], [])
 
+    def _autograd_anchor(self) -> tc.Tensor:
+        """A leaf that ties the fused forward into the autograd graph (the parameter gradients themselves are
+        written by the backward kernels straight into the `.grad` views)."""
+        if getattr(self, '_anchor', None) is None or self._anchor.device != self.engine.device:
+            self._anchor = tc.zeros(1, device=self.engine.device, requires_grad=True)
+        return self._anchor
+
     def _require_engine(self) -> LearnerEngine:
         if self.engine is None:
             raise RuntimeError('Agent.fuse(max_batch, precision) must be called first '
@@ -182,10 +216,18 @@ class Agent(tc.nn.Module):
         return (observations * 255.0).round_().clamp_(0, 255).to(tc.uint8)
 
     def forward(self, observations: tc.Tensor, predict: List[str], **kwargs):
+        """agent.py:53-75.  Under `torch.enable_grad()` the outputs are differentiable with respect to the
+        parameters: `loss.backward()` runs the fused backward kernels (drl_net_backward) and ACCUMULATES into every
+        parameter's `.grad` (which aliases the engine's flat gradient buffer), so a torch optimiser or
+        `engine.adam_step` can follow — custom losses work like with the reference.  Observations get no gradient
+        (the reference detaches them, agent.py:66-67)."""
         eng = self._require_engine()
         obs = self.to_uint8_frames(observations.detach() if self._detach_input else observations)
         obs = obs.to(eng.device).contiguous()
-        logits, values, _, _ = eng.forward(obs)
+        if tc.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            logits, values = _FusedForward.apply(self._autograd_anchor(), self, obs)
+        else:
+            logits, values, _, _ = eng.forward(obs)
         out = {}
         for key in predict:
             if key == 'policy':

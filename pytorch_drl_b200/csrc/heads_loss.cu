@@ -29,7 +29,9 @@ template <> __device__ __forceinline__ void store_act2<__nv_bfloat16>(__nv_bfloa
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-// MODE 0: forward only (logits/values/logp/entropy);  MODE 1: + losses;  MODE 2: + backward.
+// MODE 0: forward only (logits/values/logp/entropy);  MODE 1: + losses;  MODE 2: + backward;
+// MODE 3: backward of the heads from GIVEN d(logits) / d(values) (passed in logits_out / values_out): the
+// vector-Jacobian product a differentiable Agent.forward needs (no loss is evaluated).
 // OX = A + K when the launcher knows it at compile time (the Atari cases), else 0: the three O x 512 loops then
 // run exactly O iterations; with OX = 0 their iterations o >= O are predicated off but still take issue slots.
 template <int MAXA, int MODE, typename TD, int OX = 0>
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
   float gfc[16];                                  // running column sums of this lane's d(feat) columns
 #pragma unroll
   for (int q = 0; q < 16; ++q) gfc[q] = 0.f;
-  if (MODE == 2) {
+  if (MODE >= 2) {
 #pragma unroll
     for (int o = 0; o < MAXO; ++o) { gw[o][0] = 0.f; gw[o][1] = 0.f; }
   }
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
       v_new[k] = v;
       dv[k] = 0.f;
     }
-    if (live) {
+    if (MODE != 3 && live) {
       if (logits_out && lane < A) {
         float v = 0.f;
 #pragma unroll
@@ -140,7 +142,14 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
       }
       continue;
     }
-    if (live) {
+    if (MODE == 3) {
+      if (live) {                                  // upstream gradients instead of a loss
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) dlogit[j] = j < A ? logits_out[(size_t)i * A + j] : 0.f;
+#pragma unroll
+        for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) dv[k] = k < K ? values_out[(size_t)i * K + k] : 0.f;
+      }
+    } else if (live) {
       PpoSampleIn in;
       load_sample(batch, K, row_idx ? row_idx[i] : (int64_t)i, in);
       PpoSums s;
@@ -152,7 +161,7 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
         if (ent_out) ent_out[i] = ent;
       }
     }
-    if (MODE == 2) {
+    if (MODE >= 2) {
       // d(out) of this sample -> smem; features -> smem (for the CTA-wide head wgrad)
       float dout[MAXO];
 #pragma unroll
@@ -210,11 +219,11 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
       __syncthreads();
     }
   }
-  if (MODE >= 1) {
+  if (MODE == 1 || MODE == 2) {
     PpoSums tot = block_reduce_sums(acc, red);
     if (threadIdx.x == 0) ppo_accumulate_losses(tot, hp, inv_nb, losses_out);
   }
-  if (MODE == 2) {
+  if (MODE >= 2) {
     const int c0 = threadIdx.x, c1 = threadIdx.x + kWarps * 32;
 #pragma unroll
     for (int o = 0; o < MAXO; ++o) {
@@ -261,7 +270,8 @@ static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t*
   return DRL_OK;
 }
 
-// mode: 0 forward, 1 losses, 2 losses + backward.  dpre_is_bf16 selects the d(feat) dtype.
+// mode: 0 forward, 1 losses, 2 losses + backward, 3 backward from given d(logits) / d(values) (in logits_out /
+// values_out).  dpre_is_bf16 selects the d(feat) dtype.
 int heads_loss_dispatch(int mode, bool dpre_is_bf16, const float* feat, const HeadParams& hpp,
                         const int64_t* row_idx, int nb, const drl_ppo_batch_t& batch,
                         const drl_ppo_hyper_t& hp, float* losses_out, float* logits_out,
@@ -275,6 +285,8 @@ int heads_loss_dispatch(int mode, bool dpre_is_bf16, const float* feat, const He
   do {                                                             \
     if (mode == 0) GO(MAXA, 0, float);                             \
     if (mode == 1) GO(MAXA, 1, float);                             \
+    if (mode == 3 && dpre_is_bf16) GO(MAXA, 3, __nv_bfloat16);     \
+    if (mode == 3) GO(MAXA, 3, float);                             \
     if (dpre_is_bf16) GO(MAXA, 2, __nv_bfloat16);                  \
     GO(MAXA, 2, float);                                            \
   } while (0)

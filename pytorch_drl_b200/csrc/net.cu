@@ -190,6 +190,28 @@ static int ppo_common(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx
   return DRL_OK;
 }
 
+// Vector-Jacobian product of the whole network: gradients of sum(dlogits * logits) + sum(dvalues * values) with
+// respect to every parameter, for callers that build their own loss on top of drl_net_forward (a differentiable
+// Agent.forward, agent.py:53-75).  The activations are recomputed (the handle keeps no tape between calls).
+extern "C" int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dlogits,
+                                const float* dvalues, float* grads, void* stream) {
+  DRL_TRY(check_call(net, obs, nb));
+  if (!dlogits || !dvalues || !grads) return DRL_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  const bool bf16 = net->precision == DRL_PRECISION_BF16;
+  DRL_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->nparams * sizeof(float), st));
+  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
+  HeadParams hpp;
+  head_params(net, net->params, grads, hpp);
+  drl_ppo_batch_t batch{};
+  drl_ppo_hyper_t hp{};
+  hp.num_actions = net->A; hp.num_streams = net->K;
+  DRL_TRY(heads_loss_dispatch(3, bf16, net->feat, hpp, row_idx, nb, batch, hp, nullptr, const_cast<float*>(dlogits),
+                              const_cast<float*>(dvalues), nullptr, nullptr, net->dpre, st));
+  DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, st) : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
+  return DRL_OK;
+}
+
 extern "C" int drl_net_set_comm(drl_net_t* net, drl_comm_t* comm) {
   if (!net) return DRL_ERR_BAD_ARG;
   net->comm = comm;

@@ -125,6 +125,27 @@ class LearnerEngine:
                   'ppo_metrics')
         return self.losses
 
+    def backward(self, obs_u8: tc.Tensor, row_idx: Optional[tc.Tensor], dlogits: tc.Tensor, dvalues: tc.Tensor,
+                 out: Optional[tc.Tensor] = None) -> tc.Tensor:
+        """Vector-Jacobian product of the network for a custom loss: d(sum(dlogits*logits) + sum(dvalues*values))/dparams
+        as a flat tensor (drl_net_backward; the activations are recomputed, minibatches larger than max_batch are
+        processed in chunks and summed)."""
+        ops._cuda(obs_u8, tc.uint8, 'observations')
+        nb = int(row_idx.numel() if row_idx is not None else obs_u8.shape[0])
+        dl = ops._cuda(dlogits.contiguous(), tc.float32, 'dlogits')
+        dv = ops._cuda(dvalues.contiguous(), tc.float32, 'dvalues')
+        if dl.shape != (nb, self.A) or dv.shape != (nb, self.K):
+            raise ValueError('dlogits must be [nb, A] and dvalues [nb, K]')
+        total = out if out is not None else tc.zeros(self.nparams, dtype=tc.float32, device=self.device)
+        part = tc.empty(self.nparams, dtype=tc.float32, device=self.device)
+        for s in range(0, nb, self.max_batch):
+            m = min(self.max_batch, nb - s)
+            ridx = row_idx[s:s + m] if row_idx is not None else tc.arange(s, s + m, device=self.device, dtype=tc.int64)
+            check(self._L.drl_net_backward(self._h, ptr(obs_u8), ptr(ridx), m, ptr(dl[s:s + m]), ptr(dv[s:s + m]), ptr(part),
+                                           current_stream()), 'net_backward')
+            total += part
+        return total
+
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-5, grad_scale: float = 1.0) -> None:
         self.adam_steps += 1
         check(self._L.drl_net_adam_step(self._h, ptr(self.params), ptr(self.grads), ptr(self.exp_avg),

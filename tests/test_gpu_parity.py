@@ -712,3 +712,60 @@ def test_full_size_step_properties():
     g_ref = ref.grads.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(l_sub[:4], l_ref[:4], rtol=5 * TOL['bf16']['loss'], atol=5 * TOL['bf16']['loss'])
     assert g_sub @ g_ref / (np.linalg.norm(g_sub) * np.linalg.norm(g_ref)) > 0.995
+
+
+# ---- differentiable Agent.forward: custom torch losses on top of the fused network ------------------
+@pytest.mark.parametrize('precision', _precisions())
+def test_agent_forward_is_differentiable_like_the_reference(precision):
+    """loss.backward() through Agent.forward (Categorical + value heads) must give the gradients torch autograd gives
+    on the oracle model for the same custom loss, accumulate like autograd, and survive zero_grad(set_to_none=True)."""
+    from pytorch_drl_b200 import agents
+    A, rk, nb = 6, ['extrinsic', 'intrinsic_rnd'], 24
+    params = po.init_params(A, rk, seed=21)
+    preds = {'policy': agents.CategoricalPolicyHead(512, A)}
+    for k in rk:
+        preds[f'value_{k}'] = agents.SimpleValueHead(512)
+    agent = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4), preds)
+    agent.load_state_dict({k: tc.from_numpy(v) for k, v in params.items()})
+    agent.fuse(max_batch=16, precision=precision)                       # smaller than the batch: chunked backward
+    rs = np.random.RandomState(5)
+    obs_u8 = rs.randint(0, 256, size=(nb, 84, 84, 4)).astype(np.uint8)
+    actions = rs.randint(0, A, size=nb)
+    target = rs.standard_normal(nb).astype(np.float32)
+
+    def custom_loss(pi_logits, v_ext, v_int):
+        dist = tc.distributions.Categorical(logits=pi_logits)
+        a = tc.as_tensor(actions, device=pi_logits.device)
+        tgt = tc.as_tensor(target, device=pi_logits.device)
+        return -(dist.log_prob(a) * tgt).mean() - 0.03 * dist.entropy().mean() + ((v_ext - tgt) ** 2).mean() + v_int.abs().mean()
+
+    # oracle: plain torch autograd on the reference-layout parameters
+    p_ref = {k: tc.from_numpy(v.copy()).requires_grad_(True) for k, v in params.items()}
+    feat = po.trunk_forward(p_ref, po.scale_obs(tc.from_numpy(obs_u8)))
+    lg, vals = po.heads_forward(p_ref, feat, rk)
+    custom_loss(lg, vals['extrinsic'], vals['intrinsic_rnd']).backward()
+    g_ref = {k: v.grad.numpy() for k, v in p_ref.items()}
+
+    def run():
+        out = agent(tc.from_numpy(obs_u8).to(dev()), ['policy', 'value_extrinsic', 'value_intrinsic_rnd'])
+        loss = custom_loss(out['policy'].logits, out['value_extrinsic'], out['value_intrinsic_rnd'])
+        loss.backward()
+        return float(loss.detach())
+
+    opt = tc.optim.SGD(agent.parameters(), lr=0.0)
+    opt.zero_grad(set_to_none=True)
+    run()
+    t = TOL[precision]
+    got = {k: p.grad.cpu().numpy().copy() for k, p in agent.named_parameters()}
+    for k in g_ref:
+        assert rel_l2(got[k], g_ref[k]) < t['grad'], (k, rel_l2(got[k], g_ref[k]))
+    run()                                                               # second backward without zero_grad: accumulates
+    for k, p in agent.named_parameters():
+        assert rel_l2(p.grad.cpu().numpy(), 2.0 * got[k]) < 1e-4, k
+    opt.zero_grad(set_to_none=True)
+    run()
+    for k, p in agent.named_parameters():
+        assert rel_l2(p.grad.cpu().numpy(), got[k]) < 1e-4, k
+    with tc.no_grad():                                                  # no graph, no backward kernels
+        out = agent(tc.from_numpy(obs_u8).to(dev()), ['policy'])
+        assert not out['policy'].logits.requires_grad
