@@ -36,9 +36,9 @@ class RolloutStorage:
     vectorised GAE loads.  This is the storage side of drl/algos/common/rollout.py:105-224 for
     the learner (frames stay uint8: 28 224 B/sample instead of the reference's 112 896 B)."""
 
-    def __init__(self, n_envs: int, rollout_len: int, reward_keys: Sequence[str], device):
-        self.n_envs, self.T = n_envs, rollout_len
-        self.Tp = (rollout_len + 1 + 3) // 4 * 4
+    def __init__(self, n_envs: int, rollout_len: int, reward_keys: Sequence[str], device, extra_steps: int = 0):
+        self.n_envs, self.T, self.extra_steps = n_envs, rollout_len, extra_steps
+        self.Tp = (rollout_len + extra_steps + 1 + 3) // 4 * 4        # T + n frames, n = extra_steps + 1 (rollout.py:105-224)
         self.reward_keys = list(reward_keys)
         f = lambda dt, *tail: tc.zeros((n_envs, self.Tp) + tail, dtype=dt, device=device)  # noqa: E731
         self.data: Dict[str, Any] = dict(
@@ -53,8 +53,8 @@ class RolloutStorage:
         return self.data
 
     def load_env(self, e: int, observations, actions, rewards: Mapping[str, Any], dones) -> None:
-        """Fill env `e` from host/device arrays: T+1 frames/actions, T rewards/dones."""
-        d, T = self.data, self.T
+        """Fill env `e` from host/device arrays: T+n frames/actions, T+n-1 rewards/dones (n = extra_steps + 1)."""
+        d, T = self.data, self.T + self.extra_steps
         dev = d['actions'].device
         d['observations'][e, :T + 1].copy_(tc.as_tensor(observations).to(dev))
         d['actions'][e, :T + 1].copy_(tc.as_tensor(actions).to(dev))
@@ -94,8 +94,8 @@ class PPO:
             raise NotImplementedError('separate value network (use_shared_architecture: False) is not fused')
         if use_pcgrad:
             raise NotImplementedError('PCGrad is off in both shipped configs and not on the fused path')
-        if extra_steps != 0:
-            raise NotImplementedError('extra_steps > 0 (n-step estimators) is not on the fused path')
+        if extra_steps < 0:
+            raise ValueError('extra_steps must be >= 0')
         assert rollout_len % learner_batch_size == 0                    # samplers.py:51
         self._rank, self._world_size = rank, world_size
         self._rollout_len, self._extra_steps = rollout_len, extra_steps
@@ -170,7 +170,7 @@ class PPO:
         every env; fills logprobs/entropies/vpreds in place and returns the rollout."""
         obs = rollout['observations']
         n, Tp = obs.shape[0], obs.shape[1]
-        T1 = self._rollout_len + 1
+        T1 = self._rollout_len + self._extra_steps + 1                 # T + n frames (abstract.py:383-397)
         e = tc.arange(n, device=obs.device, dtype=tc.int64).unsqueeze(1) * Tp
         rows = (e + tc.arange(T1, device=obs.device, dtype=tc.int64).unsqueeze(0)).reshape(-1)
         _, values, logp, ent = self._engine.forward(obs, rows, actions=rollout['actions'])
@@ -184,10 +184,19 @@ class PPO:
     def credit_assignment(self, rollout: Dict[str, Any]) -> Dict[str, Any]:
         """abstract.py:413-445: per reward stream GAE -> vtargs = A + V -> optional per-env
         standardisation, one fused launch per stream."""
+        T, n = self._rollout_len, self._extra_steps + 1
         for k in self._get_reward_keys(omit_raw=True):
             op = self._credit_assignment_ops[k]
-            op.call_fused(self._rollout_len, rollout['rewards'][k], rollout['vpreds'][k], rollout['dones'],
-                          self._standardize_adv, rollout['advantages'][k], rollout['vtargs'][k])
+            if n == 1 and hasattr(op, 'call_fused'):
+                op.call_fused(T, rollout['rewards'][k], rollout['vpreds'][k], rollout['dones'],
+                              self._standardize_adv, rollout['advantages'][k], rollout['vtargs'][k])
+                continue
+            # n-step estimators / extra steps: estimator over T + n - 1 steps, then the reference's three lines
+            # (abstract.py:427-439): vtargs = A + V[:T], optional standardisation, both kept for the first T steps
+            adv = op(rollout_len=T, extra_steps=n - 1, rewards=rollout['rewards'][k][:, :T + n - 1],
+                     vpreds=rollout['vpreds'][k][:, :T + n], dones=rollout['dones'][:, :T + n - 1])
+            rollout['vtargs'][k][:, :T] = adv + rollout['vpreds'][k][:, :T]
+            rollout['advantages'][k][:, :T] = ops.standardize(adv.contiguous()) if self._standardize_adv else adv
         return rollout
 
     # ---- losses -------------------------------------------------------------------------------------

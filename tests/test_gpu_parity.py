@@ -769,3 +769,42 @@ def test_agent_forward_is_differentiable_like_the_reference(precision):
     with tc.no_grad():                                                  # no graph, no backward kernels
         out = agent(tc.from_numpy(obs_u8).to(dev()), ['policy'])
         assert not out['policy'].logits.requires_grad
+
+
+# ---- extra_steps > 0 in the PPO rollout path (abstract.py:413-445 with n = extra_steps + 1) ------------------------
+@pytest.mark.parametrize('op_name', ['GAE', 'NStepAdvantageEstimator'])
+def test_ppo_credit_assignment_with_extra_steps(op_name):
+    from pytorch_drl_b200 import agents, algos
+    from pytorch_drl_b200.algos.credit_assignment import NStepAdvantageEstimator
+    from oracle import credit_oracle as co
+    A, rk, n_envs, T, extra = 6, ['extrinsic'], 3, 16, 2
+    n = extra + 1
+    agent = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4),
+                         {'policy': agents.CategoricalPolicyHead(512, A), 'value_extrinsic': agents.SimpleValueHead(512)})
+    agent.load_state_dict({k: tc.from_numpy(v) for k, v in po.init_params(A, rk, 3).items()})
+    agent.fuse(max_batch=n_envs * (T + n), precision='fp32')
+    op = algos.GAE(gamma=0.99, use_dones=True, lambda_=0.9) if op_name == 'GAE' else NStepAdvantageEstimator(gamma=0.99, use_dones=True)
+    algo = algos.PPO(rank=0, world_size=1, rollout_len=T, extra_steps=extra, credit_assignment_ops={'extrinsic': op},
+                     policy_net=agent, policy_optimizer=tc.optim.Adam(agent.parameters(), lr=1e-3), standardize_adv=True,
+                     opt_epochs=1, learner_batch_size=8, envs_per_rank=n_envs, sampler_seed=0)
+    st = algos.RolloutStorage(n_envs, T, rk, dev(), extra_steps=extra)
+    assert st.Tp >= T + n
+    rs = np.random.RandomState(0)
+    obs = rs.randint(0, 256, size=(n_envs, T + n, 84, 84, 4)).astype(np.uint8)
+    act = rs.randint(0, A, size=(n_envs, T + n))
+    rew = (rs.randint(-1, 2, size=(n_envs, T + n - 1)) + rs.standard_normal((n_envs, T + n - 1)) * 0.1).astype(np.float32)
+    don = (rs.uniform(size=(n_envs, T + n - 1)) < 0.1).astype(np.float32)
+    for e in range(n_envs):
+        st.load_env(e, obs[e], act[e], {'extrinsic': rew[e]}, don[e])
+    rollout = algo.credit_assignment(algo.annotate(st.as_dict()))
+    v = rollout['vpreds']['extrinsic'].cpu().numpy()
+    # the annotate pass covered all T + n frames: value predictions equal a direct forward of those frames
+    _, vals, _, _ = agent.engine.forward(tc.from_numpy(obs.reshape(-1, 84, 84, 4)).to(dev()))
+    np.testing.assert_allclose(v[:, :T + n], vals.cpu().numpy().reshape(n_envs, T + n), rtol=1e-5, atol=1e-6)
+    for e in range(n_envs):
+        if op_name == 'GAE':
+            adv = po.gae(T, extra, rew[e], v[e, :T + n], don[e], 0.99, 0.9, True)
+        else:
+            adv = co.nstep_advantages(T, extra, rew[e], v[e, :T + n], don[e], 0.99, True)
+        np.testing.assert_allclose(rollout['vtargs']['extrinsic'][e, :T].cpu().numpy(), adv + v[e, :T], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(rollout['advantages']['extrinsic'][e, :T].cpu().numpy(), po.standardize(adv), rtol=2e-4, atol=2e-5)
