@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
     // ================= converters: raw uint8 frame -> 1024-biased fp16 block image ======================
     // Thread (quarter = warp & 3, lane) converts blocks q = tile*128 + quarter*32 + lane for two tiles.  For tap
     // (0,0) the A row of GEMM row r IS image row r, and tile row q % 128 lives in this thread's own TMEM lane: the
-    // 32 registers it just produced also go to tensor memory (tcgen05.st).  Tap (0,1) needs image row r + 1 =
-    // the registers of the NEXT lane: one shuffle per register (lane 31 converts its neighbour block itself).
-    // Both taps are then issued in TS form, so half of the A operand never crosses the shared-memory port.
+    // 32 registers it just produced also go to tensor memory (tcgen05.st).  Tap (0,1) needs image row r + 1: the
+    // thread converts that block too.  Both taps are then issued in TS form, so half of the A operand never
+    // crosses the shared-memory port.
     const int quarter = warp & 3, half = (warp - W_CONV) >> 2;
     const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
     auto convert_block = [&](uint32_t raw, int q, uint32_t (&r)[32]) {
@@ -322,17 +322,14 @@ __global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Co
         tc_fence_after();
         const uint32_t t_a = tmem_base + t_lane + 128 + slot * 64;
         tmem_st_32x32b_x32(t_a, r);                                   // tap (0,0)
-        uint32_t rn[32];
+        // tap (0,1) = image row r + 1: converted again from the raw frame (4 LDS.128 + 32 PRMT) — cheaper on the
+        // L1/shared data pipe than 32 shuffles (ncu: the LSU wavefronts of a shuffle version ate the saving)
+        if (q + 1 < 441) convert_block(raw, q + 1, r);
+        else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rn[i] = __shfl_down_sync(0xffffffffu, r[i], 1);
-        if (lane == 31) {                                             // the neighbour block lives in another warp
-          if (q + 1 < 441) convert_block(raw, q + 1, rn);
-          else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) rn[i] = 0u;
-          }
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
-        tmem_st_32x32b_x32(t_a + 32, rn);                             // tap (0,1)
+        tmem_st_32x32b_x32(t_a + 32, r);                              // tap (0,1)
       }
       tmem_st_wait();
       tc_fence_before();
