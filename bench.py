@@ -89,6 +89,8 @@ def cpu_reference_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_st
     through the same conv/linear/Adam ops the reference calls, all host threads) on a bounded sample:
     `n_envs` ranks x B samples per step.  Returns (samples/s, steps, threads)."""
     from oracle import ppo_oracle as po
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must still use all the host threads it can
+    tc.set_num_threads(max(1, os.cpu_count() or 1))
     rs = np.random.RandomState(0)
     params = po.init_params(A, REWARD_KEYS, seed=11)
     hp = po.Hyper({'extrinsic': 1.0}, 0.2, 0.01, 1.0, False, True)
