@@ -163,6 +163,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the GAE / loss / metrics-pass / sum-tree side measurements')
     ap.add_argument('--debug-flags', default='', help='kernel-variant experiments, e.g. "2=1,3=0" (drl_debug_set)')
     ap.add_argument('--comm', default='nccl', choices=['p2p-overlap', 'p2p', 'p2p-1', 'nccl-overlap', 'nccl', 'nccl-1'],
                     help='gradient exchange variant at N > 1: NCCL or NVLink peer-memory kernels, after the backward pass (2 buckets / -1: one) or overlapped with it')
@@ -321,6 +322,9 @@ def main():
             o = roof['other']
             roof['other'] = {k: roof[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
             roof.update(o)
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = run_extras(algo, rollout, n_envs, dev, ms_per_step, pk['hbm'])
     cpu = None
     if world == 1 and not args.no_cpu:
         rate, n, threads, el = cpu_reference_step_rate(8, args.cpu_seconds)
@@ -334,11 +338,94 @@ def main():
                                f'learner step = {B} samples x {n_envs} envs = {nb} samples/GPU, A={A}, K=1',
                    'parallelism': f'dp{world}', 'l2_policy': 'inputs larger than L2 (3.8 GB uint8 rollout per GPU, '
                                                              'a different random minibatch every step)'},
-        'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+        'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'extras': extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    tc.cuda.synchronize()
+    e0, e1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    tc.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_extras(algo, rollout, n_envs, dev, ms_per_step, hbm_peak):
+    """The side measurements SURVEY §8(d) asks for next to the headline (rank 0, N=1, a few hundred ms of GPU time):
+    GAE in (env x step)/s and HBM GB/s, the fused loss kernel in GB/s, the per-epoch forward-only metrics pass
+    (ppo.py:265-266) and the update throughput with that pass included, the PER sum-tree at 2^20 leaves / batch 512.
+    The HBM figures use inputs larger than L2 (126 MB); the config-sized calls are launch-latency bound and are
+    reported as microseconds."""
+    from pytorch_drl_b200 import ops
+    from pytorch_drl_b200.replay import SumTree
+    out = {}
+    g = tc.Generator(device=dev)
+    g.manual_seed(7)
+    # GAE + vtarg + per-env standardisation: 20 B per (env, step) read+written once (+8 B for the second pass
+    # of the standardisation, counted as algorithmic traffic only where it happens)
+    for tag, n in (('config', n_envs), ('large', 65536)):
+        r = tc.randint(-1, 2, (n, T), device=dev, generator=g).float()
+        v = tc.randn((n, T + 4), device=dev, generator=g)
+        d = (tc.rand((n, T), device=dev, generator=g) < 0.01).float()
+        adv, vt = tc.empty((n, T), device=dev), tc.empty((n, T), device=dev)
+        ms = _timed(lambda: ops.gae(r, v, d, 0.99, 0.95, True, True, T, adv, vt))
+        out[f'gae_{tag}'] = {'envs': n, 'steps': T, 'us': ms * 1e3, 'env_steps_per_s': n * T / (ms * 1e-3),
+                             'GBps': 20.0 * n * T / (ms * 1e-3) / 1e9, 'frac_hbm': 20.0 * n * T / (ms * 1e-3) / 1e9 / hbm_peak,
+                             'bytes_per_env_step': 20}
+        del r, v, d, adv, vt
+    # fused clipped-surrogate / value / entropy loss forward + backward on given logits: 8A + 12 + 20K B per sample
+    for tag, n in (('config', n_envs * B), ('large', 1 << 22)):
+        logits = tc.randn((n, A), device=dev, generator=g)
+        values = tc.randn((n, 1), device=dev, generator=g)
+        acts = tc.randint(0, A, (n,), device=dev, generator=g)
+        lp = tc.log_softmax(logits, -1).gather(1, acts[:, None]).squeeze(1) + 0.05 * tc.randn((n,), device=dev, generator=g)
+        advs, vold, vtg = (tc.randn((n,), device=dev, generator=g) for _ in range(3))
+        hyper = ops.make_hyper(A, [1.0], 0.2, 0.01, 1.0, False, True)
+        batch = ops.make_batch(acts, lp, [advs], [vold], [vtg])
+        bytes_per = 8 * A + 12 + 20 + 8                     # + logp and entropy written back
+        import ctypes
+        from pytorch_drl_b200 import _lib
+        from pytorch_drl_b200._lib import current_stream, ptr
+        L = _lib.lib()
+        losses, lpo, eno = tc.empty(5, device=dev), tc.empty(n, device=dev), tc.empty(n, device=dev)
+        dl, dvv = tc.empty_like(logits), tc.empty_like(values)
+
+        def call():                                          # the C-ABI entry on caller-allocated outputs
+            rc = L.drl_ppo_loss_fwd_bwd(ptr(logits), ptr(values), None, n, ctypes.byref(batch), ctypes.byref(hyper),
+                                        ptr(losses), ptr(lpo), ptr(eno), ptr(dl), ptr(dvv), current_stream())
+            assert rc == 0
+        ms = _timed(call)
+        out[f'ppo_loss_{tag}'] = {'samples': n, 'us': ms * 1e3, 'GBps': bytes_per * n / (ms * 1e-3) / 1e9,
+                                  'frac_hbm': bytes_per * n / (ms * 1e-3) / 1e9 / hbm_peak, 'bytes_per_sample': bytes_per}
+        del losses, lpo, eno, dl, dvv
+        del logits, values, acts, lp, advs, vold, vtg
+    # per-epoch metrics pass: forward + losses over the whole rollout, no gradient (ppo.py:265-266)
+    ms_metrics = _timed(lambda: algo.compute_losses_and_metrics(rollout, no_grad=True), iters=5, warm=2)
+    steps_per_epoch = T // B
+    out['metrics_pass'] = {'samples': n_envs * T, 'ms': ms_metrics, 'forward_samples_per_s': n_envs * T / (ms_metrics * 1e-3)}
+    out['update_with_metrics_pass'] = {
+        'samples_per_s': n_envs * T / ((steps_per_epoch * ms_per_step + ms_metrics) * 1e-3),
+        'note': f'one epoch = {steps_per_epoch} learner steps ({n_envs * T} update samples) + one forward-only pass over the same {n_envs * T} samples'}
+    # PER sum-tree: 2^20 leaves, batch 512 (dependent-access latency bound; GB/s is not meaningful)
+    cap, bs = 1 << 20, 512
+    tree = SumTree(cap, device=dev)
+    tree.set_leaves(tc.rand(cap, device=dev, generator=g) + 1e-3)
+    idx = tc.randint(0, cap, (bs,), device=dev, generator=g)
+    pr = tc.rand(bs, device=dev, generator=g) + 1e-3
+    u01 = tc.rand(bs, device=dev, generator=g)
+    ms_u = _timed(lambda: tree.update(idx, pr), iters=50)
+    ms_s = _timed(lambda: tree.sample(tree.stratified_u(u01)), iters=50)
+    out['sumtree'] = {'leaves': cap, 'batch': bs, 'update_us': ms_u * 1e3, 'sample_us': ms_s * 1e3,
+                      'updates_per_s': bs / (ms_u * 1e-3), 'samples_per_s': bs / (ms_s * 1e-3)}
+    return out
 
 
 def run_e2e(algo, agent, rollout, st, n_envs, dev, world, args, rows_list):

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
       load_sample(batch, K, row_idx ? row_idx[i] : (int64_t)i, in);
       PpoSums s;
       float logp, ent;
-      ppo_sample<MAXA>(logit, v_new, in, hp, inv_nb, MODE == 2, dlogit, dv, s, logp, ent);
+      ppo_sample<MAXA, OX ? OX - 1 : 0, OX ? 1 : 0>(logit, v_new, in, hp, inv_nb, MODE == 2, dlogit, dv, s, logp, ent);   // OX is only dispatched for K = 1
       if (lane == 0) {
         acc.surr += s.surr; acc.ent += s.ent; acc.clip += s.clip; acc.vf += s.vf;
         if (logp_out) logp_out[i] = logp;

@@ -6,14 +6,18 @@
 
 namespace drl {
 
-template <int MAXA>
+// AX / KX: exact action / stream counts for the common Atari heads (0 = dynamic), see ppo_math.cuh.  The kernel is
+// instruction-issue bound (ncu: ~590 warp instructions per sample at A = 6 before the exact-count instantiations), not
+// access-pattern bound: staging the logits tile through shared memory for coalesced copies made it slower (119 -> 199 us
+// at 4 M samples, profiles/r01_notes.md).
+template <int MAXA, int AX = 0, int KX = 0>
 __global__ void __launch_bounds__(256) ppo_loss_kernel(
     const float* __restrict__ logits, const float* __restrict__ values,
     const int64_t* __restrict__ row_idx, int nb, drl_ppo_batch_t batch, drl_ppo_hyper_t hp,
     float inv_nb, float* __restrict__ losses_out, float* __restrict__ logp_out,
     float* __restrict__ ent_out, float* __restrict__ dlogits, float* __restrict__ dvalues) {
   __shared__ float red[128];
-  const int A = hp.num_actions, K = hp.num_streams;
+  const int A = AX ? AX : hp.num_actions, K = KX ? KX : hp.num_streams;
   PpoSums acc{0.f, 0.f, 0.f, 0.f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
     float logit[MAXA], dlogit[MAXA], v_new[DRL_MAX_REWARD_STREAMS], dv[DRL_MAX_REWARD_STREAMS];
@@ -25,7 +29,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(
     load_sample(batch, K, row_idx ? row_idx[i] : (int64_t)i, in);
     PpoSums s;
     float logp, ent;
-    ppo_sample<MAXA>(logit, v_new, in, hp, inv_nb, dlogits != nullptr, dlogit, dv, s, logp, ent);
+    ppo_sample<MAXA, AX, KX>(logit, v_new, in, hp, inv_nb, dlogits != nullptr, dlogit, dv, s, logp, ent);
     acc.surr += s.surr; acc.ent += s.ent; acc.clip += s.clip; acc.vf += s.vf;
     if (logp_out) logp_out[i] = logp;
     if (ent_out) ent_out[i] = ent;
@@ -81,13 +85,18 @@ extern "C" int drl_ppo_loss_fwd_bwd(const float* logits, const float* values,
   if (blocks > maxb) blocks = maxb;
   const float inv_nb = 1.0f / (float)nb;
   const int A = hyper->num_actions;
-#define LAUNCH(MAXA)                                                                             \
-  ppo_loss_kernel<MAXA><<<blocks, threads, 0, st>>>(logits, values, row_idx, nb, *batch, *hyper, \
-                                                    inv_nb, losses_out, logp_out, entropy_out,   \
-                                                    dlogits, dvalues)
-  if (A <= 8) LAUNCH(8);
-  else if (A <= 18) LAUNCH(18);
-  else LAUNCH(32);
+#define LAUNCH(MAXA, AX, KX)                                                                                \
+  ppo_loss_kernel<MAXA, AX, KX><<<blocks, threads, 0, st>>>(logits, values, row_idx, nb, *batch, *hyper, inv_nb, \
+                                                            losses_out, logp_out, entropy_out, dlogits, dvalues)
+  const int K = hyper->num_streams;
+  if (A == 6 && K == 1) LAUNCH(8, 6, 1);
+  else if (A == 4 && K == 1) LAUNCH(8, 4, 1);
+  else if (A == 9 && K == 1) LAUNCH(18, 9, 1);
+  else if (A == 18 && K == 1) LAUNCH(18, 18, 1);
+  else if (A == 18 && K == 2) LAUNCH(18, 18, 2);
+  else if (A <= 8) LAUNCH(8, 0, 0);
+  else if (A <= 18) LAUNCH(18, 0, 0);
+  else LAUNCH(32, 0, 0);
 #undef LAUNCH
   DRL_LAUNCH_CHECK();
   return DRL_OK;

@@ -34,13 +34,16 @@ __device__ __forceinline__ float crit_grad(float d, int kind) {
 }
 
 // logit[0..A) in, dlogit[0..A) out (if want_grad).  v_new[k], dv[k] per reward stream.
-template <int MAXA>
+// AX / KX: action and stream counts when the launcher knows them at compile time (0 = read them from hp): the
+// predicated iterations j >= A of the unrolled loops then disappear (they still take issue slots otherwise).
+template <int MAXA, int AX = 0, int KX = 0>
 __device__ __forceinline__ void ppo_sample(const float (&logit)[MAXA], const float* v_new,
                                            const PpoSampleIn& in, const drl_ppo_hyper_t& hp,
                                            float inv_nb, bool want_grad, float (&dlogit)[MAXA],
                                            float* dv, PpoSums& out, float& logp_out,
                                            float& ent_out) {
-  const int A = hp.num_actions;
+  const int A = AX ? AX : hp.num_actions;
+  const int K = KX ? KX : hp.num_streams;
   float m = -INFINITY;
 #pragma unroll
   for (int j = 0; j < MAXA; ++j) if (j < A) m = fmaxf(m, logit[j]);
@@ -67,13 +70,16 @@ __device__ __forceinline__ void ppo_sample(const float (&logit)[MAXA], const flo
   const float lo = 1.f - hp.clip_param, hi = 1.f + hp.clip_param;
   const float clipped = fminf(fmaxf(ratio, lo), hi);
   float aw = 0.f;
-  for (int k = 0; k < hp.num_streams; ++k) aw += hp.reward_weights[k] * in.adv[k];
+#pragma unroll
+  for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) if (k < K) aw += hp.reward_weights[k] * in.adv[k];
   const float s1 = aw * ratio, s2 = aw * clipped;
   out.surr = fminf(s1, s2);
   out.clip = s1 > s2 ? 1.f : 0.f;
   out.ent = H;
   float vf = 0.f;
-  for (int k = 0; k < hp.num_streams; ++k) {
+#pragma unroll
+  for (int k = 0; k < DRL_MAX_REWARD_STREAMS; ++k) {
+    if (k >= K) break;
     const float coef = hp.vf_simple_weighting ? 1.f : hp.reward_weights[k] * hp.reward_weights[k];
     const float d1 = v_new[k] - in.vtarg[k];
     const float l1 = crit_val(d1, hp.vf_loss_kind);
