@@ -15,6 +15,7 @@
 #include "umma_tma_conv.cuh"
 #include "umma_conv1_s2d.cuh"
 #include "umma_tma_gemm2.cuh"
+#include "umma_tma_conv2.cuh"
 
 namespace drl {
 
@@ -370,7 +371,8 @@ static int make_tmap_dy1(CUtensorMap* m, const void* base, uint64_t nb) {
 }
 
 template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS, int KB, int KBX, int SHIFT_RW, int PLANES>
-static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st) {
+static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st,
+                           int pair_bit = 0) {
   ProfileScope prof(site, st);
   CUtensorMap tm;
   DRL_TRY(make_tmap_act4d(&tm, src, (uint64_t)nb, (uint64_t)H, (uint64_t)W, (uint32_t)BW, (uint32_t)BH, (uint32_t)a.planes));
@@ -387,6 +389,22 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   a.use_base_offset = 0;
   if (a.OH * a.RW > MROWS) return DRL_ERR_BAD_ARG;       // every output row must fall inside the tile
   if (a.KB != KB || a.KBX != KBX || a.SHIFT_RW != SHIFT_RW || a.planes != PLANES) return DRL_ERR_BAD_ARG;
+  if constexpr (MROWS == 128) {
+    if (pair_bit && (g_debug_flags[7] & pair_bit)) {     // CTA pairs: one sample per CTA, half of the weight rows each
+      auto kern2 = tma_conv2_kernel<N, EPI, NR, NACC, NEPI, KB, KBX, SHIFT_RW, PLANES>;
+      const int smem2 = tma_conv2_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
+      static int configured2 = 0;
+      if (configured2 < smem2) {
+        DRL_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        configured2 = smem2;
+      }
+      const int total_pairs = (nb + 1) / 2;
+      const int pairs = total_pairs < sm_count() / 2 ? total_pairs : sm_count() / 2;
+      kern2<<<2 * pairs, 32 * (4 * NEPI + 2), smem2, st>>>(tm, a);
+      DRL_LAUNCH_CHECK();
+      return DRL_OK;
+    }
+  }
   auto kern = tma_conv_kernel<N, EPI, NR, NACC, NEPI, MROWS, KB, KBX, SHIFT_RW, PLANES>;
   const int smem = tma_conv_smem<N>(a.KB, a.raw_buf_bytes, NR, a.slack_bytes);
   if (smem > 227 * 1024) return DRL_ERR_BAD_ARG;
@@ -520,7 +538,7 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     // stride 2), so tap row ky reads plane ky&1 shifted by (ky>>1)*10 + half and the GEMM rows are oy*10 + ox
     TmaConvArgs c2 = tma_conv_args(8, 2, 10, 10, 0, 1, 9, 9, e->w2f, n->act[1], p + o[3], nullptr, 5184, 9 * 64, 64, 1, 0);
     c2.planes = 2; c2.bits_out = e->bits[1];
-    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 4, 4, 2, 128, 8, 2, 10, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st)));
+    DRL_TRY((launch_tma_conv<64, EPI_BIAS_RELU_BF16, 4, 4, 2, 128, 8, 2, 10, 2>("conv2_fwd", n->act[0], nb, 20, 10, 10, 20, c2, st, 1)));
   } else {
     DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_BIAS_RELU_BF16>("conv2_fwd", a2, 1, st)));
   }
@@ -616,7 +634,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
       c.bias_grad = g + o[3]; c.bias_mod = 64;       // conv2 bias gradient
       c.bits_in = e->bits[1];
-      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2, 128, 9, 3, 11, 1>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st)));
+      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2, 128, 9, 3, 11, 1>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st, 2)));
     } else {
       DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
     }
@@ -649,7 +667,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
       c.bias_grad = g + o[1]; c.bias_mod = 32;       // conv1 bias gradient
       c.bits_in = e->bits[0];
-      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 2, 128, 4, 2, 11, 1>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st)));
+      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 2, 128, 4, 2, 11, 1>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st, 4)));
     } else {
       DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
     }

@@ -53,6 +53,76 @@ struct TmaConvArgs {
   int bias_mod;
 };
 
+// One accumulator tile of the row epilogue: GEMM row r of sample b -> bias + ReLU (+ mask bits) or ReLU-mask of the
+// layer below (+ running bias-gradient column sums).  `tmem_acc` = this warp's lane quarter, column 0 of the
+// accumulator; `release()` frees the accumulator once its last chunk sits in registers.  Shared by the single-CTA
+// kernel and the CTA-pair kernel (umma_tma_conv2.cuh).
+template <int N, int EPI, int BG, int CS, typename Release>
+__device__ __forceinline__ void tma_conv_epilogue_tile(const TmaConvArgs& args, int b, int r, bool sample_ok, uint32_t tmem_acc,
+                                                       const float* sBias, float (&cs)[CS], uint64_t* tfull_bar,
+                                                       uint32_t tfull_parity, Release release) {
+  using namespace umma;
+  auto coff = [&](int ch) -> int64_t {
+    return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
+  };
+  const int y = r / args.RW, x = r - y * args.RW;
+  const bool ok = sample_ok && y < args.OH && x < args.OW;
+  const int64_t ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(y * args.osy) * args.out_row_pitch +
+                       (int64_t)(x * args.osx) * args.out_C;
+  uint32_t mbits[N / 32];                           // ReLU mask bits of this row, one word per 32-column chunk
+  if (EPI == EPI_MASK_BF16 && ok) {
+#pragma unroll
+    for (int ch = 0; ch < N / 32; ++ch) mbits[ch] = __ldg(args.bits_in + ((ooff + coff(ch)) >> 5));
+  }
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+#pragma unroll
+  for (int ch = 0; ch < N / 32; ++ch) {
+    uint32_t rr[32];
+    tmem_ld_32x32b_x32(tmem_acc + ch * 32, rr);
+    tmem_ld_wait();
+    if (ch == N / 32 - 1) {
+      tc_fence_before();
+      release();
+    }
+    if (ok) {
+      if (EPI == EPI_BIAS_RELU_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_bf16x2_relu(fmaf(__uint_as_float(rr[2 * i]), args.scale, sBias[ch * 32 + 2 * i]),
+                                   fmaf(__uint_as_float(rr[2 * i + 1]), args.scale, sBias[ch * 32 + 2 * i + 1]));
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          stg_v8(o + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4], pk[8 * q + 5], pk[8 * q + 6],
+                 pk[8 * q + 7]);
+        const uint32_t bits = relu_bits_from_pairs(pk);
+        if (args.bits_out) args.bits_out[(ooff + ch * 32) >> 5] = bits;
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float lo = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i)) & 1u ? __uint_as_float(rr[16 * q + 2 * i]) : 0.f;
+            const float hi2 = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[16 * q + 2 * i + 1]) : 0.f;
+            pk[i] = pack_bf16x2(lo, hi2);
+            rr[16 * q + 2 * i] = __float_as_uint(lo);
+            rr[16 * q + 2 * i + 1] = __float_as_uint(hi2);
+          }
+          stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+    }
+    if (EPI == EPI_MASK_BF16 && ok) {                 // fused bias gradient of the layer below
+#pragma unroll
+      for (int i = 0; i < 32; ++i) cs[(ch % BG) * 32 + i] += __uint_as_float(rr[i]);
+    }
+  }
+}
+
 // One CTA per SM: NR staged samples in flight, NACC accumulators in TMEM, NEPI epilogue warpgroups that take
 // tiles round-robin.  The staging buffers are packed at the TMA box size: the 128-row MMA window of a tap
 // may read past its sample into the next buffer (or the `slack_bytes` tail) — those rows belong to grid
@@ -176,9 +246,6 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
     }
     __syncwarp();
   } else {
-    auto coff = [&](int ch) -> int64_t {
-      return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
-    };
     // fused bias gradient: every thread keeps running column sums of ITS rows (32 adds per chunk and tile);
     // the cross-lane reduction happens once, after the last tile.  Column chunk ch feeds bias group ch % BG.
     constexpr int BG = N == 64 ? 2 : 1;               // bias_mod / 32 (checked by the launcher)
@@ -193,63 +260,8 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
       for (int mt = 0; mt < args.MT; ++mt, ++it) {
         if (NEPI > 1 && (int)(it % NEPI) != wg) continue;
         const uint32_t acc = it % NACC;
-        const int r = mt * 128 + trow;
-        const int y = r / args.RW, x = r - y * args.RW;
-        const bool ok = y < args.OH && x < args.OW;
-        const int64_t ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(y * args.osy) * args.out_row_pitch +
-                             (int64_t)(x * args.osx) * args.out_C;
-        uint32_t mbits[N / 32];                           // ReLU mask bits of this row, one word per 32-column chunk
-        if (EPI == EPI_MASK_BF16 && ok) {
-#pragma unroll
-          for (int ch = 0; ch < N / 32; ++ch) mbits[ch] = __ldg(args.bits_in + ((ooff + coff(ch)) >> 5));
-        }
-        mbar_wait(tfull + acc, (it / NACC) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ch = 0; ch < N / 32; ++ch) {
-          uint32_t rr[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * N + ch * 32, rr);
-          tmem_ld_wait();
-          if (ch == N / 32 - 1) {
-            tc_fence_before();
-            mbar_arrive(tempty + acc);
-          }
-          if (ok) {
-            if (EPI == EPI_BIAS_RELU_BF16) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                pk[i] = pack_bf16x2_relu(fmaf(__uint_as_float(rr[2 * i]), args.scale, sBias[ch * 32 + 2 * i]),
-                                         fmaf(__uint_as_float(rr[2 * i + 1]), args.scale, sBias[ch * 32 + 2 * i + 1]));
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-                stg_v8(o + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4], pk[8 * q + 5], pk[8 * q + 6],
-                       pk[8 * q + 7]);
-              const uint32_t bits = relu_bits_from_pairs(pk);
-              if (args.bits_out) args.bits_out[(ooff + ch * 32) >> 5] = bits;
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float lo = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i)) & 1u ? __uint_as_float(rr[16 * q + 2 * i]) : 0.f;
-                  const float hi2 = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[16 * q + 2 * i + 1]) : 0.f;
-                  pk[i] = pack_bf16x2(lo, hi2);
-                  rr[16 * q + 2 * i] = __float_as_uint(lo);
-                  rr[16 * q + 2 * i + 1] = __float_as_uint(hi2);
-                }
-                stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-              }
-            }
-          }
-          if (EPI == EPI_MASK_BF16 && ok) {                 // fused bias gradient of the layer below
-#pragma unroll
-            for (int i = 0; i < 32; ++i) cs[(ch % BG) * 32 + i] += __uint_as_float(rr[i]);
-          }
-        }
+        tma_conv_epilogue_tile<N, EPI, BG>(args, b, mt * 128 + trow, true, tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * N,
+                                           sBias, cs, tfull + acc, (it / NACC) & 1, [&]() { mbar_arrive(tempty + acc); });
       }
     }
     if (EPI == EPI_MASK_BF16 && args.bias_grad) {

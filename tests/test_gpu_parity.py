@@ -432,6 +432,9 @@ def test_rnd_learn_wrapper_semantics():
     assert not tc.equal(rnd.student_params, p0) and rnd.adam_steps == 1
 
 
+PAIR_DEFAULT = 0     # library default of debug flag 7 (conv kernels on CTA pairs)
+
+
 def test_alternative_bf16_engines_stay_in_parity():
     """The cp.async row-gather conv / wgrad kernels and the shared-memory-operand conv1 forward are kept behind
     drl_debug_set (they measured slower): they must keep producing the same gradients as the default engines."""
@@ -459,13 +462,14 @@ def test_alternative_bf16_engines_stay_in_parity():
                            [d['vtargs']['extrinsic']])
     try:
         # (tma conv fwd/dgrad kernels, tma conv wgrad kernels, conv1 forward A operand in TMEM)
-        for flags in ((0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 0, 2), (1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 1, 0)):
+        for flags in ((0, 0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 0, 2, 0), (1, 1, 1, 1, 1, 1, 7), (1, 1, 1, 1, 1, 0, 5), (1, 1, 1, 1, 1, 1, 0)):
             L.drl_debug_set(1, flags[0])
             L.drl_debug_set(2, flags[1])
             L.drl_debug_set(3, flags[2])
             L.drl_debug_set(4, flags[3])      # conv1 weight gradient on the space-to-depth block image
             L.drl_debug_set(5, flags[4])      # conv1 forward on the space-to-depth block image
             L.drl_debug_set(6, flags[5])      # fc GEMMs on CTA pairs (cta_group::2): 0 none, 1 forward, 2 forward + data gradient
+            L.drl_debug_set(7, flags[6])      # conv kernels on CTA pairs: bit 0 conv2 forward, bit 1 conv3 dgrad, bit 2 conv2 dgrad
             eng, _ = _build('bf16', A, rk, n_envs * B)
             eng.ppo_step(d['observations'], rows, batch, hyper)
             gv = eng.named_views(eng.grads)
@@ -478,6 +482,7 @@ def test_alternative_bf16_engines_stay_in_parity():
         L.drl_debug_set(4, 1)
         L.drl_debug_set(5, 1)
         L.drl_debug_set(6, 1)
+        L.drl_debug_set(7, PAIR_DEFAULT)
 
 
 # ---- reward normaliser -------------------------------------------------------------------
