@@ -303,4 +303,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 }  // namespace umma
+// 16-byte vector reduction (SASS RED.E.ADD.F32x4...): one L2 atomic operation for four consecutive floats
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace drl

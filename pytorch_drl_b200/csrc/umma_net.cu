@@ -33,7 +33,12 @@ struct Bf16Engine {
   uint32_t* bits[3] = {nullptr, nullptr, nullptr};   // ReLU masks of act1/act2/act3, 1 bit per element
   float* b1eff = nullptr; // conv1 effective bias (last block of pack_all_kernel)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
+  // weight-gradient scratch in GEMM order [kp = (ky, kx, ci)][co]: fc 3136 x 512, conv3 640 x 64, conv2 512 x 64.
+  // All-zero between steps: wgrad_untranspose_kernel moves a layer's sums to the OIHW gradient and clears them.
+  float* gt = nullptr;
 };
+constexpr int64_t kGtFc = 0, kGtConv3 = (int64_t)3136 * 512, kGtConv2 = kGtConv3 + 640 * 64, kGtTotal = kGtConv2 + 512 * 64;
+
 
 // ---- packing -----------------------------------------------------------------------------------------
 enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_CONV1_S2D = 5 };
@@ -222,6 +227,8 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&e->w3d, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->b1eff, 32 * sizeof(float)));
+  DRL_CUDA(cudaMalloc(&e->gt, kGtTotal * sizeof(float)));
+  DRL_CUDA(cudaMemset(e->gt, 0, kGtTotal * sizeof(float)));
   DRL_CUDA(cudaMalloc(&e->bits[0], nb * 12800 / 8));
   DRL_CUDA(cudaMalloc(&e->bits[1], nb * 5184 / 8));
   DRL_CUDA(cudaMalloc(&e->bits[2], nb * 3136 / 8));
@@ -231,7 +238,7 @@ int bf16_alloc(drl_net* n) {
 void bf16_free(drl_net* n) {
   Bf16Engine* e = n->bf16;
   if (!e) return;
-  cudaFree(e->w1f); cudaFree(e->w1s); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
+  cudaFree(e->w1f); cudaFree(e->w1s); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff); cudaFree(e->gt); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
   delete e;
   n->bf16 = nullptr;
 }
@@ -334,12 +341,17 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [0] descriptor base-offset field for shifted operands: MEASURED on B200 (scripts/try_base_offset.py): the
 //     128B swizzle is applied to the absolute smem address bits, so shifted starts need base offset 0.
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
-// [2] TMA + shifted-descriptor conv weight-gradient kernels (1) or cp.async wgrad kernels (0)
+// [2] conv weight-gradient kernels: 0 cp.async kernels, 1 TMA + shifted descriptors with one scattered atomic per
+//     element, 2 (default) the same with 16-byte reductions into the [kp][co] scratch + wgrad_untranspose_kernel
+//     (the fc weight gradient follows the same switch)
 // [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
 // [4] conv1 weight gradient on the space-to-depth block image (1) or the im2col kernel (0)
 // [5] conv1 forward on the space-to-depth block image (1), else the kernel flag [3] selects
 // [6] fc GEMMs on CTA pairs (cta_group::2, 256 x 256 tiles): 0 none, 1 forward only (default), 2 forward + data gradient
-int g_debug_flags[8] = {0, 1, 1, 1, 1, 1, 1, 0};
+// [7] descriptor-shifted conv kernels on CTA pairs (umma_tma_conv2.cuh), bit mask: 1 conv2 forward, 2 conv3 data
+//     gradient, 4 conv2 data gradient.  Measured at 32 768 samples: conv2 fwd 0.255 -> 0.251 ms, conv3 dgrad 0.251 ->
+//     0.232 ms, conv2 dgrad 0.253 -> 0.340 ms (it is HBM / epilogue bound: the pair only couples two epilogues) => 3.
+int g_debug_flags[8] = {0, 1, 2, 1, 1, 1, 1, 3};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -427,6 +439,57 @@ static TmaConvArgs tma_conv_args(int KB, int KBX, int RW, int SHIFT_RW, int pad,
   a.out = out; a.bias = bias; a.scale = 1.f; a.mask_src = reinterpret_cast<const __nv_bfloat16*>(mask);
   a.out_sample_pitch = sample_pitch; a.out_row_pitch = row_pitch; a.out_C = out_C; a.osy = os; a.osx = os; a.classes = classes;
   return a;
+}
+
+// The weight-gradient kernels hold dW^T rows kp = (ky, kx, ci) with the output channels along the accumulator
+// columns, the gradient buffer is OIHW (co slowest, (ci, ky, kx) contiguous): flushing the accumulators straight into
+// it is one scattered 4-byte atomic per element from every CTA (measured: ~40 us of a 0.19 ms kernel).  Instead the
+// CTAs reduce 16 bytes at a time into the [kp][co] scratch (full sectors), and this kernel moves the finished sums of one
+// layer into the gradient buffer — both sides coalesced through a shared-memory tile — and clears the scratch.
+//   grid (Cout / 32, Cin / CI_T), 256 threads; tile = rows {t * Cin + ci0 + cl} x 32 output channels.
+template <int CI_T>
+__global__ void __launch_bounds__(256) wgrad_untranspose_kernel(float* __restrict__ gt, float* __restrict__ g, int Cin, int khw,
+                                                                int Cout) {
+  extern __shared__ float tile[];                       // [32][CI_T * khw + 1]
+  const int E = CI_T * khw, ES = E + 1;
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * CI_T;
+  constexpr int U = 8;                                  // loads in flight per thread (the kernel is latency bound)
+  for (int base = threadIdx.x; base < E * 32; base += blockDim.x * U) {
+    float v[U];
+    float* src[U];
+    int dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * (int)blockDim.x;
+      const int row = idx >> 5, c = idx & 31;           // row = t * CI_T + cl
+      const int t = row / CI_T, cl = row - t * CI_T;
+      src[u] = gt + (int64_t)(t * Cin + ci0 + cl) * Cout + co0 + c;
+      dst[u] = c * ES + cl * khw + t;
+      v[u] = idx < E * 32 ? *src[u] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * (int)blockDim.x < E * 32) {
+        *src[u] = 0.f;
+        tile[dst[u]] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < E * 32; idx += blockDim.x) {
+    const int c = idx / E, e = idx - c * E;
+    g[((int64_t)(co0 + c) * Cin + ci0) * khw + e] += tile[c * ES + e];     // += like the atomics it replaces
+  }
+}
+
+// adds one layer's sums from the scratch to its OIHW gradient and leaves the scratch zero
+static int wgrad_untranspose(const char* site, float* gt, float* g, int Cin, int khw, int Cout, cudaStream_t st) {
+  ProfileScope prof(site, st);
+  constexpr int CI_T = 2;
+  const int smem = 32 * (CI_T * khw + 1) * (int)sizeof(float);
+  wgrad_untranspose_kernel<CI_T><<<dim3(Cout / 32, Cin / CI_T), 256, smem, st>>>(gt, g, Cin, khw, Cout);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
 }
 
 template <int NT, int MB, int NR, int KSTEPS>
@@ -585,6 +648,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     DRL_TRY(make_tmap_bf16(&td, n->dpre, (uint64_t)nb, 512, 32));
     WgradTmaArgs w{};
     w.M = nb; w.n_tiles = 2; w.kp_valid = 3136; w.gw = g + o[6]; w.Cin = 64; w.KH = 7; w.KW = 7;
+    w.gt = g_debug_flags[2] == 2 ? e->gt + kGtFc : nullptr; w.gt_ld = 512;
     auto kern = wgrad_tma_kernel<256, 1>;
     static bool configured = false;
     if (!configured) {
@@ -597,6 +661,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     kern<<<dim3(gx, 50), 192, Cf::kSmem, st>>>(tp, td, w);
     DRL_LAUNCH_CHECK();
   }
+  if (g_debug_flags[2] == 2) DRL_TRY(wgrad_untranspose("fc_wgrad_t", e->gt + kGtFc, g + o[6], 64, 49, 512, st));
   // fc weights, fc bias and the heads (everything from the fc weight on = 95 % of the gradient) are final: start
   // their all-reduce on the side stream while the convolution gradients are computed
   if (n->comm && comm_world(n->comm) > 1) DRL_TRY(comm_allreduce_after(n->comm, g, o[6], n->nparams, st));
@@ -618,7 +683,9 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     for (int mb = 0; mb < 5; ++mb) { w.a_off[mb] = sh[2 * mb] * 128; w.a_lbo[mb] = (sh[2 * mb + 1] - sh[2 * mb]) * 128; }
     w.p_plane_bytes = 11264;                         // 88 rows >= 63 + 21 + 1
     w.gw = g + o[4]; w.Cin = 64; w.KH = 3; w.KW = 3; w.kp_valid = 576;
+    w.gt = g_debug_flags[2] == 2 ? e->gt + kGtConv3 : nullptr;
     DRL_TRY((launch_wgrad_conv<64, 5, 4, 4>("conv3_wgrad", n->act[1], 9, 9, 9, 9, n->dact[2], 7, 7, 9, 8, nb, w, st)));
+    if (w.gt) DRL_TRY(wgrad_untranspose("conv3_wgrad_t", w.gt, g + o[4], 64, 9, 64, st));
   } else {
     DRL_TRY((launch_wgrad<64, SRC_BF16, 5>("conv3_wgrad", w3, splits(nb * 49, 1), 1, st)));
   }
@@ -649,7 +716,9 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     w.p_plane_bytes = 14336;                         // 112 rows >= 95 + 11 + 1
     for (int ky = 0; ky < 4; ++ky) { w.a_off[ky] = (ky & 1) * w.p_plane_bytes + (ky >> 1) * 10 * 128; w.a_lbo[ky] = 128; }
     w.gw = g + o[2]; w.Cin = 32; w.KH = 4; w.KW = 4; w.kp_valid = 512;
+    w.gt = g_debug_flags[2] == 2 ? e->gt + kGtConv2 : nullptr;
     DRL_TRY((launch_wgrad_conv<64, 4, 4, 6>("conv2_wgrad", n->act[0], 20, 10, 10, 20, n->dact[1], 9, 9, 10, 10, nb, w, st)));
+    if (w.gt) DRL_TRY(wgrad_untranspose("conv2_wgrad_t", w.gt, g + o[2], 32, 16, 64, st));
   } else {
     DRL_TRY((launch_wgrad<64, SRC_BF16, 4>("conv2_wgrad", w2, splits(nb * 81, 1), 1, st)));
   }

@@ -305,6 +305,7 @@ struct WgradConvArgs {
   int p_planes, p_pad, p_box_bytes, p_plane_bytes, p_buf_bytes;
   int dy_box_bytes, dy_buf_bytes;
   float* gw; int Cin, KH, KW, kp_valid;
+  float* gt;                // when set: partial sums go to the [kp][NT] scratch with 16-byte reductions (see wgrad_untranspose_kernel)
 };
 
 template <int NT, int MB, int NR, int KSTEPS>
@@ -408,7 +409,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_conv_tma_kernel(const __grid_con
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * NT + ch * 32, r);
           tmem_ld_wait();
-          if (ok) {
+          if (ok && args.gt) {
+            float* t = args.gt + (int64_t)kp * NT + ch * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              red_add_v4(t + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                         __uint_as_float(r[4 * q + 3]));
+          } else if (ok) {
 #pragma unroll
             for (int jn = 0; jn < 32; ++jn) atomicAdd(g0 + (int64_t)(ch * 32 + jn) * args.Cin * khw, __uint_as_float(r[jn]));
           }

@@ -236,6 +236,7 @@ struct WgradTmaArgs {
   int kp_valid;          // valid accumulator rows (3136)
   float* gw;             // OIHW fp32 gradient, kp = (ky, kx, ci)
   int Cin, KH, KW;
+  float* gt; int gt_ld;  // when set: partial sums go to the [kp][gt_ld] scratch with 16-byte reductions
 };
 
 template <int NT, int MB>
@@ -346,7 +347,13 @@ __global__ void __launch_bounds__(192, 2) wgrad_tma_kernel(const __grid_constant
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * NT + ch * 32, r);
           tmem_ld_wait();
-          if (ok) {
+          if (ok && args.gt) {
+            float* t = args.gt + (int64_t)kp * args.gt_ld + n0 + ch * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              red_add_v4(t + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                         __uint_as_float(r[4 * q + 3]));
+          } else if (ok) {
 #pragma unroll
             for (int jn = 0; jn < 32; ++jn)
               atomicAdd(g0 + (int64_t)(n0 + ch * 32 + jn) * args.Cin * khw, __uint_as_float(r[jn]));
