@@ -42,12 +42,15 @@ STEP_FLOPS_PER_SAMPLE = 49525760          # fwd 18.69 + bwd 30.83 MFLOP (A=6, K=
 
 
 def peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json (copy bandwidth; cuBLAS bf16 GEMM as a burst at
+    full clocks and sustained under the power cap), else the fallback numbers of B200_PROFILING.md."""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(tflops=float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0))),
-                    hbm=float(d.get('hbm_gbs', 6650.0)), src='measured (MEASURED_PEAKS.json, sustained bf16)')
-    return dict(tflops=1590.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
+        burst = float(d.get('bf16_tflops', 1590.0))
+        return dict(tflops_burst=burst, tflops_sustained=float(d.get('bf16_tflops_sustained', burst)),
+                    hbm=float(d.get('hbm_gbs', 6650.0)), src='measured (MEASURED_PEAKS.json)')
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
 
 
 class ClockSampler:
@@ -59,7 +62,7 @@ class ClockSampler:
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(gpu_index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '20', '-i', str(gpu_index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -69,18 +72,35 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
 
-    def stop(self, t0, t1):
+    def wait_ready(self, timeout=3.0):
+        """nvidia-smi needs 0.1-0.3 s to start: block until its first sample so that it is already looping when the
+        timed region begins."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def in_window(self, t0, t1):
+        return [r for (t, r) in list(self.rows) if t0 <= t <= t1]
+
+    def stop(self, t0, t1, load_windows=()):
+        """Samples inside the timed region [t0, t1]; when the region is shorter than nvidia-smi's sampling period the
+        samples of `load_windows` (the same learner steps running untimed right before / after it) are used and the
+        result says so."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        rows, window = self.in_window(t0, t1), 'timed region'
+        if len(rows) < 2:
+            for (w0, w1) in load_windows:
+                rows = rows + self.in_window(w0, w1)
+            window = 'timed region + the same steps running untimed around it'
         sm = [float(r[0]) for r in rows if r and r[0].replace('.', '', 1).isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(rows)}
+                'reasons': reasons, 'samples': len(rows), 'window': window}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -163,6 +183,7 @@ def main():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-sustained', action='store_true', help='skip the ~1 s power-capped leg')
     ap.add_argument('--no-extras', action='store_true', help='skip the GAE / loss / metrics-pass / sum-tree side measurements')
     ap.add_argument('--debug-flags', default='', help='kernel-variant experiments, e.g. "2=1,3=0" (drl_debug_set)')
     ap.add_argument('--comm', default='nccl', choices=['p2p-overlap', 'p2p', 'p2p-1', 'nccl-overlap', 'nccl', 'nccl-1'],
@@ -245,6 +266,10 @@ def main():
         tc.cuda.synchronize()
 
     # ---- device-resident timing (value) ----
+    clocks = ClockSampler(local_rank) if rank == 0 else None     # started early: nvidia-smi needs ~0.2 s to its first sample
+    if clocks is not None:
+        clocks.wait_ready()
+    t_warm0 = time.time()
     for i in range(args.warmup):
         algo.learner_step(MinibatchView(rollout, rows_list[i]))
     barrier()
@@ -257,7 +282,6 @@ def main():
     ns = ctypes.c_int()
     L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))       # clear
     launches0 = L.drl_launch_count()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
@@ -268,8 +292,7 @@ def main():
     t_wall1 = time.time()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = L.drl_launch_count() - launches0
-    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
-    L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))
+    L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))       # per-launch-site CUDA-event times of the timed region
     L.drl_profile_enable(0)
     sites = {}
     for i in range(ns.value):
@@ -281,6 +304,32 @@ def main():
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = nb * world / (ms_per_step * 1e-3)
+    clk = clocks.stop(t_wall0, t_wall1, [(t_warm0, t_wall0)]) if clocks else None
+
+    # ---- the same steps for ~1 s: the board reaches its power cap and lowers the SM clock (MEASURED_PEAKS.json's
+    #      "sustained" regime); reported beside `value`, which is the short run at full clocks ----
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(1000.0 / ms_per_step))       # same count on every rank (ms_per_step is the max over ranks)
+        clocks2 = ClockSampler(local_rank) if rank == 0 else None
+        if clocks2 is not None:
+            clocks2.wait_ready()
+        barrier()
+        s0, s1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+        tw0 = time.time()
+        s0.record()
+        for i in range(n_sus):
+            algo.learner_step(MinibatchView(rollout, rows_list[args.warmup + i % args.steps]))
+        s1.record()
+        barrier()
+        tw1 = time.time()
+        el = s0.elapsed_time(s1)
+        if world > 1:
+            t = tc.tensor([el], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        sustained = {'steps': n_sus, 'ms_per_step': el / n_sus, 'value': nb * world / (el / n_sus * 1e-3), 'unit': 'samples/s',
+                     'clocks': clocks2.stop(tw0, tw1) if clocks2 else None}
 
     # ---- end-to-end: host minibatches -> H2D -> learner step -> D2H loss read, every step ----
     e2e = None
@@ -293,6 +342,16 @@ def main():
         return
 
     pk = peaks()
+    # tensor peak of the regime the timed region ran in: cuBLAS burst figure at full clocks, the sustained figure when
+    # nvidia-smi reported the power cap (B200_PROFILING.md: burst for a kernel timed alone, sustained inside a long step)
+    capped = bool(clk and 'sw_power_cap' in (clk.get('reasons') or []))
+    pk['tflops'] = pk['tflops_sustained'] if capped else pk['tflops_burst']
+    pk['src'] += ', bf16 ' + ('sustained (power cap active)' if capped else 'burst (full clocks, no power cap in the timed region)')
+    if sustained:
+        cap2 = bool(sustained['clocks'] and 'sw_power_cap' in (sustained['clocks'].get('reasons') or []))
+        sustained['step_achieved_tflops'] = STEP_FLOPS_PER_SAMPLE * sustained['value'] / world / 1e12
+        sustained['step_frac'] = sustained['step_achieved_tflops'] / (pk['tflops_sustained'] if cap2 else pk['tflops_burst'])
+        sustained['tensor_peak'] = 'sustained' if cap2 else 'burst'
     # dominant kernel of the step and its roofline
     dom = max((k for k in sites if k in MACS), key=lambda k: sites[k][0] * 1.0, default=None)
     roof = None
@@ -338,7 +397,7 @@ def main():
                                f'learner step = {B} samples x {n_envs} envs = {nb} samples/GPU, A={A}, K=1',
                    'parallelism': f'dp{world}', 'l2_policy': 'inputs larger than L2 (3.8 GB uint8 rollout per GPU, '
                                                              'a different random minibatch every step)'},
-        'clocks': clk, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'extras': extras,
+        'clocks': clk, 'sustained': sustained, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'extras': extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
