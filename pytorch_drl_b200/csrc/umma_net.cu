@@ -476,9 +476,19 @@ __global__ void __launch_bounds__(256) wgrad_untranspose_kernel(float* __restric
     }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < E * 32; idx += blockDim.x) {
-    const int c = idx / E, e = idx - c * E;
-    g[((int64_t)(co0 + c) * Cin + ci0) * khw + e] += tile[c * ES + e];     // += like the atomics it replaces
+  for (int base = threadIdx.x; base < E * 32; base += blockDim.x * U) {
+    float v[U];
+    float* dstp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * (int)blockDim.x;
+      const int c = idx / E, e = idx - c * E;
+      dstp[u] = g + ((int64_t)(co0 + c) * Cin + ci0) * khw + e;
+      v[u] = idx < E * 32 ? *dstp[u] + tile[c * ES + e] : 0.f;     // += like the atomics it replaces
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (base + u * (int)blockDim.x < E * 32) *dstp[u] = v[u];
   }
 }
 

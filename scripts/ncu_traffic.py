@@ -1,6 +1,6 @@
 """profiles/r01_step_ncu_full_summary.json (scripts/ncu_summarize.py of an `ncu --set full` capture of
 scripts/one_step.py) -> profiles/r01_kernel_traffic.json: DRAM bytes and pipe utilisation per launch site of ONE learner
-step, keyed like bench.py's per_kernel_ms.  The last len(SITES) launches of the capture are one whole step.
+step, keyed like bench.py's per_kernel_ms.  The last complete run of len(SITES) launches starting at the pack kernel is one whole step.
 
 Usage: python scripts/ncu_traffic.py profiles/r01_step_ncu_full_summary.json profiles/r01_kernel_traffic.json [samples]"""
 import json
@@ -20,7 +20,9 @@ P = 'avg.pct_of_peak_sustained_'
 def main():
     rows = json.load(open(sys.argv[1]))
     samples = int(sys.argv[3]) if len(sys.argv) > 3 else 32768
-    rows = [r for r in rows if 'memset' not in r['kernel'].lower()][-len(SITES):]
+    rows = [r for r in rows if 'memset' not in r['kernel'].lower()]
+    starts = [i for i, r in enumerate(rows) if SITES[0][1] in r['kernel'] and i + len(SITES) <= len(rows)]
+    rows = rows[starts[-1]:starts[-1] + len(SITES)]          # the last COMPLETE step of the capture
     out = {'samples_per_launch': samples,
            'source': 'ncu --set full --clock-control none, scripts/one_step.py 2 bf16 (last captured step), B200', 'kernels': {}}
     for (site, pat), r in zip(SITES, rows):
