@@ -207,6 +207,23 @@ int drl_bellman_backups_f32(const float* rewards, const float* qpreds, const flo
                             int64_t ld_out, float gamma, int use_dones, int double_q, float* out, void* stream);
 
 /* =============================================================================================
+ * DQN head blocks — replace DuelingArchitecture.forward behind SimpleDiscreteActionValueHead.forward
+ * (drl/agents/architectures/stateless/dueling.py:50-57, drl/agents/heads/action_value_heads.py:124-140) and the
+ * arithmetic of EpsilonGreedyCategoricalPolicyHead.forward (drl/agents/heads/policy_heads.py:219-224).
+ * ============================================================================================= */
+/* q[nb, A] = (adv - mean(adv)) + val from features [nb, in_dim]; weights in torch nn.Linear layout ([out, in]):
+ * w0 [50, in_dim], wa1 / wv1 [25, 50], wa2 [A, 25], wv2 [1, 25]; both streams end in a ReLU like the reference's MLP
+ * (mlp.py:32-41).  widening must be 1, in_dim <= 512, A <= DRL_MAX_ACTIONS.  Forward only. */
+int drl_dueling_forward_f32(const float* feat, int nb, int in_dim, int num_actions, int widening, const float* w0,
+                            const float* b0, const float* wa1, const float* ba1, const float* wa2, const float* ba2,
+                            const float* wv1, const float* bv1, const float* wv2, const float* bv2, float* q_out,
+                            void* stream);
+/* probs[nb, A] = (1 - eps) * one_hot(argmax_a q) + eps / A (first maximum on ties, like torch.argmax), bit-identical
+ * to the reference's float32 expression; greedy_out (nullable) receives the argmax.  eps outside [0, 1] is refused. */
+int drl_epsilon_greedy_probs_f32(const float* q, int nb, int num_actions, double epsilon, float* probs_out,
+                                 int64_t* greedy_out, void* stream);
+
+/* =============================================================================================
  * Reward normaliser — replaces ReturnAcc and the per-step part of NormalizeRewardWrapper.step
  * (drl/envs/wrappers/stateful/normalize_reward.py:20-100, 171-194) for n_envs environments at once.
  * ============================================================================================= */

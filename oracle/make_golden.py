@@ -16,6 +16,9 @@ What is pinned (all from reference code, never from the oracle):
                  drl/algos/common/credit_assignment.py:225-249, 276-305
   reward_norm.npz ReturnAcc.update/forward (the reward normaliser's accumulator)
                  drl/envs/wrappers/stateful/normalize_reward.py:20-100
+  dueling.npz    DuelingArchitecture.forward through SimpleDiscreteActionValueHead, and the probabilities of
+                 EpsilonGreedyCategoricalPolicyHead  (dueling.py:50-57, action_value_heads.py:124-140,
+                 policy_heads.py:197-226)
 Large tensors are stored as (sum, l2, strided sample) summaries to keep fixtures small.
 """
 import os
@@ -386,6 +389,33 @@ def gen_reward_norm():
     np.savez_compressed(os.path.join(GOLD, 'reward_norm.npz'), **out)
 
 
+def gen_dueling():
+    from drl.agents.architectures.stateless.dueling import DuelingArchitecture
+    from drl.agents.heads.action_value_heads import SimpleDiscreteActionValueHead
+    from drl.agents.heads.policy_heads import EpsilonGreedyCategoricalPolicyHead
+    out = {}
+    cases = [(6, 16, 0.1, 'orth'), (18, 33, 0.05, 'orth'), (4, 8, 1.0, 'orth'), (18, 4, 0.0, 'zeros')]
+    for i, (A, nb, eps, init) in enumerate(cases):
+        tc.manual_seed(100 + i)
+        w_init = (lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5)) if init == 'orth' else tc.nn.init.zeros_
+        b_init = (lambda b: tc.nn.init.normal_(b, std=0.1)) if init == 'orth' else tc.nn.init.zeros_
+        head = SimpleDiscreteActionValueHead(num_features=512, num_actions=A, head_architecture_cls=DuelingArchitecture,
+                                             head_architecture_cls_args={'widening': 1}, w_init=w_init, b_init=b_init)
+        feats = tc.relu(tc.randn(nb, 512))
+        with tc.no_grad():
+            q = head(feats)
+            pol = EpsilonGreedyCategoricalPolicyHead(action_value_head=head)
+            pol.epsilon = eps
+            dist = pol(feats)
+        sd = head._action_value_head.state_dict()
+        for k, v in sd.items():
+            out[f'c{i}_p_{k}'] = v.numpy()
+        out.update({f'c{i}_meta': np.array([A, nb, eps]), f'c{i}_feat': feats.numpy(), f'c{i}_q': q.numpy(),
+                    f'c{i}_probs': dist.probs.numpy()})
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'dueling.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_loader.load()
@@ -397,6 +427,7 @@ def main():
     gen_rnd()
     gen_reward_norm()
     gen_nstep_bellman()
+    gen_dueling()
     gen_ppo('ppo_2rank', ['extrinsic'], {'extrinsic': 1.0}, False, 29611)
     gen_ppo('ppo_2rank_rnd', ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
             True, 29612)

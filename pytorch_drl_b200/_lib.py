@@ -88,6 +88,8 @@ PROTOTYPES = {
                                          c_float, c_int, c_void_p, c_void_p]),
     'drl_bellman_backups_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64,
                                         c_int64, c_int64, c_float, c_int, c_int, c_void_p, c_void_p]),
+    'drl_dueling_forward_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 10 + [c_void_p, c_void_p]),
+    'drl_epsilon_greedy_probs_f32': (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     'drl_return_acc_update_f32': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'drl_reward_norm_apply_f32': (c_int, [c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),

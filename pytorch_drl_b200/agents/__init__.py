@@ -6,6 +6,8 @@ from typing import Any, Callable, List, Mapping, Optional, Type
 import torch as tc
 
 from ..engine import LearnerEngine
+from .dqn_heads import (MLP, DuelingArchitecture, EpsilonGreedyCategoricalPolicyHead,  # noqa: F401
+                        SimpleDiscreteActionValueHead)
 
 
 class ToChannelMajor(tc.nn.Module):

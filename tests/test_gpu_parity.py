@@ -813,3 +813,48 @@ def test_ppo_credit_assignment_with_extra_steps(op_name):
             adv = co.nstep_advantages(T, extra, rew[e], v[e, :T + n], don[e], 0.99, True)
         np.testing.assert_allclose(rollout['vtargs']['extrinsic'][e, :T].cpu().numpy(), adv + v[e, :T], rtol=2e-5, atol=2e-6)
         np.testing.assert_allclose(rollout['advantages']['extrinsic'][e, :T].cpu().numpy(), po.standardize(adv), rtol=2e-4, atol=2e-5)
+
+
+# ---- DQN head blocks ---------------------------------------------------------------------
+def test_dueling_head_and_epsilon_greedy_vs_reference_golden(golden_dir):
+    """The drop-in modules load the reference's state_dict unchanged; Q-values match the reference to float32
+    rounding, the epsilon-greedy probabilities bit for bit against the oracle's float32 expression."""
+    from oracle import dueling_oracle as do
+    from pytorch_drl_b200 import _lib, agents
+    from pytorch_drl_b200._lib import current_stream, ptr
+    g = np.load(os.path.join(golden_dir, 'dueling.npz'))
+    for i in range(int(g['ncases'])):
+        A, nb, eps = int(g[f'c{i}_meta'][0]), int(g[f'c{i}_meta'][1]), float(g[f'c{i}_meta'][2])
+        head = agents.SimpleDiscreteActionValueHead(num_features=512, num_actions=A, head_architecture_cls=agents.DuelingArchitecture,
+                                                    head_architecture_cls_args={'widening': 1})
+        head._action_value_head.load_state_dict({k: tc.from_numpy(g[f'c{i}_p_{k}']) for k in do.PARAM_KEYS}, strict=True)
+        head.to(dev())
+        feats = cu(g[f'c{i}_feat'])
+        q = head(feats)
+        np.testing.assert_allclose(q.cpu().numpy(), g[f'c{i}_q'], rtol=1e-5, atol=2e-6)
+        pol = agents.EpsilonGreedyCategoricalPolicyHead(action_value_head=head)
+        pol.epsilon = eps
+        dist = pol(feats)
+        np.testing.assert_allclose(dist.probs.cpu().numpy(), g[f'c{i}_probs'], rtol=0, atol=1.2e-7)
+        # raw kernel on the REFERENCE's q: bit-identical to the float32 expression, argmax = first maximum
+        qref = cu(g[f'c{i}_q'])
+        probs, greedy = tc.empty_like(qref), tc.empty(nb, dtype=tc.int64, device=dev())
+        assert _lib.lib().drl_epsilon_greedy_probs_f32(ptr(qref), nb, A, eps, ptr(probs), ptr(greedy), current_stream()) == 0
+        np.testing.assert_array_equal(probs.cpu().numpy(), do.epsilon_greedy_probs(g[f'c{i}_q'], eps))
+        np.testing.assert_array_equal(greedy.cpu().numpy(), np.argmax(g[f'c{i}_q'], axis=-1))
+    # ties, larger batch than CTAs x warps, error behaviour
+    qt = cu(np.array([[1., 3., 3., 0.], [2., 2., 2., 2.]], np.float32))
+    probs, greedy = tc.empty_like(qt), tc.empty(2, dtype=tc.int64, device=dev())
+    assert _lib.lib().drl_epsilon_greedy_probs_f32(ptr(qt), 2, 4, 0.2, ptr(probs), ptr(greedy), current_stream()) == 0
+    assert greedy.cpu().tolist() == [1, 0]
+    assert _lib.lib().drl_epsilon_greedy_probs_f32(ptr(qt), 2, 4, 1.5, ptr(probs), ptr(greedy), current_stream()) != 0
+    big = tc.relu(tc.randn(5000, 512, device=dev()))
+    params = {k: g[f'c1_p_{k}'] for k in do.PARAM_KEYS}
+    head = agents.SimpleDiscreteActionValueHead(512, 18, agents.DuelingArchitecture, {'widening': 1})
+    head._action_value_head.load_state_dict({k: tc.from_numpy(v) for k, v in params.items()})
+    head.to(dev())
+    np.testing.assert_allclose(head(big).cpu().numpy(), do.dueling_forward(params, big.cpu().numpy()), rtol=1e-5, atol=3e-6)
+    with pytest.raises(RuntimeError):
+        head(tc.zeros(2, 512))                                   # CPU features: no fallback
+    with pytest.raises(NotImplementedError):
+        agents.SimpleDiscreteActionValueHead(512, 6, agents.Linear, {})

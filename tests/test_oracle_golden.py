@@ -243,3 +243,24 @@ def test_gae_extra_steps_oracle_vs_reference_golden(golden_dir):
         T, extra, gam, lam, ud = g[f'c{i}_meta']
         adv = po.gae(int(T), int(extra), g[f'c{i}_r'], g[f'c{i}_v'], g[f'c{i}_d'], float(gam), float(lam), bool(ud))
         np.testing.assert_array_equal(adv, g[f'c{i}_adv'])
+
+
+def test_dueling_and_epsilon_greedy_oracle_vs_reference_golden(golden_dir):
+    """dueling.py:50-57 (through SimpleDiscreteActionValueHead) and policy_heads.py:219-224: the oracle reproduces the
+    reference's Q-values to float32 rounding (matmul order) and its normalised action probabilities."""
+    from oracle import dueling_oracle as do
+    g = np.load(os.path.join(golden_dir, 'dueling.npz'))
+    for i in range(int(g['ncases'])):
+        A, nb, eps = g[f'c{i}_meta']
+        params = {k: g[f'c{i}_p_{k}'] for k in do.PARAM_KEYS}
+        q = do.dueling_forward(params, g[f'c{i}_feat'])
+        assert q.shape == (int(nb), int(A))
+        np.testing.assert_allclose(q, g[f'c{i}_q'], rtol=1e-5, atol=2e-6)
+        pr = do.epsilon_greedy_probs(g[f'c{i}_q'], float(eps))
+        pr = pr / pr.sum(-1, keepdims=True)                       # Categorical(probs=...) normalises
+        np.testing.assert_allclose(pr, g[f'c{i}_probs'], rtol=0, atol=1.2e-7)
+    # the reference's own test: all-zero weights give all-zero Q (test_dueling.py:7-21) = golden case 3
+    assert not g['c3_q'].any()
+    # ties: the first maximum is the greedy action (torch.argmax)
+    pr = do.epsilon_greedy_probs(np.array([[1., 3., 3., 0.]], np.float32), 0.2)
+    np.testing.assert_allclose(pr, [[0.05, 0.85, 0.05, 0.05]], rtol=1e-6)
