@@ -340,6 +340,8 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 
 // [0] descriptor base-offset field for shifted operands: MEASURED on B200 (scripts/try_base_offset.py): the
 //     128B swizzle is applied to the absolute smem address bits, so shifted starts need base offset 0.
+//     [0] = 2: staging buffers of the TMA conv kernels packed at 128-byte instead of 1024-byte granularity (experiment
+//     behind tma_conv2s_kernel: the TMA unit swizzles by absolute address bits too, scripts/try_unaligned_tma.py).
 // [1] TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
 // [2] conv weight-gradient kernels: 0 cp.async kernels, 1 TMA + shifted descriptors with one scattered atomic per
 //     element, 2 (default) the same with 16-byte reductions into the [kp][co] scratch + wgrad_untranspose_kernel
@@ -351,7 +353,9 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [7] descriptor-shifted conv kernels on CTA pairs (umma_tma_conv2.cuh), bit mask: 1 conv2 forward, 2 conv3 data
 //     gradient, 4 conv2 data gradient.  Measured at 32 768 samples: conv2 fwd 0.255 -> 0.251 ms, conv3 dgrad 0.251 ->
 //     0.232 ms, conv2 dgrad 0.253 -> 0.340 ms (it is HBM / epilogue bound: the pair only couples two epilogues) => 3.
-int g_debug_flags[8] = {0, 1, 2, 1, 1, 1, 1, 3};
+//     bit 8: conv3 data gradient on CTA pairs with accumulator tiles that span samples (tma_conv2s_kernel, groups of 5
+//     samples in 4 tiles): 0.235 -> 0.217 ms => default 11.
+int g_debug_flags[8] = {0, 1, 2, 1, 1, 1, 1, 11};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -392,7 +396,7 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   a.box_bytes = BW * (BH / a.planes) * 128;
   const int tap_rows = (a.KB - 1) / a.KBX;               // last tap row
   const int max_shift = (a.planes == 2 ? tap_rows / 2 : tap_rows) * a.SHIFT_RW + (a.KBX - 1);
-  a.plane_bytes = (a.box_bytes + 1023) / 1024 * 1024;
+  a.plane_bytes = g_debug_flags[0] == 2 ? a.box_bytes : (a.box_bytes + 1023) / 1024 * 1024;   // [0] = 2: experiment, 128-byte aligned TMA destinations
   a.raw_buf_bytes = a.plane_bytes * a.planes;
   const int window = (MROWS + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
   a.slack_bytes = window > a.plane_bytes ? (window - a.plane_bytes + 1023) / 1024 * 1024 : 0;
@@ -427,6 +431,33 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   }
   const int ctas = sm_count();
   kern<<<nb < ctas ? nb : ctas, 32 * (4 * NEPI + 2), smem, st>>>(tm, a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+// CTA pairs + accumulator tiles that span samples (tma_conv2s_kernel): groups of G samples on one row stream
+template <int N, int EPI, int NRG, int NEPI, int KB, int KBX, int SHIFT_RW, int G, int ROWS_PER_SAMPLE, int MT>
+static int launch_tma_conv2s(const char* site, const void* src, int nb, int H, int W, int BW, TmaConvArgs a, cudaStream_t st) {
+  ProfileScope prof(site, st);
+  constexpr int SROWS = ROWS_PER_SAMPLE * SHIFT_RW;
+  constexpr int MAX_SHIFT = ((KB - 1) / KBX) * SHIFT_RW + (KBX - 1);
+  if (BW != SHIFT_RW || a.RW != SHIFT_RW || a.planes != 1 || a.KB != KB || a.KBX != KBX) return DRL_ERR_BAD_ARG;
+  if (a.OH > ROWS_PER_SAMPLE || a.bias_grad && a.bias_mod != (N == 64 ? 64 : 32)) return DRL_ERR_BAD_ARG;
+  CUtensorMap tm;
+  DRL_TRY(make_tmap_act4d(&tm, src, (uint64_t)nb, (uint64_t)H, (uint64_t)W, (uint32_t)BW, (uint32_t)ROWS_PER_SAMPLE));
+  a.nb = nb;
+  a.box_bytes = SROWS * 128;
+  auto kern = tma_conv2s_kernel<N, EPI, NRG, NEPI, KB, KBX, SHIFT_RW, G, SROWS, MT>;
+  constexpr int smem = tma_conv2s_smem<N, NRG, KB, G, SROWS, MT, MAX_SHIFT>();
+  static_assert(smem <= 227 * 1024, "shared memory plan too large");
+  static bool configured = false;
+  if (!configured) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int total_pg = ((nb + G - 1) / G + 1) / 2;
+  const int pairs = total_pg < sm_count() / 2 ? total_pg : sm_count() / 2;
+  kern<<<2 * pairs, 32 * (4 * NEPI + 2), smem, st>>>(tm, a);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -711,7 +742,10 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(9, 3, 11, 11, 2, 1, 9, 9, e->w3d, n->dact[1], nullptr, n->act[1], 5184, 9 * 64, 64, 1, 0);
       c.bias_grad = g + o[3]; c.bias_mod = 64;       // conv2 bias gradient
       c.bits_in = e->bits[1];
-      DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2, 128, 9, 3, 11, 1>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st, 2)));
+      if (g_debug_flags[7] & 8)   // groups of 5 samples on one row stream: 4 accumulator tiles instead of 5
+        DRL_TRY((launch_tma_conv2s<64, EPI_MASK_BF16, 2, 2, 9, 3, 11, 5, 9, 4>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, c, st)));
+      else
+        DRL_TRY((launch_tma_conv<64, EPI_MASK_BF16, 4, 4, 2, 128, 9, 3, 11, 1>("conv3_dgrad", n->dact[2], nb, 7, 7, 11, 11, c, st, 2)));
     } else {
       DRL_TRY((launch_rowgather<64, SRC_BF16, EPI_MASK_BF16>("conv3_dgrad", a, 1, st)));
     }
