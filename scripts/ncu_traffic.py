@@ -11,7 +11,7 @@ SITES = [('pack_weights', 'pack_all_kernel'), ('conv1_fwd', 'conv1_fwd_s2d_kerne
          ('conv3_fwd', 'tma_conv_kernel<64'), ('fc_fwd', 'tma_gemm2_kernel'), ('heads_loss', 'heads_loss_kernel'),
          ('fc_wgrad', 'wgrad_tma_kernel'), ('fc_wgrad_t', 'wgrad_untranspose_kernel'), ('fc_dgrad', 'tma_gemm_kernel<256'),
          ('conv3_wgrad', 'wgrad_conv_tma_kernel<64, 5'), ('conv3_wgrad_t', 'wgrad_untranspose_kernel'),
-         ('conv3_dgrad', 'tma_conv2_kernel<64'), ('conv2_wgrad', 'wgrad_conv_tma_kernel<64, 4'),
+         ('conv3_dgrad', 'tma_conv2s_kernel<64'), ('conv2_wgrad', 'wgrad_conv_tma_kernel<64, 4'),
          ('conv2_wgrad_t', 'wgrad_untranspose_kernel'), ('conv2_dgrad', 'tma_conv_kernel<128'),
          ('conv1_wgrad', 'conv1_wgrad_s2d_kernel'), ('adam', 'adam_kernel')]
 P = 'avg.pct_of_peak_sustained_'
