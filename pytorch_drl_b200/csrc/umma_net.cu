@@ -349,13 +349,14 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 // [3] conv1 forward with its A operand in tensor memory (1) or in swizzled shared memory (0)
 // [4] conv1 weight gradient on the space-to-depth block image (1) or the im2col kernel (0)
 // [5] conv1 forward on the space-to-depth block image (1), else the kernel flag [3] selects
-// [6] fc GEMMs on CTA pairs (cta_group::2, 256 x 256 tiles): 0 none, 1 forward only (default), 2 forward + data gradient
+// [6] fc GEMMs: bits 0-1 CTA pairs (cta_group::2, 256 x 256 tiles): 0 none, 1 forward only (default), 2 forward + data
+//     gradient; bit 2: the single-CTA data gradient with FOUR epilogue warpgroups (0.107 -> 0.102 ms) => default 5
 // [7] descriptor-shifted conv kernels on CTA pairs (umma_tma_conv2.cuh), bit mask: 1 conv2 forward, 2 conv3 data
 //     gradient, 4 conv2 data gradient.  Measured at 32 768 samples: conv2 fwd 0.255 -> 0.251 ms, conv3 dgrad 0.251 ->
 //     0.232 ms, conv2 dgrad 0.253 -> 0.340 ms (it is HBM / epilogue bound: the pair only couples two epilogues) => 3.
 //     bit 8: conv3 data gradient on CTA pairs with accumulator tiles that span samples (tma_conv2s_kernel, groups of 5
 //     samples in 4 tiles): 0.235 -> 0.217 ms => default 11.
-int g_debug_flags[8] = {0, 1, 2, 1, 1, 1, 1, 11};
+int g_debug_flags[8] = {0, 1, 2, 1, 1, 1, 5, 11};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -559,7 +560,7 @@ static int launch_wgrad_conv(const char* site, const void* p_src, int pH, int pW
   return DRL_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NEPI = 2>
 static int launch_tma_gemm(const char* site, const void* a, int M, int K, const void* b, int N_total, const TmaGemmArgs& args,
                            cudaStream_t st) {
   ProfileScope prof(site, st);
@@ -568,7 +569,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
   // CTA pairs: each CTA stages 128 rows of A and 128 columns of B.  Measured: fc forward (49 k-blocks per tile)
   // 0.106 -> 0.098 ms, fc data gradient (8 k-blocks per tile, heavy epilogue) 0.105 -> 0.113 ms => [6] = 1 pairs the
   // forward only, [6] = 2 both.
-  if (BN == 256 && (g_debug_flags[6] == 2 || (g_debug_flags[6] == 1 && EPI == EPI_BIAS_RELU_F32))) {
+  if (BN == 256 && ((g_debug_flags[6] & 3) == 2 || ((g_debug_flags[6] & 3) == 1 && EPI == EPI_BIAS_RELU_F32))) {
     DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, 128));
     if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;
     auto kern2 = tma_gemm2_kernel<EPI>;
@@ -585,7 +586,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
   }
   DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, BN));
   if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
-  auto kern = tma_gemm_kernel<BN, EPI>;
+  auto kern = tma_gemm_kernel<BN, EPI, NEPI>;
   constexpr int smem = TmaGemmCfg<BN>::kSmem;
   static bool configured = false;
   if (!configured) {
@@ -593,7 +594,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
     configured = true;
   }
   const int tiles = ((M + 127) / 128) * ((N_total + BN - 1) / BN);
-  kern<<<tiles < sm_count() ? tiles : sm_count(), kTmaGemmThreads, smem, st>>>(ta, tb, args);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 32 * (4 * NEPI + 2), smem, st>>>(ta, tb, args);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }
@@ -712,7 +713,8 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     a.mask_src = (const __nv_bfloat16*)n->act[2];
     a.bias_grad = g + o[5]; a.bias_mod = 64;          // conv3 bias gradient = column sums of dact3 (column % 64)
     a.bits_in = g_debug_flags[1] ? e->bits[2] : nullptr;   // bits are written by the TMA conv3 forward
-    DRL_TRY((launch_tma_gemm<256, EPI_MASK_BF16>("fc_dgrad", n->dpre, nb, 512, e->wfd, 3136, a, st)));
+    if (g_debug_flags[6] & 4) DRL_TRY((launch_tma_gemm<256, EPI_MASK_BF16, 4>("fc_dgrad", n->dpre, nb, 512, e->wfd, 3136, a, st)));   // 4 epilogue warpgroups
+    else DRL_TRY((launch_tma_gemm<256, EPI_MASK_BF16>("fc_dgrad", n->dpre, nb, 512, e->wfd, 3136, a, st)));
   }
   // ---- conv3 (its bias gradient was accumulated by the fc data-gradient epilogue)
   WgradArgs w3 = wgrad_args(nb, n->act[1], nullptr, 49, 7, 9, 9, 64, 1, 3, 9, n->dact[2], 64, 5, 1, g + o[4], 64, 3, 3);
@@ -780,7 +782,9 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
       TmaConvArgs c = tma_conv_args(4, 2, 11, 11, 1, 1, 10, 10, e->w2d, n->dact[0], nullptr, n->act[0], 12800, 20 * 32, 32, 2, 1);
       c.bias_grad = g + o[1]; c.bias_mod = 32;       // conv1 bias gradient
       c.bits_in = e->bits[0];
-      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 2, 128, 4, 2, 11, 1>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st, 4)));
+      // FOUR epilogue warpgroups: with N = 128 (4 column chunks per row: mask, bf16 pack, 4 x 32 column sums) this layer
+      // was bound by epilogue throughput — 2 / 3 / 4 warpgroups: 0.257 / 0.231 / 0.220 ms (the N = 64 layers do not gain)
+      DRL_TRY((launch_tma_conv<128, EPI_MASK_BF16, 4, 4, 4, 128, 4, 2, 11, 1>("conv2_dgrad", n->dact[1], nb, 9, 9, 11, 11, c, st, 4)));
     } else {
       DRL_TRY((launch_rowgather<128, SRC_BF16, EPI_MASK_BF16>("conv2_dgrad", a, 1, st)));
     }

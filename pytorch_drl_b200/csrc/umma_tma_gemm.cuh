@@ -50,9 +50,11 @@ struct TmaGemmCfg {
 
 // Warps 0-7: two epilogue warpgroups, each drains HALF the columns of every tile (the epilogue of a 128 x 256 tile
 // costs about as much as its 32 MMAs, so one warpgroup was the critical path); warp 8: MMA; warp 9: TMA.
+// NEPI = 4 (data gradient: mask + bf16 pack + column sums per chunk): four warpgroups, chunk ch = wg + 4 * c2, so a
+// thread only ever sees ONE of the two 32-column bias groups (32 running sums instead of 64: fits 112 registers).
 constexpr int kTmaGemmThreads = 320;
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+template <int BN, int EPI, int NEPI = 2>
+__global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                           const __grid_constant__ CUtensorMap tmap_b,
                                                           const TmaGemmArgs args) {
   using namespace umma;
@@ -75,17 +77,19 @@ __global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128 * NEPI); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
-  if (warp == 9 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  constexpr int W_MMA = 4 * NEPI, W_TMA = 4 * NEPI + 1;
+  static_assert(NEPI == 2 || NEPI == 4, "epilogue warpgroups");
+  if (warp == W_MMA) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == W_TMA && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
+  if (warp == W_TMA) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __gr
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
+  } else if (warp == W_MMA) {
     {
       constexpr uint32_t idesc = make_idesc_f16(1u, 128, BN, 0, 0);
       constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
@@ -136,7 +140,8 @@ __global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __gr
     int last_nt = -1;
     // fused bias gradient: per-thread running column sums (bias index = column % 64, two 32-column groups);
     // one cross-lane reduction after the last tile
-    constexpr int BG = 2;
+    constexpr int BG = NEPI == 2 ? 2 : 1;                 // bias groups a thread meets
+    constexpr int CPW = BN / 32 / NEPI;                   // 32-column chunks per warpgroup and tile
     float cs[EPI == EPI_MASK_BF16 ? 32 * BG : 1];
 #pragma unroll
     for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
@@ -146,21 +151,21 @@ __global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __gr
       const int m = mt * 128 + (int)(threadIdx.x & 127);
       const int n0 = nt * BN;
       if (EPI == EPI_BIAS_RELU_F32 && nt != last_nt) {     // (re)load the bias slice of this N tile
-        asm volatile("bar.sync 1, 256;");
-        for (int i = threadIdx.x; i < BN; i += 256) sBias[i] = n0 + i < args.N_total ? args.bias[n0 + i] : 0.f;
-        asm volatile("bar.sync 1, 256;");
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * NEPI));
+        for (int i = threadIdx.x; i < BN; i += 128 * NEPI) sBias[i] = n0 + i < args.N_total ? args.bias[n0 + i] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * NEPI));
         last_nt = nt;
       }
       mbar_wait(tfull + acc, (j >> 1) & 1);
       tc_fence_after();
-      const int wg = warp >> 2;                             // warpgroup 0: columns [0, BN/2), warpgroup 1: the rest
+      const int wg = warp >> 2;                             // NEPI = 2: warpgroup 0 takes columns [0, BN/2), 1 the rest
 #pragma unroll
-      for (int c2 = 0; c2 < BN / 64; ++c2) {
-        const int ch = wg * (BN / 64) + c2;
+      for (int c2 = 0; c2 < CPW; ++c2) {
+        const int ch = NEPI == 2 ? wg * CPW + c2 : wg + NEPI * c2;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * BN + ch * 32, r);
         tmem_ld_wait();
-        if (c2 == BN / 64 - 1) {
+        if (c2 == CPW - 1) {
           tc_fence_before();
           mbar_arrive(tempty + acc);
         }
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __gr
         }
         if (EPI == EPI_MASK_BF16 && m < args.M && n < args.N_total) {   // fused bias gradient of the layer below
 #pragma unroll
-          for (int i = 0; i < 32; ++i) cs[(c2 % BG) * 32 + i] += __uint_as_float(r[i]);   // ch = wg * BN/64 + c2, BN/64 even
+          for (int i = 0; i < 32; ++i) cs[(c2 % BG) * 32 + i] += __uint_as_float(r[i]);   // NEPI = 2: ch = wg * CPW + c2, CPW even; NEPI = 4: ch % 2 = wg % 2
         }
       }
     }
@@ -217,13 +222,13 @@ __global__ void __launch_bounds__(kTmaGemmThreads, 1) tma_gemm_kernel(const __gr
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = cs[g * 32 + i];
-        atomicAdd(args.bias_grad + g * 32 + lane, warp_colsum32(v, lane));
+        atomicAdd(args.bias_grad + (NEPI == 2 ? g : ((warp >> 2) & 1)) * 32 + lane, warp_colsum32(v, lane));
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }

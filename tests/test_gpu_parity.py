@@ -462,13 +462,13 @@ def test_alternative_bf16_engines_stay_in_parity():
                            [d['vtargs']['extrinsic']])
     try:
         # (tma conv fwd/dgrad kernels, tma conv wgrad kernels, conv1 forward A operand in TMEM)
-        for flags in ((0, 0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 0, 2, 0), (1, 2, 1, 1, 1, 1, 7), (1, 1, 1, 1, 1, 0, 5), (1, 2, 1, 1, 1, 1, 0), (1, 2, 1, 1, 1, 1, 11)):
+        for flags in ((0, 0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 0, 2, 0), (1, 2, 1, 1, 1, 1, 7), (1, 1, 1, 1, 1, 0, 5), (1, 2, 1, 1, 1, 5, 0), (1, 2, 1, 1, 1, 1, 11)):
             L.drl_debug_set(1, flags[0])
             L.drl_debug_set(2, flags[1])      # conv / fc weight gradients: 0 cp.async kernels, 1 TMA kernels + scattered atomics, 2 + [kp][co] scratch
             L.drl_debug_set(3, flags[2])
             L.drl_debug_set(4, flags[3])      # conv1 weight gradient on the space-to-depth block image
             L.drl_debug_set(5, flags[4])      # conv1 forward on the space-to-depth block image
-            L.drl_debug_set(6, flags[5])      # fc GEMMs on CTA pairs (cta_group::2): 0 none, 1 forward, 2 forward + data gradient
+            L.drl_debug_set(6, flags[5])      # fc GEMMs: bits 0-1 CTA pairs (0 none, 1 forward, 2 forward + data gradient), bit 2 four epilogue warpgroups in the data gradient
             L.drl_debug_set(7, flags[6])      # conv kernels on CTA pairs: bit 0 conv2 forward, bit 1 conv3 dgrad, bit 2 conv2 dgrad, bit 3 conv3 dgrad with sample-spanning tiles
             eng, _ = _build('bf16', A, rk, n_envs * B)
             eng.ppo_step(d['observations'], rows, batch, hyper)
@@ -481,7 +481,7 @@ def test_alternative_bf16_engines_stay_in_parity():
         L.drl_debug_set(3, 1)
         L.drl_debug_set(4, 1)
         L.drl_debug_set(5, 1)
-        L.drl_debug_set(6, 1)
+        L.drl_debug_set(6, 5)
         L.drl_debug_set(7, PAIR_DEFAULT)
 
 
