@@ -104,7 +104,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_steps: int = 200, steps=None):
+def cpu_reference_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_steps: int = 2000, steps=None):
     """Times the CPU restatement of the reference's learner step (oracle port: torch-CPU fp32 autograd
     through the same conv/linear/Adam ops the reference calls, all host threads) on a bounded sample:
     `n_envs` ranks x B samples per step.  Returns (samples/s, steps, threads)."""
