@@ -111,3 +111,41 @@ def test_credit_op_registry():
     assert isinstance(op, algos.GAE)
     with pytest.raises(ValueError):
         algos.get_credit_assignment_op('Nope', {})     # credit_assignment.py:25
+
+
+def test_dqn_head_dropins_keep_reference_names_and_refuse_cpu(golden_dir):
+    """SimpleDiscreteActionValueHead(DuelingArchitecture) loads the reference's state_dict with strict=True (the golden
+    file holds the reference module's own tensors), mirrors its constructor errors, and never computes on the CPU."""
+    from oracle import dueling_oracle as do
+    g = np.load(os.path.join(golden_dir, 'dueling.npz'))
+    head = agents.SimpleDiscreteActionValueHead(num_features=512, num_actions=6, head_architecture_cls=agents.DuelingArchitecture,
+                                                head_architecture_cls_args={'widening': 1},
+                                                w_init=lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5), b_init=tc.nn.init.zeros_)
+    arch = head._action_value_head
+    assert sorted(arch.state_dict().keys()) == sorted(do.PARAM_KEYS)
+    arch.load_state_dict({k: tc.from_numpy(g[f'c0_p_{k}']) for k in do.PARAM_KEYS}, strict=True)
+    assert arch.input_shape == [512] and arch.output_dim == 6 and head.num_actions == 6 and head.num_features == 512
+    pol = agents.EpsilonGreedyCategoricalPolicyHead(action_value_head=head)
+    with pytest.raises(AssertionError):
+        pol.epsilon = 1.5                                             # policy_heads.py:185-188
+    pol.epsilon = 0.1
+    with pytest.raises(RuntimeError):
+        head(tc.zeros(2, 512))                                        # CPU features: refused, not computed
+    with pytest.raises(ValueError):
+        agents.MLP(4, 4, 4, 1)                                        # mlp.py:30-31
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver times next to ours): one JSON line with the contract's keys, run
+    on the host CPU with every core, without touching CUDA."""
+    import json
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS='1', CUDA_VISIBLE_DEVICES='')       # what torchrun would export
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                                  text=True, env=env, timeout=600)
+    line = json.loads([l for l in out.splitlines() if l.startswith('{')][-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'samples/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['steps'] == 1 and line['n_gpus'] >= 1
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == (os.cpu_count() or 1)
+    assert line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
+    assert 'workload' in line['config']
