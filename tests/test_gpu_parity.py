@@ -858,3 +858,35 @@ def test_dueling_head_and_epsilon_greedy_vs_reference_golden(golden_dir):
         head(tc.zeros(2, 512))                                   # CPU features: no fallback
     with pytest.raises(NotImplementedError):
         agents.SimpleDiscreteActionValueHead(512, 6, agents.Linear, {})
+
+
+# ---- the reference's own known-answer tests for the agent stack, run through the fused path -------------------
+@pytest.mark.parametrize('precision', _precisions())
+def test_reference_known_answers_zero_weights(precision):
+    """test_nature_cnn.py:7-22 (all-zero weights and biases: zero features), integration/test_agent.py:10-57 and
+    test_launch.py:310-318 (zero-initialised heads: value 0, uniform policy, log_prob = log(1/A)) and
+    heads/test_policy_heads.py:15-27 — on frames that are NOT zero, so any leak of the input would show."""
+    from pytorch_drl_b200 import agents
+    A, nb = 6, 32
+    z = tc.nn.init.zeros_
+    ag = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4, z, z),
+                      {'policy': agents.CategoricalPolicyHead(512, A, w_init=z, b_init=z),
+                       'value_extrinsic': agents.SimpleValueHead(512, w_init=z, b_init=z)})
+    ag.fuse(max_batch=nb, precision=precision, device=dev())
+    g = tc.Generator(device=dev())
+    g.manual_seed(5)
+    obs = tc.randint(0, 256, (nb, 84, 84, 4), device=dev(), dtype=tc.uint8, generator=g)
+    with tc.no_grad():
+        pred = ag(obs, ['policy', 'value_extrinsic'])
+    tc.testing.assert_close(pred['value_extrinsic'], tc.zeros(nb, device=dev()), rtol=1e-4, atol=1e-4)
+    acts = tc.zeros(nb, dtype=tc.int64, device=dev())
+    tc.testing.assert_close(pred['policy'].log_prob(acts), tc.log(tc.full((nb,), 1.0 / A, device=dev())), rtol=1e-4, atol=1e-4)
+    tc.testing.assert_close(pred['policy'].entropy(), tc.full((nb,), float(np.log(A)), device=dev()), rtol=1e-4, atol=1e-4)
+    # zero trunk, non-zero head bias: features are exactly zero, so logits == bias for every sample
+    with tc.no_grad():
+        dict(ag.named_parameters())['_predictors.policy._policy_head._network.0.bias'].copy_(tc.arange(A, dtype=tc.float32) * 0.25)
+    ag.engine.sync_params()
+    with tc.no_grad():
+        pred = ag(obs, ['policy'])
+    ref = tc.log_softmax(tc.arange(A, dtype=tc.float32, device=dev()) * 0.25, 0)
+    tc.testing.assert_close(pred['policy'].logits, ref.expand(nb, A), rtol=1e-5, atol=1e-5)
