@@ -149,3 +149,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] == (os.cpu_count() or 1)
     assert line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
     assert 'workload' in line['config']
+
+
+def test_nested_tensor_helpers_match_reference_tests():
+    """drl/utils/test_nested.py:26-50: clone and slice (python slice and numpy index array) of a nested dict of tensors.
+    Host tensors keep the reference's gather semantics; only a CUDA int64 index applied to a device rollout turns into
+    a MinibatchView (tests/test_gpu_parity.py)."""
+    from pytorch_drl_b200.utils.nested import clone_nested_tensor, slice_nested_tensor
+
+    def make():
+        return {'foo': tc.arange(10), 'bar': {'baz': tc.zeros(10, dtype=tc.float32)}}
+
+    def same(a, b):
+        if isinstance(a, tc.Tensor):
+            tc.testing.assert_close(actual=a, expected=b)
+        else:
+            assert set(a.keys()) == set(b.keys())
+            for k in a:
+                same(a[k], b[k])
+
+    nt = make()
+    cl = clone_nested_tensor(nt)
+    same(nt, cl)
+    assert cl['foo'].data_ptr() != nt['foo'].data_ptr()
+    same(slice_nested_tensor(make(), slice(0, 3)), {'foo': tc.arange(3), 'bar': {'baz': tc.zeros(3)}})
+    same(slice_nested_tensor(make(), np.array([1, 2, 5])), {'foo': tc.tensor([1, 2, 5]), 'bar': {'baz': tc.zeros(3)}})
