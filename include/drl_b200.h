@@ -155,6 +155,10 @@ int drl_net_forward(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, 
                     float* logits, float* values, const int64_t* actions, float* logp_out,
                     float* entropy_out, void* stream);
 
+/* Trunk only: feat_out [nb, 512] = the post-ReLU NatureCNN features (nature_cnn.py:27-36) of the minibatch, for heads
+ * outside the fused policy / value heads (the DQN action-value heads: drl_dueling_forward_f32). */
+int drl_net_features(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, float* feat_out, void* stream);
+
 /* One learner step without the optimiser: forward, fused losses, backward.  grads (flat, same
  * layout as params) is OVERWRITTEN with d composite / d params, where composite is the mean over
  * the nb samples (== mean over ranks of per-rank means for equal shards).

@@ -58,6 +58,7 @@ PROTOTYPES = {
     'drl_net_set_params': (c_int, [c_void_p, c_void_p, c_void_p]),
     'drl_net_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    'drl_net_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'drl_net_ppo_step': (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(PpoBatch),
                                  POINTER(PpoHyper), c_void_p, c_void_p, c_void_p]),
     'drl_net_ppo_metrics': (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(PpoBatch),

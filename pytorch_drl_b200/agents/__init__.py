@@ -6,7 +6,7 @@ from typing import Any, Callable, List, Mapping, Optional, Type
 import torch as tc
 
 from ..engine import LearnerEngine
-from .dqn_heads import (MLP, DuelingArchitecture, EpsilonGreedyCategoricalPolicyHead,  # noqa: F401
+from .dqn_heads import (MLP, DuelingArchitecture, EpsilonGreedyCategoricalPolicyHead, QAgent,  # noqa: F401
                         SimpleDiscreteActionValueHead)
 
 

@@ -127,3 +127,54 @@ class EpsilonGreedyCategoricalPolicyHead(tc.nn.Module):
         check(_lib.lib().drl_epsilon_greedy_probs_f32(ptr(q), q.shape[0], q.shape[1], float(self._epsilon), ptr(probs), None,
                                                       current_stream()), 'epsilon_greedy_probs')
         return tc.distributions.Categorical(probs=probs)
+
+
+class QAgent(tc.nn.Module):
+    """The reference's `Agent` (drl/agents/integration/agent.py:14-75) for the DQN predictor set that
+    `get_predictors` builds (drl/utils/launch.py:268-282): a `DiscreteActionValueHead` under its own key plus the
+    epsilon-greedy 'policy' derived from it.  Forward only (acting, target-network evaluation): the NatureCNN trunk
+    runs on the fused engine (`drl_net_features`), the heads on csrc/dueling.cu.  state_dict keys are the
+    reference's (`_architecture._network.*`, `_predictors.<key>._action_value_head.*`)."""
+
+    def __init__(self, preprocessing, architecture, predictors: Mapping[str, tc.nn.Module], detach_input: bool = True):
+        super().__init__()
+        from . import NatureCNN
+        if not isinstance(architecture, NatureCNN):
+            raise NotImplementedError('only NatureCNN is fused')
+        heads = {k: v for k, v in predictors.items() if isinstance(v, SimpleDiscreteActionValueHead)}
+        if len(heads) != 1:
+            raise ValueError('QAgent needs exactly one SimpleDiscreteActionValueHead predictor')
+        self._preprocessing = tc.nn.Sequential(*preprocessing)
+        self._architecture = architecture
+        self._predictors = tc.nn.ModuleDict(dict(predictors))
+        if 'policy' not in self._predictors:               # launch.py:278-282
+            self._predictors['policy'] = EpsilonGreedyCategoricalPolicyHead(action_value_head=next(iter(heads.values())))
+        self._q_key = next(iter(heads.keys()))
+        self._detach_input = detach_input
+        self.engine = None
+
+    def fuse(self, max_batch: int, precision: str = 'bf16', device=None) -> 'QAgent':
+        from ..engine import TRUNK_NAMES, LearnerEngine
+        eng = LearnerEngine(self._predictors[self._q_key].num_actions, ['value_extrinsic'], max_batch, precision, device)
+        named = dict(self.named_parameters())
+        views = eng.named_views()
+        for n in TRUNK_NAMES:                               # the engine's own policy / value heads stay zero and unused
+            views[n].copy_(named[n].detach().to(eng.device, tc.float32))
+            named[n].data = views[n]
+        eng.sync_params()
+        self._predictors.to(eng.device)
+        self.engine = eng
+        return self
+
+    def sync(self) -> None:
+        """Call after changing trunk parameters in place (e.g. a target-network copy): refreshes the packed operands."""
+        self.engine.sync_params()
+
+    @tc.no_grad()
+    def forward(self, observations: tc.Tensor, predict, **kwargs):
+        if self.engine is None:
+            raise RuntimeError('call fuse() first: there is no unfused / CPU path')
+        from . import Agent
+        obs = Agent.to_uint8_frames(observations.detach() if self._detach_input else observations)
+        feats = self.engine.features(obs.to(self.engine.device).contiguous())
+        return {key: self._predictors[key](feats) for key in predict}

@@ -157,6 +157,19 @@ extern "C" int drl_net_forward(drl_net_t* net, const uint8_t* obs, const int64_t
                              logp_out, entropy_out, nullptr, st);
 }
 
+// Trunk only: the 512 post-ReLU features of NatureCNN (nature_cnn.py:27-36) for heads that live outside the fused
+// policy / value heads (the DQN action-value heads, csrc/dueling.cu).
+extern "C" int drl_net_features(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, float* feat_out,
+                                void* stream) {
+  DRL_TRY(check_call(net, obs, nb));
+  if (!feat_out) return DRL_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  DRL_TRY(net->precision == DRL_PRECISION_FP32 ? fp32_trunk_forward(net, obs, row_idx, nb, st)
+                                               : bf16_trunk_forward(net, obs, row_idx, nb, st));
+  DRL_CUDA(cudaMemcpyAsync(feat_out, net->feat, (size_t)nb * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DRL_OK;
+}
+
 static int ppo_common(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb,
                       const drl_ppo_batch_t* batch, const drl_ppo_hyper_t* hyper, float* grads,
                       float* losses_out, void* stream) {

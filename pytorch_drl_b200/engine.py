@@ -111,6 +111,18 @@ class LearnerEngine:
         cat = lambda i: None if out[0][i] is None else tc.cat([o[i] for o in out])  # noqa: E731
         return cat(0), cat(1), cat(2), cat(3)
 
+    def features(self, obs_u8: tc.Tensor, row_idx: Optional[tc.Tensor] = None, nb: Optional[int] = None) -> tc.Tensor:
+        """No-grad trunk forward: the [nb, 512] NatureCNN features (for heads outside the fused ones, e.g. the DQN heads)."""
+        ops._cuda(obs_u8, tc.uint8, 'observations')
+        nb = int(nb if nb is not None else (row_idx.numel() if row_idx is not None else obs_u8.shape[0]))
+        feat = tc.empty((nb, 512), dtype=tc.float32, device=self.device)
+        for s in range(0, nb, self.max_batch):
+            m = min(self.max_batch, nb - s)
+            ridx = row_idx[s:s + m] if row_idx is not None else tc.arange(s, s + m, device=self.device, dtype=tc.int64)
+            check(self._L.drl_net_features(self._h, ptr(obs_u8), ptr(ridx), m, ptr(feat[s:s + m]), current_stream()),
+                  'net_features')
+        return feat
+
     def ppo_step(self, obs_u8: tc.Tensor, row_idx: tc.Tensor, batch: _lib.PpoBatch,
                  hyper: _lib.PpoHyper, grads: bool = True) -> tc.Tensor:
         """forward + fused losses (+ backward into self.grads). Returns the device losses[5]."""

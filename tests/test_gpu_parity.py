@@ -890,3 +890,40 @@ def test_reference_known_answers_zero_weights(precision):
         pred = ag(obs, ['policy'])
     ref = tc.log_softmax(tc.arange(A, dtype=tc.float32, device=dev()) * 0.25, 0)
     tc.testing.assert_close(pred['policy'].logits, ref.expand(nb, A), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('precision', _precisions())
+def test_qagent_trunk_features_and_dueling_q_vs_oracle(precision, golden_dir):
+    """DQN acting / target evaluation through the fused trunk: QAgent = NatureCNN on the engine (drl_net_features) +
+    dueling action-value head + epsilon-greedy policy, against the oracle trunk (nature_cnn.py:27-36) followed by the
+    oracle dueling head with the reference's own head weights (golden case 0)."""
+    from oracle import dueling_oracle as do
+    from pytorch_drl_b200 import agents
+    A, nb = 6, 45
+    g = np.load(os.path.join(golden_dir, 'dueling.npz'))
+    hp = {k: g[f'c0_p_{k}'] for k in do.PARAM_KEYS}
+    trunk = po.init_params(A, ['extrinsic'], seed=21)
+    head = agents.SimpleDiscreteActionValueHead(512, A, agents.DuelingArchitecture, {'widening': 1})
+    head._action_value_head.load_state_dict({k: tc.from_numpy(v) for k, v in hp.items()})
+    qa = agents.QAgent([agents.ToChannelMajor()], agents.NatureCNN(4), {'action_value': head})
+    qa.load_state_dict({k: tc.from_numpy(trunk[k]) for k in po.TRUNK_KEYS}, strict=False)
+    qa.fuse(max_batch=32, precision=precision, device=dev())          # 45 samples > max_batch: the engine chunks
+    rs = np.random.RandomState(2)
+    obs = rs.randint(0, 256, size=(nb, 84, 84, 4), dtype=np.uint8)
+    feat_ref = po.trunk_forward({k: tc.from_numpy(trunk[k]) for k in po.TRUNK_KEYS}, po.scale_obs(tc.from_numpy(obs))).numpy()
+    q_ref = do.dueling_forward(hp, feat_ref)
+    feats = qa.engine.features(cu(obs))
+    t = TOL[precision]
+    assert rel_l2(feats.cpu().numpy(), feat_ref) < t['act']
+    pol = qa._predictors['policy']
+    pol.epsilon = 0.1
+    out = qa(cu(obs), ['action_value', 'policy'])
+    q = out['action_value'].cpu().numpy()
+    assert q.shape == (nb, A) and rel_l2(q, q_ref) < 2 * t['act']
+    probs = out['policy'].probs.cpu().numpy()
+    np.testing.assert_allclose(probs.sum(-1), 1.0, rtol=1e-6)
+    np.testing.assert_array_equal(probs.argmax(-1), q.argmax(-1))         # greedy action = argmax of the SAME q
+    np.testing.assert_allclose(np.sort(probs, -1)[:, -1], 0.9 + 0.1 / A, rtol=1e-5)
+    # float32 frames pre-scaled by 1/255 (the reference's rollout format) map back to the same bytes
+    out2 = qa(po.scale_obs(tc.from_numpy(obs)).to(dev()), ['action_value'])
+    np.testing.assert_array_equal(out2['action_value'].cpu().numpy(), q)
