@@ -174,3 +174,44 @@ def test_nested_tensor_helpers_match_reference_tests():
     assert cl['foo'].data_ptr() != nt['foo'].data_ptr()
     same(slice_nested_tensor(make(), slice(0, 3)), {'foo': tc.arange(3), 'bar': {'baz': tc.zeros(3)}})
     same(slice_nested_tensor(make(), np.array([1, 2, 5])), {'foo': tc.tensor([1, 2, 5]), 'bar': {'baz': tc.zeros(3)}})
+
+
+def test_state_dicts_round_trip_with_the_real_reference_modules():
+    """f3 (checkpoint compatibility) against the UNMODIFIED reference where it is mounted (this container; skipped on
+    the GPU box): the reference's Agent(NatureCNN + categorical policy + value heads) and its
+    SimpleDiscreteActionValueHead(DuelingArchitecture) exchange state_dicts with the drop-ins in both directions with
+    strict=True — same keys, same shapes, same tensor layouts (drl/utils/checkpointing.py:64 loads exactly these)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not mounted')
+    ref_loader.load()
+    from drl.agents.architectures import NatureCNN as RNature, Linear as RLinear, DuelingArchitecture as RDueling
+    from drl.agents.heads import CategoricalPolicyHead as RPol, SimpleValueHead as RVal
+    from drl.agents.heads.action_value_heads import SimpleDiscreteActionValueHead as RQ
+    from drl.agents.integration import Agent as RAgent
+    from drl.agents.preprocessing import ToChannelMajor as RTCM
+    w = lambda t: tc.nn.init.orthogonal_(t, gain=2 ** 0.5)       # noqa: E731
+    b = tc.nn.init.zeros_
+    tc.manual_seed(3)
+    ref = RAgent(preprocessing=[RTCM()], architecture=RNature(img_channels=4, w_init=w, b_init=b),
+                 predictors={'policy': RPol(num_features=512, num_actions=6, head_architecture_cls=RLinear,
+                                            head_architecture_cls_args={}, w_init=w, b_init=b),
+                             'value_extrinsic': RVal(num_features=512, head_architecture_cls=RLinear,
+                                                     head_architecture_cls_args={}, w_init=w, b_init=b)})
+    mine = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4, w, b),
+                        {'policy': agents.CategoricalPolicyHead(512, 6, w_init=w, b_init=b),
+                         'value_extrinsic': agents.SimpleValueHead(512, w_init=w, b_init=b)})
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert list(rsd.keys()) == list(msd.keys())
+    assert [tuple(v.shape) for v in rsd.values()] == [tuple(v.shape) for v in msd.values()]
+    mine.load_state_dict(rsd, strict=True)
+    for k in rsd:
+        assert tc.equal(mine.state_dict()[k], rsd[k])
+    ref.load_state_dict(msd, strict=True)
+    # DQN head
+    rq = RQ(num_features=512, num_actions=18, head_architecture_cls=RDueling, head_architecture_cls_args={'widening': 1},
+            w_init=w, b_init=b)
+    mq = agents.SimpleDiscreteActionValueHead(512, 18, agents.DuelingArchitecture, {'widening': 1}, w_init=w, b_init=b)
+    assert list(rq.state_dict().keys()) == list(mq.state_dict().keys())
+    mq.load_state_dict(rq.state_dict(), strict=True)
+    rq.load_state_dict(mq.state_dict(), strict=True)
