@@ -34,8 +34,12 @@ template <> __device__ __forceinline__ void store_act2<__nv_bfloat16>(__nv_bfloa
 // vector-Jacobian product a differentiable Agent.forward needs (no loss is evaluated).
 // OX = A + K when the launcher knows it at compile time (the Atari cases), else 0: the three O x 512 loops then
 // run exactly O iterations; with OX = 0 their iterations o >= O are predicated off but still take issue slots.
-template <int MAXA, int MODE, typename TD, int OX = 0>
-__global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
+// MINB = resident CTAs per SM the register allocation aims for: 2 (<= 128 registers; what the compiler chose on its own: 127)
+// for the general instantiations, 3 (80 registers, 64 bytes of spill) for the exact-(A, K) training kernels with A <= 8: the
+// kernel waits on its global loads (ncu: 16 resident warps, issue slots 49 % busy), so 24 resident warps pay: 0.094 -> 0.084 ms.
+// (MINB = 1 lets the allocator take 168+ registers = one CTA per SM: 0.161 ms.)
+template <int MAXA, int MODE, typename TD, int OX = 0, int MINB = 2>
+__global__ void __launch_bounds__(kWarps * 32, MINB) heads_loss_kernel(
     const float* __restrict__ feat, HeadParams hp_ptrs, const int64_t* __restrict__ row_idx, int nb,
     drl_ppo_batch_t batch, drl_ppo_hyper_t hp, float inv_nb, float* __restrict__ losses_out,
     float* __restrict__ logits_out, float* __restrict__ values_out, float* __restrict__ logp_out,
@@ -252,6 +256,8 @@ __global__ void __launch_bounds__(kWarps * 32) heads_loss_kernel(
   }
 }
 
+extern int g_debug_flags[16];
+
 template <int MAXA, int MODE, typename TD, int OX = 0>
 static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t* row_idx, int nb,
                         const drl_ppo_batch_t& batch, const drl_ppo_hyper_t& hp, float* losses_out,
@@ -260,9 +266,20 @@ static int launch_heads(const float* feat, const HeadParams& hpp, const int64_t*
   constexpr int MAXO = MAXA + DRL_MAX_REWARD_STREAMS;
   const int O = hp.num_actions + hp.num_streams;
   const size_t smem = sizeof(float) * ((size_t)O * kFeat + MAXO + kWarps * kFeat + kWarps * MAXO + 128);
+  const int ntiles = (nb + kWarps - 1) / kWarps;
+  if constexpr (OX != 0 && MAXA <= 8 && MODE == 2) {
+    if (g_debug_flags[8]) {                              // 3 resident CTAs per SM (register-capped), one wave
+      auto kern3 = heads_loss_kernel<MAXA, MODE, TD, OX, 3>;
+      DRL_CUDA(cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int blocks3 = ntiles < sm_count() * 3 ? ntiles : sm_count() * 3;
+      kern3<<<blocks3, kWarps * 32, smem, st>>>(feat, hpp, row_idx, nb, batch, hp, 1.0f / (float)nb, losses_out, logits_out,
+                                                values_out, logp_out, ent_out, dpre);
+      DRL_LAUNCH_CHECK();
+      return DRL_OK;
+    }
+  }
   auto kern = heads_loss_kernel<MAXA, MODE, TD, OX>;
   DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int ntiles = (nb + kWarps - 1) / kWarps;
   int blocks = ntiles < sm_count() * 4 ? ntiles : sm_count() * 4;   // latency-bound: as many CTAs as the registers allow
   kern<<<blocks, kWarps * 32, smem, st>>>(feat, hpp, row_idx, nb, batch, hp, 1.0f / (float)nb,
                                           losses_out, logits_out, values_out, logp_out, ent_out, dpre);

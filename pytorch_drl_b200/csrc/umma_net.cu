@@ -356,7 +356,9 @@ static int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 //     0.232 ms, conv2 dgrad 0.253 -> 0.340 ms (it is HBM / epilogue bound: the pair only couples two epilogues) => 3.
 //     bit 8: conv3 data gradient on CTA pairs with accumulator tiles that span samples (tma_conv2s_kernel, groups of 5
 //     samples in 4 tiles): 0.235 -> 0.217 ms => default 11.
-int g_debug_flags[8] = {0, 1, 2, 1, 1, 1, 5, 11};
+// [8] heads kernel compiled for 3 resident CTAs per SM (80 registers instead of 127, 64 bytes of spill) for the exact-(A, K)
+//     training instantiations with A <= 8: 0.094 -> 0.084 ms => default 1
+int g_debug_flags[16] = {0, 1, 2, 1, 1, 1, 5, 11, 1, 0, 0, 0, 0, 0, 0, 0};
 
 // NHWC bf16 activation [nb, H, W, C64] (C64 = 64 elements per pixel row) -> 4-D tiles of (64, BW, BH, 1)
 static int make_tmap_act4d(CUtensorMap* m, const void* base, uint64_t nb, uint64_t H, uint64_t W, uint32_t BW, uint32_t BH,
@@ -826,7 +828,7 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
 // debug switches (parity experiments): key 0 = descriptor base offset for shifted operands,
 // key 1 = TMA implicit-GEMM conv kernels (1) or cp.async row-gather kernels (0)
 extern "C" int drl_debug_set(int key, int value) {
-  if (key < 0 || key >= 8) return DRL_ERR_BAD_ARG;
+  if (key < 0 || key >= 16) return DRL_ERR_BAD_ARG;
   drl::g_debug_flags[key] = value;
   return DRL_OK;
 }
