@@ -330,11 +330,28 @@ def test_ppo_step_losses_and_grads_vs_oracle(precision, A, rk, rw, vclip):
     np.testing.assert_allclose(m2, losses, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize('precision', ['fp32'])
+# Bars of `PPO.optimize` against the unmodified reference's 2-rank DDP run, per precision mode (measured values in
+# profiles/r02_precision.json; DESIGN.md §4 "Precision modes" explains the bf16 figures):
+#   annotate  logp / vtarg / advantage of the T+1-frame no-grad forward              (abs / rel)
+#   param     final parameter tensors after opt_epochs x T/B Adam steps: relative error of the summary vector
+#   update    the same error divided by how far the reference moved that tensor (the 12 Adam updates) — the
+#             bf16 engine's ReLU masks differ from the fp32 ones for ~0.1 % of the activations, which under Adam's
+#             first steps (update ~ lr * sign(g)) shows as up to ~0.2 of the update norm
+#   metric    per-epoch policy / value / composite loss and mean entropy (rel + abs)
+GOLDEN_TOL = {
+    'fp32': dict(logp=(1e-4, 1e-5), adv=(2e-3, 2e-4), vtarg=(1e-4, 1e-5), param_rtol=2e-3, param_atol=5e-5, update=1e-3,
+                 metric=(5e-3, 5e-5)),
+    'bf16': dict(logp=(0, 5e-4), adv=(5e-3, 2e-3), vtarg=(1e-3, 1e-3), param_rtol=None, param_atol=None, update=0.35,
+                 metric=(1.5e-2, 4e-2)),
+}
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('tag', ['ppo_2rank', 'ppo_2rank_rnd'])
 def test_ppo_optimize_vs_reference_2rank_golden(golden_dir, precision, tag):
     """The drop-in PPO.optimize on one GPU with envs_per_rank=2 against the UNMODIFIED reference run
-    as 2 gloo ranks (tests/golden/ppo_2rank*.npz): final parameters, first-step grads, epoch metrics."""
+    as 2 gloo ranks (tests/golden/ppo_2rank*.npz): final parameters, first-step grads, epoch metrics —
+    for BOTH engines: the CUDA-core fp32 engine and the tcgen05 bf16 engine that bench.py times."""
     from pytorch_drl_b200 import agents, algos
     from _util import close_to_summary
     g = np.load(os.path.join(golden_dir, f'{tag}.npz'))
@@ -362,19 +379,31 @@ def test_ppo_optimize_vs_reference_2rank_golden(golden_dir, precision, tag):
         raw = po.make_synthetic_env_rollout(r, seed, T, A, rk)
         st.load_env(r, raw['observations'], raw['actions'], raw['rewards'], raw['dones'])
     rollout = algo.credit_assignment(algo.annotate(st.as_dict()))
+    tol = GOLDEN_TOL[precision]
     for r in range(world):
-        np.testing.assert_allclose(rollout['logprobs'][r, :T].cpu().numpy(), g[f'r{r}::logp'], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(rollout['logprobs'][r, :T].cpu().numpy(), g[f'r{r}::logp'], rtol=tol['logp'][0], atol=tol['logp'][1])
         for k in rk:
-            np.testing.assert_allclose(rollout['advantages'][k][r, :T].cpu().numpy(), g[f'r{r}::adv_{k}'], rtol=2e-3, atol=2e-4)
-            np.testing.assert_allclose(rollout['vtargs'][k][r, :T].cpu().numpy(), g[f'r{r}::vtarg_{k}'], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(rollout['advantages'][k][r, :T].cpu().numpy(), g[f'r{r}::adv_{k}'], rtol=tol['adv'][0], atol=tol['adv'][1])
+            np.testing.assert_allclose(rollout['vtargs'][k][r, :T].cpu().numpy(), g[f'r{r}::vtarg_{k}'], rtol=tol['vtarg'][0], atol=tol['vtarg'][1])
+    init = po.init_params(A, rk, int(g['cfg_param_seed']))
     algo.optimize(rollout)
     final = {k: v.detach().cpu().numpy() for k, v in agent.state_dict().items()}
+    from _util import summary
     for k in po.param_keys(rk):
-        close_to_summary(final[k], g[f'r0::final::{k}'], rtol=2e-3, atol=5e-5)
+        gold = g[f'r0::final::{k}']
+        if tol['param_rtol'] is not None:
+            close_to_summary(final[k], gold, rtol=tol['param_rtol'], atol=tol['param_atol'])
+        # error relative to the distance the reference moved the tensor (sum / norm entries of the summary left out)
+        big = final[k].size > 4096
+        got_s = summary(final[k])[2:] if big else np.asarray(final[k], np.float64).ravel()
+        init_s = summary(init[k])[2:] if big else np.asarray(init[k], np.float64).ravel()
+        gold_s = np.asarray(gold, np.float64).ravel()[2:] if big else np.asarray(gold, np.float64).ravel()
+        moved = np.linalg.norm(gold_s - init_s)
+        assert np.linalg.norm(got_s - gold_s) <= tol['update'] * moved + 1e-7, (k, np.linalg.norm(got_s - gold_s) / max(moved, 1e-30))
     em = g['r0::epoch_metrics']
     for ep in range(epochs):
         got = np.array([algo.last_epoch_metrics[ep][n] for n in algos.ppo.METRIC_NAMES])
-        np.testing.assert_allclose(got[:4], em[ep][:4], rtol=5e-3, atol=5e-5)
+        np.testing.assert_allclose(got[:4], em[ep][:4], rtol=tol['metric'][0], atol=tol['metric'][1])
         assert abs(got[4] - em[ep][4]) <= 2.0 / T + 1e-6
 
 
@@ -709,14 +738,23 @@ def test_full_size_step_properties():
     l_b, g_b = step(ident[nb // 2:])
     np.testing.assert_allclose(0.5 * (l_a + l_b)[:4], l_all[:4], rtol=1e-4, atol=1e-6)
     assert np.linalg.norm(0.5 * (g_a + g_b) - g_all) <= 2e-4 * np.linalg.norm(g_all)
-    sub = ident[1000:1512]
+    sub = ident[1000:1000 + 4096]
     l_sub, g_sub = step(sub)
+    names = eng.names
+    offs = eng.offsets
     del eng
-    ref, _ = _build('fp32', A, rk, 512)
+    ref, _ = _build('fp32', A, rk, 4096)
     l_ref = ref.ppo_step(obs, sub, batch, hyper).cpu().numpy()
     g_ref = ref.grads.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(l_sub[:4], l_ref[:4], rtol=5 * TOL['bf16']['loss'], atol=5 * TOL['bf16']['loss'])
     assert g_sub @ g_ref / (np.linalg.norm(g_sub) * np.linalg.norm(g_ref)) > 0.995
+    # rel-L2 per parameter tensor at 4 096 samples (measured 0.5-7 %: with random-sign advantages the minibatch gradient is
+    # a sum of cancelling per-sample terms, so the ~0.1 % of ReLU masks that differ between bf16 and fp32 activations
+    # show as sqrt(2 f) of the norm and do NOT average out with the batch size — DESIGN.md §4 "Precision modes")
+    per = {n: rel_l2(g_sub[offs[i]:offs[i + 1]], g_ref[offs[i]:offs[i + 1]]) for i, n in enumerate(names)}
+    print('bf16 vs fp32 engine, gradient rel-L2 per tensor at 4096 samples:', {k.split('._network')[0][-24:] + k[-9:]: round(v, 4) for k, v in per.items()})
+    assert rel_l2(g_sub, g_ref) < 2e-2, rel_l2(g_sub, g_ref)
+    assert max(per.values()) < 0.12, per
 
 
 # ---- differentiable Agent.forward: custom torch losses on top of the fused network ------------------
