@@ -53,8 +53,8 @@ long long drl_launch_count(void);
  * device, returns for each site seen since the last read its name (48-char slots), summed
  * milliseconds and launch count, and clears the records. */
 int drl_profile_enable(int on);
-/* Engineering switches used by the parity experiments (key 0: smem-descriptor base offset for shifted
- * operands, key 1: TMA implicit-GEMM conv kernels vs cp.async row-gather kernels). */
+/* Kernel-variant switches for A/B measurements (keys 6-8: CTA-pair / epilogue-warpgroup variants of the fc and conv
+ * kernels, heads-kernel occupancy; see csrc/umma_net.cu).  Defaults are the measured-fastest variants. */
 int drl_debug_set(int key, int value);
 int drl_profile_read(int max_sites, char* names_out, float* total_ms, int* counts, int* n_sites);
 

@@ -191,7 +191,7 @@ static int ppo_common(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx
                               nullptr, nullptr, nullptr, nullptr, net->dpre, st));
   }
   if (grads)
-    DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, st)
+    DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, /*overlap_comm=*/true, st)
                  : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
   if (grads && net->comm && comm_world(net->comm) > 1) {
     // bf16 engine: the fc + heads range is already in flight (queued after the fc weight gradient); here the rest.
@@ -221,7 +221,9 @@ extern "C" int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_
   hp.num_actions = net->A; hp.num_streams = net->K;
   DRL_TRY(heads_loss_dispatch(3, bf16, net->feat, hpp, row_idx, nb, batch, hp, nullptr, const_cast<float*>(dlogits),
                               const_cast<float*>(dvalues), nullptr, nullptr, net->dpre, st));
-  DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, st) : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
+  // no collective here: the caller owns `grads` (a scratch buffer of the autograd path) and decides when to exchange it
+  DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, /*overlap_comm=*/false, st)
+               : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
   return DRL_OK;
 }
 

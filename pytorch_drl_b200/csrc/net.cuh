@@ -54,6 +54,8 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
 int comm_allreduce_after(drl_comm* c, float* flat, int64_t lo, int64_t hi, cudaStream_t producer);
 int comm_join(drl_comm* c, cudaStream_t consumer);
 int comm_world(const drl_comm* c);
-int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, float* grads, cudaStream_t st);
+// overlap_comm: start the all-reduce of the fc + heads range on the attached communicator's side stream as soon as it is final
+// (only the learner step does: it joins the exchange afterwards)
+int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, float* grads, bool overlap_comm, cudaStream_t st);
 
 }  // namespace drl

@@ -465,8 +465,8 @@ PAIR_DEFAULT = 11     # library default of debug flag 7 (conv kernels on CTA pai
 
 
 def test_alternative_bf16_engines_stay_in_parity():
-    """The cp.async row-gather conv / wgrad kernels and the shared-memory-operand conv1 forward are kept behind
-    drl_debug_set (they measured slower): they must keep producing the same gradients as the default engines."""
+    """The kernel variants still selectable through drl_debug_set (fc GEMMs with / without CTA pairs and 2 / 4 epilogue
+    warpgroups; conv kernels on single CTAs, CTA pairs, sample-spanning tiles) must keep producing the default gradients."""
     from pytorch_drl_b200 import _lib, ops
     from pytorch_drl_b200.algos import RolloutStorage
     L = _lib.lib()
@@ -490,26 +490,16 @@ def test_alternative_bf16_engines_stay_in_parity():
     batch = ops.make_batch(d['actions'], d['logprobs'], [d['advantages']['extrinsic']], [d['vpreds']['extrinsic']],
                            [d['vtargs']['extrinsic']])
     try:
-        # (tma conv fwd/dgrad kernels, tma conv wgrad kernels, conv1 forward A operand in TMEM)
-        for flags in ((0, 0, 0, 0, 0, 0, 0), (1, 1, 1, 1, 0, 2, 0), (1, 2, 1, 1, 1, 1, 7), (1, 1, 1, 1, 1, 0, 5), (1, 2, 1, 1, 1, 5, 0), (1, 2, 1, 1, 1, 1, 11)):
-            L.drl_debug_set(1, flags[0])
-            L.drl_debug_set(2, flags[1])      # conv / fc weight gradients: 0 cp.async kernels, 1 TMA kernels + scattered atomics, 2 + [kp][co] scratch
-            L.drl_debug_set(3, flags[2])
-            L.drl_debug_set(4, flags[3])      # conv1 weight gradient on the space-to-depth block image
-            L.drl_debug_set(5, flags[4])      # conv1 forward on the space-to-depth block image
-            L.drl_debug_set(6, flags[5])      # fc GEMMs: bits 0-1 CTA pairs (0 none, 1 forward, 2 forward + data gradient), bit 2 four epilogue warpgroups in the data gradient
-            L.drl_debug_set(7, flags[6])      # conv kernels on CTA pairs: bit 0 conv2 forward, bit 1 conv3 dgrad, bit 2 conv2 dgrad, bit 3 conv3 dgrad with sample-spanning tiles
+        for f6, f7 in ((0, 0), (2, 0), (1, 7), (5, 3), (5, 11)):
+            L.drl_debug_set(6, f6)      # fc GEMMs: bits 0-1 CTA pairs (0 none, 1 forward, 2 forward + data gradient), bit 2 four epilogue warpgroups in the data gradient
+            L.drl_debug_set(7, f7)      # conv kernels on CTA pairs: bit 0 conv2 forward, bit 1 conv3 dgrad, bit 2 conv2 dgrad, bit 3 conv3 dgrad with sample-spanning tiles
+            flags = (f6, f7)
             eng, _ = _build('bf16', A, rk, n_envs * B)
             eng.ppo_step(d['observations'], rows, batch, hyper)
             gv = eng.named_views(eng.grads)
             for k in po.param_keys(rk):
                 assert rel_l2(gv[k].cpu().numpy(), ref_g[k]) < TOL['bf16']['grad'], (flags, k)
     finally:
-        L.drl_debug_set(1, 1)
-        L.drl_debug_set(2, 2)
-        L.drl_debug_set(3, 1)
-        L.drl_debug_set(4, 1)
-        L.drl_debug_set(5, 1)
         L.drl_debug_set(6, 5)
         L.drl_debug_set(7, PAIR_DEFAULT)
 
