@@ -265,8 +265,15 @@ typedef struct drl_rnd drl_rnd_t;
 int drl_rnd_create(drl_rnd_t** out, int device, int max_batch, int widening, int precision);
 int drl_rnd_destroy(drl_rnd_t* rnd);
 int64_t drl_rnd_param_count(int student, int widening);
+/* precision: DRL_PRECISION_FP32 (CUDA cores, strict parity) or DRL_PRECISION_BF16 (tcgen05: sample pairs packed along the
+ * channels of block-diagonal implicit GEMMs, csrc/umma_rnd.cu).  (Re)binds the flat parameter buffers and, in BF16 mode,
+ * refreshes the packed operand copies of both networks. */
 int drl_rnd_set_params(drl_rnd_t* rnd, const float* teacher_params, const float* student_params,
                        void* stream);
+/* Adam on the student's flat parameters (rnd_optimizer.step(), random_network_distillation.py:233), also refreshing the
+ * student's packed operand copies (BF16 mode).  Arguments as drl_adam_step. */
+int drl_rnd_adam_step(drl_rnd_t* rnd, float* student_params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                      double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale, void* stream);
 /* Intrinsic reward (step, :193-196): err[i] = mean_d (teacher - student)^2 of the normalised,
  * clipped LAST channel of uint8 frame row_idx[i]; no gradient. */
 int drl_rnd_reward(drl_rnd_t* rnd, const uint8_t* obs, const int64_t* row_idx, int nb,

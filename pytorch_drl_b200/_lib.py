@@ -77,6 +77,8 @@ PROTOTYPES = {
     'drl_rnd_destroy': (c_int, [c_void_p]),
     'drl_rnd_param_count': (c_int64, [c_int, c_int]),
     'drl_rnd_set_params': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    'drl_rnd_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double,
+                                  c_int64, c_float, c_void_p]),
     'drl_rnd_reward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
     'drl_rnd_learn': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

@@ -2,14 +2,14 @@
 // (drl/envs/wrappers/stateful/intrinsic/random_network_distillation.py:209-235, 186-201) with the
 // _TeacherNetwork / _StudentNetwork of the same file (:22-87).
 //
-// Round-1 engine: the fp32 CUDA-core implicit GEMM (simt_conv.cu), i.e. the strict-parity mode;
-// the uint8 frame's last channel is read directly, and x*(1/255), the observation normaliser
-// (normalize.py:149-162) and the +-5 clip are fused into the first conv's gather.  The predictor
-// MSE forward/backward is one warp-per-sample kernel.  (A tcgen05 version of these small convs
-// follows the NatureCNN kernels; DRL_PRECISION_BF16 is refused here, loudly.)
+// Two engines behind one handle: DRL_PRECISION_FP32 = the fp32 CUDA-core implicit GEMM (simt_conv.cu), the strict-parity
+// mode (the uint8 frame's last channel is read directly; x*(1/255), the observation normaliser (normalize.py:149-162) and
+// the +-5 clip are fused into the first conv's gather; the predictor MSE forward/backward is one warp-per-sample kernel);
+// DRL_PRECISION_BF16 = the tcgen05 engine of umma_rnd.cu (throughput mode).
 #include <new>
-#include "common.cuh"
+#include "rnd.cuh"
 #include "simt_conv.cuh"
+#include "net.cuh"
 
 namespace drl {
 
@@ -47,19 +47,6 @@ static const ConvGeom kStudentFc[3] = {ConvGeom{6, 6, 32, 1, 1, 256, 6, 6, 1}, C
 
 }  // namespace drl
 
-struct drl_rnd {
-  int device = 0, max_batch = 0;
-  const float* tp = nullptr;    // teacher params (flat)
-  const float* sp = nullptr;    // student params (flat)
-  int64_t toff[9] = {0}, soff[13] = {0};
-  float* ta[3] = {nullptr, nullptr, nullptr};   // teacher trunk activations
-  float* sa[3] = {nullptr, nullptr, nullptr};   // student trunk activations
-  float* sh[2] = {nullptr, nullptr};            // student hidden layers [nb,256]
-  float *y = nullptr, *yh = nullptr, *dyh = nullptr;
-  float* dsh[2] = {nullptr, nullptr};
-  float* dsa[3] = {nullptr, nullptr, nullptr};
-};
-
 using namespace drl;
 
 static void rnd_offsets(drl_rnd* r) {
@@ -83,13 +70,20 @@ extern "C" int drl_rnd_create(drl_rnd_t** out, int device, int max_batch, int wi
   if (!out) return DRL_ERR_BAD_ARG;
   *out = nullptr;
   if (max_batch < 1) return DRL_ERR_BAD_SHAPE;
-  if (widening != 1 || precision != DRL_PRECISION_FP32) return DRL_ERR_UNSUPPORTED;
+  if (widening != 1) return DRL_ERR_UNSUPPORTED;
+  if (precision != DRL_PRECISION_FP32 && precision != DRL_PRECISION_BF16) return DRL_ERR_BAD_ARG;
   DRL_TRY(drl_check_device(device));
   DRL_CUDA(cudaSetDevice(device));
   drl_rnd* r = new (std::nothrow) drl_rnd();
   if (!r) return DRL_ERR_CUDA;
-  r->device = device; r->max_batch = max_batch;
+  r->device = device; r->max_batch = max_batch; r->precision = precision;
   rnd_offsets(r);
+  if (precision == DRL_PRECISION_BF16) {
+    const int s = rnd_bf16_alloc(r);
+    if (s != DRL_OK) { drl_rnd_destroy(r); return s; }
+    *out = r;
+    return DRL_OK;
+  }
   const size_t nb = (size_t)max_batch;
   const size_t e[3] = {nb * 400 * 16, nb * 81 * 32, nb * 36 * 32};
   auto al = [](float** p, size_t n) { return cudaMalloc(p, n * sizeof(float)); };
@@ -117,13 +111,28 @@ extern "C" int drl_rnd_destroy(drl_rnd_t* r) {
   for (int i = 0; i < 3; ++i) { cudaFree(r->ta[i]); cudaFree(r->sa[i]); cudaFree(r->dsa[i]); }
   for (int i = 0; i < 2; ++i) { cudaFree(r->sh[i]); cudaFree(r->dsh[i]); }
   cudaFree(r->y); cudaFree(r->yh); cudaFree(r->dyh);
+  rnd_bf16_free(r);
   delete r;
   return DRL_OK;
 }
 
-extern "C" int drl_rnd_set_params(drl_rnd_t* r, const float* teacher_params, const float* student_params, void*) {
+extern "C" int drl_rnd_set_params(drl_rnd_t* r, const float* teacher_params, const float* student_params, void* stream) {
   if (!r || !teacher_params || !student_params) return DRL_ERR_BAD_ARG;
   r->tp = teacher_params; r->sp = student_params;
+  if (r->precision == DRL_PRECISION_BF16) return rnd_bf16_pack(r, true, true, as_stream(stream));
+  return DRL_OK;
+}
+
+extern "C" int drl_rnd_adam_step(drl_rnd_t* r, float* student_params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                 double lr, double beta1, double beta2, double eps, int64_t step, float grad_scale, void* stream) {
+  if (!r || !r->tp) return DRL_ERR_BAD_ARG;
+  {
+    ProfileScope prof("rnd_adam", as_stream(stream));
+    DRL_TRY(adam_launch(student_params, grads, exp_avg, exp_avg_sq, r->soff[12], lr, beta1, beta2, eps, step, grad_scale,
+                        as_stream(stream)));
+  }
+  r->sp = student_params;
+  if (r->precision == DRL_PRECISION_BF16) return rnd_bf16_pack(r, false, true, as_stream(stream));
   return DRL_OK;
 }
 
@@ -157,6 +166,10 @@ extern "C" int drl_rnd_reward(drl_rnd_t* r, const uint8_t* obs, const int64_t* r
   DRL_TRY(rnd_check(r, obs, nb, m1, m2));
   if (!err_out) return DRL_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
+  if (r->precision == DRL_PRECISION_BF16) {
+    DRL_TRY(rnd_bf16_forward(r, obs, row_idx, nb, m1, m2, false, st));
+    return rnd_bf16_mse(r, nb, err_out, nullptr, false, nullptr, st);
+  }
   DRL_TRY(rnd_forward(r, obs, row_idx, nb, m1, m2, st));
   rnd_mse_kernel<<<(nb + 7) / 8 < sm_count() * 4 ? (nb + 7) / 8 : sm_count() * 4, 256, 0, st>>>(r->y, r->yh, nb, err_out, nullptr,
                                                                                             nullptr);
@@ -173,6 +186,11 @@ extern "C" int drl_rnd_learn(drl_rnd_t* r, const uint8_t* obs, const int64_t* ro
   const int64_t* so = r->soff;
   DRL_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   DRL_CUDA(cudaMemsetAsync(g, 0, (size_t)so[12] * sizeof(float), st));
+  if (r->precision == DRL_PRECISION_BF16) {
+    DRL_TRY(rnd_bf16_forward(r, obs, row_idx, nb, m1, m2, true, st));
+    DRL_TRY(rnd_bf16_mse(r, nb, nullptr, loss_out, true, g, st));
+    return rnd_bf16_backward(r, obs, row_idx, nb, g, st);
+  }
   DRL_TRY(rnd_forward(r, obs, row_idx, nb, m1, m2, st));
   rnd_mse_kernel<<<(nb + 7) / 8 < sm_count() * 4 ? (nb + 7) / 8 : sm_count() * 4, 256, 0, st>>>(r->y, r->yh, nb, nullptr, loss_out,
                                                                                             r->dyh);

@@ -290,6 +290,14 @@ __device__ __forceinline__ uint32_t relu_bits_from_pairs(const uint32_t (&w)[16]
   for (int i = 15; i >= 0; --i) acc = (acc >> 1) | ((w[i] + 0x7FFF7FFFu) & 0x80008000u);
   return acc;
 }
+// LeakyReLU outputs keep their sign: bit = (value > 0), same bit positions.  (mag + 0x7FFF) raises bit 15 / 31 iff the
+// magnitude is non-zero (no carry between the halves: 0x7FFF + 0x7FFF < 0x10000); & ~w clears it for negative values.
+__device__ __forceinline__ uint32_t pos_bits_from_pairs(const uint32_t (&w)[16]) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 15; i >= 0; --i) acc = (acc >> 1) | ((((w[i] & 0x7FFF7FFFu) + 0x7FFF7FFFu) & ~w[i]) & 0x80008000u);
+  return acc;
+}
 // {lo, hi} -> bf16x2 with the ReLU folded into the conversion (negative -> +0)
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   uint32_t d;

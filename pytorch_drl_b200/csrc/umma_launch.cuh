@@ -102,7 +102,7 @@ static int launch_tma_conv(const char* site, const void* src, int nb, int H, int
   const int window = (MROWS + max_shift) * 128;     // bytes a shifted 128-row window can reach from a plane start
   a.slack_bytes = window > a.plane_bytes ? (window - a.plane_bytes + 1023) / 1024 * 1024 : 0;
   if (a.MT != 1) return DRL_ERR_BAD_ARG;                // one 128-row tile per sample (all NatureCNN layers)
-  if (a.bias_grad && a.bias_mod != (N == 64 ? 64 : 32)) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
+  if (a.bias_grad && (a.bias_mod < 1 || (N == 64 ? 64 : 32) % a.bias_mod != 0)) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   a.use_base_offset = 0;
   if (a.OH * a.RW > MROWS) return DRL_ERR_BAD_ARG;       // every output row must fall inside the tile
   if (a.KB != KB || a.KBX != KBX || a.SHIFT_RW != SHIFT_RW || a.planes != PLANES) return DRL_ERR_BAD_ARG;
@@ -270,7 +270,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
     return DRL_OK;
   }
   DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, BN));
-  if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
+  if (args.bias_grad && args.bias_mod != 64 && args.bias_mod != 32) return DRL_ERR_BAD_ARG;   // kernel's bias-group layout
   auto kern = tma_gemm_kernel<BN, EPI, NEPI>;
   constexpr int smem = TmaGemmCfg<BN>::kSmem;
   static int configured[kMaxDevices] = {0};

@@ -49,8 +49,10 @@ struct TmaConvArgs {
   int use_base_offset;    // debug switch for the descriptor base-offset field
   uint32_t* bits_out;     // EPI_BIAS_RELU: ReLU mask words (umma.cuh relu_bit_pos), word e >> 5 for output element index e
   const uint32_t* bits_in; // EPI_MASK: the same bit layout for the tensor shaped like `out` (replaces mask_src reads)
-  float* bias_grad;       // EPI_MASK: += column sums of the produced gradient, index = column % bias_mod (or nullptr)
-  int bias_mod;
+  float* bias_grad;       // EPI_MASK: += column sums of the produced gradient, index = column % bias_mod (or nullptr);
+  int bias_mod;           //    bias_mod may be any divisor of the kernel's 32 / 64-column bias group (pair-packed samples fold)
+  int chunk_pitch;        // elements between the 32-column chunks of an output row (0 = 32: contiguous).  RND conv3 forward
+                          //    writes the two samples of a pair (chunks 0 / 1) to separate per-sample [36][32] blocks.
 };
 
 // One accumulator tile of the row epilogue: GEMM row r of sample b -> bias + ReLU (+ mask bits) or ReLU-mask of the
@@ -63,14 +65,15 @@ __device__ __forceinline__ void tma_conv_epilogue_tile(const TmaConvArgs& args, 
                                                        uint32_t tfull_parity, Release release) {
   using namespace umma;
   auto coff = [&](int ch) -> int64_t {
-    return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C : (int64_t)ch * 32;
+    return args.classes ? (int64_t)(ch >> 1) * args.out_row_pitch + (int64_t)(ch & 1) * args.out_C
+                        : (int64_t)ch * (args.chunk_pitch ? args.chunk_pitch : 32);
   };
   const int y = r / args.RW, x = r - y * args.RW;
   const bool ok = sample_ok && y < args.OH && x < args.OW;
   const int64_t ooff = (int64_t)b * args.out_sample_pitch + (int64_t)(y * args.osy) * args.out_row_pitch +
                        (int64_t)(x * args.osx) * args.out_C;
   uint32_t mbits[N / 32];                           // ReLU mask bits of this row, one word per 32-column chunk
-  if (EPI == EPI_MASK_BF16 && ok) {
+  if (epi_is_mask(EPI) && ok) {
 #pragma unroll
     for (int ch = 0; ch < N / 32; ++ch) mbits[ch] = __ldg(args.bits_in + ((ooff + coff(ch)) >> 5));
   }
@@ -86,19 +89,21 @@ __device__ __forceinline__ void tma_conv_epilogue_tile(const TmaConvArgs& args, 
       release();
     }
     if (ok) {
-      if (EPI == EPI_BIAS_RELU_BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + ch * 32;
+      if (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_LEAKY_BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_bf16x2_relu(fmaf(__uint_as_float(rr[2 * i]), args.scale, sBias[ch * 32 + 2 * i]),
-                                   fmaf(__uint_as_float(rr[2 * i + 1]), args.scale, sBias[ch * 32 + 2 * i + 1]));
+        for (int i = 0; i < 16; ++i) {
+          const float v0 = fmaf(__uint_as_float(rr[2 * i]), args.scale, sBias[ch * 32 + 2 * i]);
+          const float v1 = fmaf(__uint_as_float(rr[2 * i + 1]), args.scale, sBias[ch * 32 + 2 * i + 1]);
+          pk[i] = EPI == EPI_BIAS_RELU_BF16 ? pack_bf16x2_relu(v0, v1)
+                                            : pack_bf16x2(fmaxf(v0, kLeakySlope * v0), fmaxf(v1, kLeakySlope * v1));
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q)
           stg_v8(o + 16 * q, pk[8 * q], pk[8 * q + 1], pk[8 * q + 2], pk[8 * q + 3], pk[8 * q + 4], pk[8 * q + 5], pk[8 * q + 6],
                  pk[8 * q + 7]);
-        const uint32_t bits = relu_bits_from_pairs(pk);
-        if (args.bits_out) args.bits_out[(ooff + ch * 32) >> 5] = bits;
+        if (args.bits_out) args.bits_out[(ooff + coff(ch)) >> 5] = EPI == EPI_BIAS_RELU_BF16 ? relu_bits_from_pairs(pk) : pos_bits_from_pairs(pk);
       } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff + coff(ch);
 #pragma unroll
@@ -106,8 +111,10 @@ __device__ __forceinline__ void tma_conv_epilogue_tile(const TmaConvArgs& args, 
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float lo = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i)) & 1u ? __uint_as_float(rr[16 * q + 2 * i]) : 0.f;
-            const float hi2 = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? __uint_as_float(rr[16 * q + 2 * i + 1]) : 0.f;
+            const float a0 = __uint_as_float(rr[16 * q + 2 * i]), a1 = __uint_as_float(rr[16 * q + 2 * i + 1]);
+            const float off0 = EPI == EPI_MASK_LEAKY_BF16 ? kLeakySlope * a0 : 0.f, off1 = EPI == EPI_MASK_LEAKY_BF16 ? kLeakySlope * a1 : 0.f;
+            const float lo = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i)) & 1u ? a0 : off0;
+            const float hi2 = (mbits[ch] >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? a1 : off1;
             pk[i] = pack_bf16x2(lo, hi2);
             rr[16 * q + 2 * i] = __float_as_uint(lo);
             rr[16 * q + 2 * i + 1] = __float_as_uint(hi2);
@@ -116,7 +123,7 @@ __device__ __forceinline__ void tma_conv_epilogue_tile(const TmaConvArgs& args, 
         }
       }
     }
-    if (EPI == EPI_MASK_BF16 && ok) {                 // fused bias gradient of the layer below
+    if (epi_is_mask(EPI) && ok) {                     // fused bias gradient of the layer below
 #pragma unroll
       for (int i = 0; i < 32; ++i) cs[(ch % BG) * 32 + i] += __uint_as_float(rr[i]);
     }
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (EPI != EPI_MASK_BF16 && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
+  if (!epi_is_mask(EPI) && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int a = 0; a < NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, 1); }
     for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
@@ -249,9 +256,9 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
     // fused bias gradient: every thread keeps running column sums of ITS rows (32 adds per chunk and tile);
     // the cross-lane reduction happens once, after the last tile.  Column chunk ch feeds bias group ch % BG.
     constexpr int BG = N == 64 ? 2 : 1;               // bias_mod / 32 (checked by the launcher)
-    float cs[EPI == EPI_MASK_BF16 ? 32 * BG : 1];
+    float cs[epi_is_mask(EPI) ? 32 * BG : 1];
 #pragma unroll
-    for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
+    for (int i = 0; i < (epi_is_mask(EPI) ? 32 * BG : 1); ++i) cs[i] = 0.f;
     // MROWS = 64: the accumulator rows live in lanes 0-15 of each 32-lane quarter (row = 16*quarter + lane)
     const int wg = warp >> 2;
     const int trow = MROWS == 128 ? (int)(threadIdx.x & 127) : (lane < 16 ? 16 * (warp & 3) + lane : 1 << 20);
@@ -264,13 +271,13 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
                                            sBias, cs, tfull + acc, (it / NACC) & 1, [&]() { mbar_arrive(tempty + acc); });
       }
     }
-    if (EPI == EPI_MASK_BF16 && args.bias_grad) {
+    if (epi_is_mask(EPI) && args.bias_grad) {
 #pragma unroll
       for (int g = 0; g < BG; ++g) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = cs[g * 32 + i];
-        atomicAdd(args.bias_grad + g * 32 + lane, warp_colsum32(v, lane));
+        atomicAdd(args.bias_grad + (g * 32 + lane) % args.bias_mod, warp_colsum32(v, lane));
       }
     }
   }
@@ -306,6 +313,9 @@ struct WgradConvArgs {
   int dy_box_bytes, dy_buf_bytes;
   float* gw; int Cin, KH, KW, kp_valid;
   float* gt;                // when set: partial sums go to the [kp][NT] scratch with 16-byte reductions (see wgrad_untranspose_kernel)
+  int pair_c;               // > 0: SAMPLE PAIRS packed along the channels (RND predictor): input channel = s * pair_c + ci, output
+                            //    column = s' * 32 + co (NT = 64).  Only the diagonal blocks s' == s are gradients (the others are
+                            //    products across the two samples): they are folded into the scratch row (tap, ci) of 32 columns.
 };
 
 template <int NT, int MB, int NR, int KSTEPS>
@@ -409,7 +419,16 @@ __global__ void __launch_bounds__(192, 1) wgrad_conv_tma_kernel(const __grid_con
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * NT + ch * 32, r);
           tmem_ld_wait();
-          if (ok && args.gt) {
+          if (ok && args.gt && args.pair_c) {
+            const int cinp = 2 * args.pair_c, tap = kp / cinp, rem = kp - tap * cinp, s = rem / args.pair_c;
+            if (ch == s) {
+              float* t = args.gt + (int64_t)(tap * args.pair_c + rem - s * args.pair_c) * 32;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                red_add_v4(t + 4 * q, __uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                           __uint_as_float(r[4 * q + 3]));
+            }
+          } else if (ok && args.gt) {
             float* t = args.gt + (int64_t)kp * NT + ch * 32;
 #pragma unroll
             for (int q = 0; q < 8; ++q)

@@ -35,8 +35,11 @@ struct TmaGemmArgs {
   const float* bias;           // EPI_BIAS_RELU_F32
   const __nv_bfloat16* mask_src;   // EPI_MASK_BF16 (same layout as out)
   const uint32_t* bits_in;     // EPI_MASK_BF16: ReLU mask words (umma.cuh relu_bit_pos) of act, element e = m*out_ld + n
-  float* bias_grad;            // EPI_MASK_BF16: += column sums of the produced gradient at index column % bias_mod
+  float* bias_grad;            // EPI_MASK_*: += column sums of the produced gradient at index column % bias_mod (64 or 32)
   int bias_mod;
+  int pair_out;                // EPI_MASK_LEAKY_BF16 (RND fc1 data gradient): row m, 32-column chunk c of the [M, out_ld] result goes to
+                               //   the SAMPLE-PAIR packed map  out[(m >> 1) * 2 * out_ld + c * 64 + (m & 1) * 32]  ([pairs][pixel c][2][32]);
+                               //   the mask bits stay in the plain [M, out_ld] order; an odd M gets a zero phantom row M.
 };
 
 template <int BN>
@@ -142,15 +145,15 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const 
     // one cross-lane reduction after the last tile
     constexpr int BG = NEPI == 2 ? 2 : 1;                 // bias groups a thread meets
     constexpr int CPW = BN / 32 / NEPI;                   // 32-column chunks per warpgroup and tile
-    float cs[EPI == EPI_MASK_BF16 ? 32 * BG : 1];
+    float cs[epi_is_mask(EPI) ? 32 * BG : 1];
 #pragma unroll
-    for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
+    for (int i = 0; i < (epi_is_mask(EPI) ? 32 * BG : 1); ++i) cs[i] = 0.f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int mt = tile % m_tiles, nt = tile / m_tiles;
       const uint32_t acc = j & 1;
       const int m = mt * 128 + (int)(threadIdx.x & 127);
       const int n0 = nt * BN;
-      if (EPI == EPI_BIAS_RELU_F32 && nt != last_nt) {     // (re)load the bias slice of this N tile
+      if (!epi_is_mask(EPI) && nt != last_nt) {            // (re)load the bias slice of this N tile
         asm volatile("bar.sync 1, %0;" ::"n"(128 * NEPI));
         for (int i = threadIdx.x; i < BN; i += 128 * NEPI) sBias[i] = n0 + i < args.N_total ? args.bias[n0 + i] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(128 * NEPI));
@@ -171,19 +174,35 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const 
         }
         const int n = n0 + ch * 32;
         if (m < args.M && n < args.N_total) {
-          if (EPI == EPI_BIAS_RELU_F32) {
+          if (EPI == EPI_BIAS_RELU_F32 || EPI == EPI_BIAS_F32) {
             float* o = reinterpret_cast<float*>(args.out) + (int64_t)m * args.out_ld + n;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint32_t v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(r[8 * q + i]) + sBias[ch * 32 + 8 * q + i], 0.f));
+              for (int i = 0; i < 8; ++i) {
+                const float x = __uint_as_float(r[8 * q + i]) + sBias[ch * 32 + 8 * q + i];
+                v[i] = __float_as_uint(EPI == EPI_BIAS_RELU_F32 ? fmaxf(x, 0.f) : x);
+              }
               stg_v8(o + 8 * q, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            }
+          } else if (EPI == EPI_BIAS_RELU_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + (int64_t)m * args.out_ld + n;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                pk[i] = pack_bf16x2_relu(__uint_as_float(r[16 * q + 2 * i]) + sBias[ch * 32 + 16 * q + 2 * i],
+                                         __uint_as_float(r[16 * q + 2 * i + 1]) + sBias[ch * 32 + 16 * q + 2 * i + 1]);
+              stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             }
           } else {
             const int64_t off = (int64_t)m * args.out_ld + n;
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + off;
-            uint32_t mb;                                   // ReLU mask of these 32 columns, 1 bit per element
+            const int64_t ooff = (EPI == EPI_MASK_LEAKY_BF16 && args.pair_out)
+                                     ? (int64_t)(m >> 1) * 2 * args.out_ld + (int64_t)(n >> 5) * 64 + (m & 1) * 32 : off;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + ooff;
+            uint32_t mb;                                   // activation-derivative mask of these 32 columns, 1 bit per element
             if (args.bits_in) {
               mb = __ldg(args.bits_in + (off >> 5));
             } else {                                       // fallback: derive it from the bf16 activation itself
@@ -193,15 +212,17 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const 
                 const uint4 mv = ldg_v4(args.mask_src + off + 8 * q);
                 mw[4 * q] = mv.x; mw[4 * q + 1] = mv.y; mw[4 * q + 2] = mv.z; mw[4 * q + 3] = mv.w;
               }
-              mb = relu_bits_from_pairs(mw);
+              mb = EPI == EPI_MASK_LEAKY_BF16 ? pos_bits_from_pairs(mw) : relu_bits_from_pairs(mw);
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float lo = (mb >> relu_bit_pos(16 * q + 2 * i)) & 1u ? __uint_as_float(r[16 * q + 2 * i]) : 0.f;
-                const float hi2 = (mb >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? __uint_as_float(r[16 * q + 2 * i + 1]) : 0.f;
+                const float a0 = __uint_as_float(r[16 * q + 2 * i]), a1 = __uint_as_float(r[16 * q + 2 * i + 1]);
+                const float off0 = EPI == EPI_MASK_LEAKY_BF16 ? kLeakySlope * a0 : 0.f, off1 = EPI == EPI_MASK_LEAKY_BF16 ? kLeakySlope * a1 : 0.f;
+                const float lo = (mb >> relu_bit_pos(16 * q + 2 * i)) & 1u ? a0 : off0;
+                const float hi2 = (mb >> relu_bit_pos(16 * q + 2 * i + 1)) & 1u ? a1 : off1;
                 pk[i] = pack_bf16x2(lo, hi2);
                 r[16 * q + 2 * i] = __float_as_uint(lo);
                 r[16 * q + 2 * i + 1] = __float_as_uint(hi2);
@@ -209,20 +230,25 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const 
               stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             }
           }
+        } else if (EPI == EPI_MASK_LEAKY_BF16 && args.pair_out && m == args.M && (args.M & 1) && n < args.N_total) {
+          // odd number of samples: the second half of the last pair is a phantom sample whose gradient must read as zero
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + (int64_t)(m >> 1) * 2 * args.out_ld + (int64_t)(n >> 5) * 64 + 32;
+          stg_v8(o, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+          stg_v8(o + 16, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
         }
-        if (EPI == EPI_MASK_BF16 && m < args.M && n < args.N_total) {   // fused bias gradient of the layer below
+        if (epi_is_mask(EPI) && m < args.M && n < args.N_total) {       // fused bias gradient of the layer below
 #pragma unroll
           for (int i = 0; i < 32; ++i) cs[(c2 % BG) * 32 + i] += __uint_as_float(r[i]);   // NEPI = 2: ch = wg * CPW + c2, CPW even; NEPI = 4: ch % 2 = wg % 2
         }
       }
     }
-    if (EPI == EPI_MASK_BF16 && args.bias_grad) {
+    if (epi_is_mask(EPI) && args.bias_grad) {
 #pragma unroll
       for (int g = 0; g < BG; ++g) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = cs[g * 32 + i];
-        atomicAdd(args.bias_grad + (NEPI == 2 ? g : ((warp >> 2) & 1)) * 32 + lane, warp_colsum32(v, lane));
+        atomicAdd(args.bias_grad + ((NEPI == 2 ? g : ((warp >> 2) & 1)) * 32 + lane) % args.bias_mod, warp_colsum32(v, lane));
       }
     }
   }

@@ -39,7 +39,8 @@ def _views(flat: tc.Tensor, keys, shapes) -> Dict[str, tc.Tensor]:
 
 class RandomNetworkDistillation:
     def __init__(self, rnd_optimizer_args: Mapping[str, float], world_size: int, widening: int = 1,
-                 non_learning_steps: int = 0, max_batch: int = 1024, comm=None, device=None, seed: int = 0):
+                 non_learning_steps: int = 0, max_batch: int = 1024, comm=None, device=None, seed: int = 0,
+                 precision: str = 'bf16'):
         if not tc.cuda.is_available():
             raise RuntimeError('RND needs a CUDA device; there is no CPU fallback')
         self.device = tc.device('cuda', tc.cuda.current_device()) if device is None else tc.device(device)
@@ -61,8 +62,10 @@ class RandomNetworkDistillation:
         self.loss = f(1)
         self._init_weights(seed)
         h = ctypes.c_void_p()
-        check(self._L.drl_rnd_create(ctypes.byref(h), self.device.index or 0, max_batch, widening, _lib.PRECISION_FP32),
-              'rnd_create')
+        # 'bf16' = tcgen05 engine (csrc/umma_rnd.cu), 'fp32' = CUDA-core strict-parity engine
+        self.precision_name = precision
+        prec = {'fp32': _lib.PRECISION_FP32, 'bf16': _lib.PRECISION_BF16}[precision]
+        check(self._L.drl_rnd_create(ctypes.byref(h), self.device.index or 0, max_batch, widening, prec), 'rnd_create')
         self._h = h
         self.max_batch = max_batch
         self._bind()
@@ -98,6 +101,7 @@ class RandomNetworkDistillation:
             v.copy_(tc.as_tensor(teacher[k]).to(self.device))
         for k, v in self.student_views().items():
             v.copy_(tc.as_tensor(student[k]).to(self.device))
+        self._bind()                      # the tcgen05 engine keeps packed operand copies of the parameters
 
     @property
     def checkpointables(self):
@@ -148,8 +152,10 @@ class RandomNetworkDistillation:
             self._comm.allreduce_(self.student_grads)
             world = self._comm.world
         self.adam_steps += 1
-        ops.adam_step(self.student_params, self.student_grads, self.exp_avg, self.exp_avg_sq, self.adam_steps,
-                      self._opt['lr'], tuple(self._opt['betas']), self._opt['eps'], grad_scale=1.0 / world)
+        b1, b2 = self._opt['betas']
+        check(self._L.drl_rnd_adam_step(self._h, ptr(self.student_params), ptr(self.student_grads), ptr(self.exp_avg),
+                                        ptr(self.exp_avg_sq), float(self._opt['lr']), float(b1), float(b2), float(self._opt['eps']),
+                                        self.adam_steps, 1.0 / world, current_stream()), 'rnd_adam_step')
         return self.loss
 
     def _sync_normalizers_global(self) -> None:

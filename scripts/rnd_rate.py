@@ -1,5 +1,5 @@
-"""RND predictor throughput on cuda:0 (fp32 CUDA-core engine): learn steps and batched intrinsic reward.
-Usage: python scripts/rnd_rate.py [samples]"""
+"""RND predictor throughput on cuda:0: learn steps and batched intrinsic reward, with the per-launch-site breakdown.
+Usage: python scripts/rnd_rate.py [samples] [bf16|fp32]"""
 import os
 import sys
 import time
@@ -11,8 +11,9 @@ import torch as tc  # noqa: E402
 from pytorch_drl_b200.envs import RandomNetworkDistillation  # noqa: E402
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+precision = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 dev = tc.device('cuda', 0)
-rnd = RandomNetworkDistillation({'lr': 1e-4, 'betas': (0.9, 0.999), 'eps': 1e-8}, world_size=1, max_batch=nb, device=dev)
+rnd = RandomNetworkDistillation({'lr': 1e-4, 'betas': (0.9, 0.999), 'eps': 1e-8}, world_size=1, max_batch=nb, device=dev, precision=precision)
 rnd._synced_normalizer.moment2.fill_(1.0)
 obs = tc.randint(0, 256, (nb, 84, 84, 4), device=dev, dtype=tc.uint8)
 rows = tc.arange(nb, device=dev, dtype=tc.int64)
@@ -27,7 +28,7 @@ for name, fn in (('learn', lambda: rnd.learn_rows(obs, rows)), ('intrinsic_rewar
     e1.record()
     tc.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f'rnd {name}: {nb} samples in {ms:.3f} ms = {nb / ms * 1e3 / 1e6:.2f} M samples/s')
+    print(f'rnd[{precision}] {name}: {nb} samples in {ms:.3f} ms = {nb / ms * 1e3 / 1e6:.2f} M samples/s')
     # per-launch-site breakdown (CUDA events recorded by the library)
     import ctypes
     from pytorch_drl_b200 import _lib

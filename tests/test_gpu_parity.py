@@ -408,13 +408,18 @@ def test_ppo_optimize_vs_reference_2rank_golden(golden_dir, precision, tag):
 
 
 # ---- RND predictor ---------------------------------------------------------------------------------------
-def test_rnd_learn_vs_reference_golden(golden_dir):
+# fp32 = CUDA-core engine (summation order only); bf16 = tcgen05 engine (bf16 operands incl. the normalised frame, fp32 accumulation)
+RND_TOL = {'fp32': dict(per=2e-4, loss=2e-4, grad=2e-4), 'bf16': dict(per=2e-2, loss=1e-2, grad=0.1)}     # 8-sample fixture: see TOL['bf16']
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_rnd_learn_vs_reference_golden(golden_dir, precision):
     """Predictor loss, per-sample intrinsic reward and student gradients against the UNMODIFIED
-    reference networks (tests/golden/rnd.npz) and the oracle, fp32 engine: rel-L2 <= 2e-4."""
+    reference networks (tests/golden/rnd.npz) and the oracle, for both engines (bars in RND_TOL)."""
     from pytorch_drl_b200.envs import RandomNetworkDistillation
     g = np.load(os.path.join(golden_dir, 'rnd.npz'))
     items, obs_u8 = ro.rnd_fixture_inputs()
-    rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=32, max_batch=16)
+    rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=32, max_batch=16, precision=precision)
     teacher, student = ro.init_net(False, 100), ro.init_net(True, 200)
     rnd.load({k: tc.from_numpy(v) for k, v in teacher.items()}, {k: tc.from_numpy(v) for k, v in student.items()})
     rnd.observe(cu(items))
@@ -424,19 +429,52 @@ def test_rnd_learn_vs_reference_golden(golden_dir):
         nz.update(it)
     loss_ref, per_ref, y_ref, yh_ref, grads_ref = ro.rnd_learn_loss_and_grads(teacher, student, nz, obs_u8)
     np.testing.assert_allclose(loss_ref, float(g['loss']), rtol=1e-5)
+    t = RND_TOL[precision]
     obs = cu(obs_u8)
     err = rnd.intrinsic_reward(obs).cpu().numpy()
-    np.testing.assert_allclose(err, g['per'], rtol=2e-4)
+    np.testing.assert_allclose(err, g['per'], rtol=t['per'])
     before = rnd.student_params.clone()
     rows = tc.arange(obs_u8.shape[0], device=dev(), dtype=tc.int64)
     loss = rnd.learn_rows(obs, rows)
-    np.testing.assert_allclose(float(loss.item()), float(g['loss']), rtol=2e-4)
+    np.testing.assert_allclose(float(loss.item()), float(g['loss']), rtol=t['loss'])
     gv = rnd.student_views(rnd.student_grads)
-    for k in ro.STUDENT_KEYS:
-        assert rel_l2(gv[k].cpu().numpy(), grads_ref[k]) < 2e-4, k
+    worst = {k: rel_l2(gv[k].cpu().numpy(), grads_ref[k]) for k in ro.STUDENT_KEYS}
+    assert max(worst.values()) < t['grad'], worst
     # one Adam step moved the student (lr 1e-4, first step = lr * sign)
     delta = (rnd.student_params - before).abs().max().item()
     assert 0.5e-4 < delta < 1.5e-4
+
+
+@pytest.mark.parametrize('nb', [1, 2, 7, 148, 297, 301])
+def test_rnd_bf16_engine_ragged_batches_vs_fp32_engine(nb):
+    """The tcgen05 RND engine packs sample PAIRS along the channels: odd batches (a phantom second sample), fewer pairs than
+    SMs, more than one pair per CTA, row-index gathers.  Rewards, loss and every student gradient tensor must agree with the
+    CUDA-core fp32 engine (itself checked against the reference golden); a second learn step checks the repacked weights."""
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
+    g = tc.Generator(device=dev())
+    g.manual_seed(500 + nb)
+    frames = tc.randint(0, 256, (nb + 5, 84, 84, 4), device=dev(), dtype=tc.uint8, generator=g)
+    rows = tc.randperm(nb + 5, device=dev(), generator=g)[:nb].contiguous()
+    items = tc.rand((6, 84, 84, 1), device=dev(), generator=g)
+    teacher, student = ro.init_net(False, 101), ro.init_net(True, 201)
+    out = {}
+    for precision in ('fp32', 'bf16'):
+        rnd = RandomNetworkDistillation({'lr': 1e-3, 'eps': 1e-5}, world_size=32, max_batch=nb, precision=precision)
+        rnd.load({k: tc.from_numpy(v) for k, v in teacher.items()}, {k: tc.from_numpy(v) for k, v in student.items()})
+        rnd.observe(items)
+        rnd._sync_normalizers_global(); rnd._sync_normalizers_local()
+        err = rnd.intrinsic_reward(frames, rows).cpu().numpy()
+        loss = float(rnd.learn_rows(frames, rows).item())
+        grads = {k: v.cpu().numpy().copy() for k, v in rnd.student_views(rnd.student_grads).items()}
+        loss2 = float(rnd.learn_rows(frames, rows).item())          # after one Adam step: exercises the operand repack
+        out[precision] = (err, loss, grads, loss2)
+    (e32, l32, g32, l32b), (e16, l16, g16, l16b) = out['fp32'], out['bf16']
+    np.testing.assert_allclose(e16, e32, rtol=3e-2)
+    np.testing.assert_allclose([l16, l16b], [l32, l32b], rtol=1e-2)
+    assert l32b < l32                                               # the step reduced the predictor loss
+    for k in g32:
+        assert np.isfinite(g16[k]).all(), k
+        assert rel_l2(g16[k], g32[k]) < (0.15 if nb < 16 else 8e-2), (nb, k, rel_l2(g16[k], g32[k]))     # single-digit batches: see TOL['bf16']
 
 
 def test_rnd_learn_wrapper_semantics():
