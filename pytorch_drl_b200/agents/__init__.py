@@ -6,6 +6,7 @@ from typing import Any, Callable, List, Mapping, Optional, Type
 import torch as tc
 
 from ..engine import LearnerEngine
+from ..utils.checkpoint import DDPShim  # noqa: F401
 from .dqn_heads import (MLP, DuelingArchitecture, EpsilonGreedyCategoricalPolicyHead, QAgent,  # noqa: F401
                         SimpleDiscreteActionValueHead)
 
@@ -185,6 +186,8 @@ class Agent(tc.nn.Module):
         self._require_engine().sync_params()
 
     def load_state_dict(self, state_dict, strict: bool = True):
+        from ..utils.checkpoint import strip_module_prefix
+        state_dict = strip_module_prefix(state_dict)       # checkpoints of the reference's DDP-wrapped Agent (launch.py:310)
         if self.engine is None:
             return super().load_state_dict(state_dict, strict)
         with tc.no_grad():

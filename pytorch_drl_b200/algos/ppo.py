@@ -106,6 +106,7 @@ class PPO:
         self._checkpoint_frequency, self._checkpoint_dir = checkpoint_frequency, checkpoint_dir
         self._log_dir, self._media_dir = log_dir, media_dir
         self._reward_weights = reward_weights
+        self._policy_net_wrapped = policy_net                           # what gets checkpointed (a DDPShim keeps the `module.` keys)
         self._policy_net = getattr(policy_net, 'module', policy_net)    # accept a DDP-style wrapper
         self._policy_optimizer, self._policy_scheduler = policy_optimizer, policy_scheduler
         self._standardize_adv = standardize_adv
@@ -116,6 +117,11 @@ class PPO:
         self._vf_loss_clipping, self._vf_simple_weighting = vf_loss_clipping, vf_simple_weighting
         self._envs_per_rank, self._comm = envs_per_rank, comm
         self._engine = self._policy_net._require_engine()
+        if policy_optimizer is not None:
+            # the fused Adam's flat state becomes the torch optimizer's `state` (views), so policy_optimizer.state_dict() is
+            # complete and a state loaded before construction (launch.py:377-383) or later is adopted (ppo.py:295-307)
+            from ..utils.checkpoint import bind_flat_adam
+            bind_flat_adam(self._engine, policy_optimizer, list(self._policy_net.parameters()))
         if comm is not None and hasattr(comm, 'attach') and getattr(comm, 'overlap', False):
             comm.attach(self._engine)                # opt-in: gradient exchange overlapped with the backward pass
         self._samplers = []
@@ -277,6 +283,47 @@ class PPO:
                 self.on_epoch_metrics(opt_epoch, m)
         if self._policy_scheduler:
             self._policy_scheduler.step()
+
+    # ---- the rest of Algo's surface (drl/algos/abstract.py:173-221, ppo.py:283-307) ---------------------------------------
+    @property
+    def checkpointables(self) -> Dict[str, Any]:
+        """What `persist` saves (ppo.py:295-307): the policy network (with the `module.` prefix if it was handed over wrapped),
+        its optimizer and scheduler, and the env wrappers' checkpointables."""
+        out = {'policy_net': self._policy_net_wrapped, 'policy_optimizer': self._policy_optimizer,
+               'policy_scheduler': self._policy_scheduler, 'value_net': None, 'value_optimizer': None, 'value_scheduler': None}
+        w = self._env
+        while w is not None:                         # every wrapper of the chain (a reference wrapper already merges its inner ones)
+            for k, v in (getattr(w, 'checkpointables', None) or {}).items():
+                out.setdefault(k, v)
+            w = getattr(w, 'env', None)
+        return out
+
+    def collect(self):
+        """abstract.py:173-186.  Env stepping is the actor's side (out of scope): a caller supplies
+        `rollout_source()` -> (RolloutStorage dict with frames / actions / rewards / dones filled, metadata); annotate and
+        credit assignment run here, on the device."""
+        src = getattr(self, 'rollout_source', None)
+        if src is None:
+            raise NotImplementedError('set algo.rollout_source = callable returning (rollout, metadata): the fused path replaces '
+                                      'the learner half; env stepping stays with the reference\'s RolloutManager')
+        rollout, metadata = src()
+        rollout = self.credit_assignment(self.annotate(rollout))
+        self._global_step += self._world_size * self._envs_per_rank * self._rollout_len        # abstract.py:185
+        return rollout, metadata
+
+    def persist(self, metadata: Optional[Mapping[str, Any]] = None) -> None:
+        """ppo.py:283-307 without the tensorboard writer: rank 0 saves every checkpointable at multiples of
+        checkpoint_frequency in the reference's file format."""
+        if self._rank == 0 and self._checkpoint_dir and self._global_step % self._checkpoint_frequency == 0:
+            from ..utils.checkpoint import save_checkpoints
+            save_checkpoints(self._checkpoint_dir, self.checkpointables, self._global_step)
+
+    def training_loop(self) -> None:
+        """abstract.py:211-221."""
+        while self._global_step < self._max_steps:
+            rollout, metadata = self.collect()
+            self.optimize(rollout)
+            self.persist(metadata)
 
     def _update_trainable_wrappers(self, minibatch) -> None:
         """drl/algos/common/wrapper_ops.py:9-25."""

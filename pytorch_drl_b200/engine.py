@@ -159,7 +159,11 @@ class LearnerEngine:
         return total
 
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-5, grad_scale: float = 1.0) -> None:
+        from .utils import checkpoint
+        checkpoint.check_flat_adam_binding(self)       # a torch optimizer bound to this state may have been re-loaded
         self.adam_steps += 1
+        if getattr(self, '_bound_opt', None) is not None:
+            self._bound_opt[2].fill_(float(self.adam_steps))
         check(self._L.drl_net_adam_step(self._h, ptr(self.params), ptr(self.grads), ptr(self.exp_avg),
                                         ptr(self.exp_avg_sq), lr, betas[0], betas[1], eps, self.adam_steps,
                                         grad_scale, current_stream()), 'adam_step')

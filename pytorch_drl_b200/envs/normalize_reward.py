@@ -72,11 +72,15 @@ class BatchedRewardNormalizer:
         self.moment2.fill_(self.synced[2])
 
     @property
-    def checkpointables(self) -> Dict[str, Dict[str, tc.Tensor]]:
-        """The reference checkpoints the synchronised ReturnAcc's Normalizer buffers (:158-162)."""
-        s = self.synced.detach().cpu()
-        return {'reward_normalizer': {'_normalizer._steps': s[0].clone(), '_normalizer._moment1': s[1].clone(),
-                                      '_normalizer._moment2': s[2].clone()}}
+    def checkpointables(self):
+        """The reference checkpoints the synchronised ReturnAcc's Normalizer buffers (:158-162): an object with
+        state_dict() / load_state_dict() under the same keys."""
+        from ..utils.checkpoint import DictCheckpointable
+
+        def get():
+            s = self.synced.detach().cpu()
+            return {'_normalizer._steps': s[0].clone(), '_normalizer._moment1': s[1].clone(), '_normalizer._moment2': s[2].clone()}
+        return {'reward_normalizer': DictCheckpointable(get, self.load_checkpointables)}
 
     def load_checkpointables(self, sd: Dict[str, tc.Tensor]) -> None:
         vals = [float(sd['_normalizer._steps']), float(sd['_normalizer._moment1']), float(sd['_normalizer._moment2'])]

@@ -105,8 +105,17 @@ class RandomNetworkDistillation:
 
     @property
     def checkpointables(self):
-        return {'rnd_observation_normalizer': self._synced_normalizer, 'rnd_teacher_net': self.teacher_views(),
-                'rnd_student_net': self.student_views()}
+        """random_network_distillation.py:175-184: objects with state_dict() / load_state_dict() under the reference's key
+        names (the networks are DDP-wrapped there: `module.` prefix; the optimizer is a torch.optim.Adam state_dict)."""
+        from ..utils.checkpoint import FlatAdamCheckpointable, ViewsCheckpointable
+
+        def set_steps(n):
+            self.adam_steps = n
+        return {'rnd_observation_normalizer': self._synced_normalizer,
+                'rnd_teacher_net': ViewsCheckpointable(self.teacher_views, 'module.', self._bind),
+                'rnd_student_net': ViewsCheckpointable(self.student_views, 'module.', self._bind),
+                'rnd_optimizer': FlatAdamCheckpointable(STUDENT_SHAPES, self.exp_avg, self.exp_avg_sq, lambda: self.adam_steps,
+                                                        set_steps, lambda: self._opt)}
 
     # ---- actor side, batched ----------------------------------------------------------------------------
     def intrinsic_reward(self, frames_u8: tc.Tensor, row_idx: Optional[tc.Tensor] = None) -> tc.Tensor:

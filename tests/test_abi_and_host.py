@@ -215,3 +215,92 @@ def test_state_dicts_round_trip_with_the_real_reference_modules():
     assert list(rq.state_dict().keys()) == list(mq.state_dict().keys())
     mq.load_state_dict(rq.state_dict(), strict=True)
     rq.load_state_dict(mq.state_dict(), strict=True)
+
+
+def test_checkpoint_objects_round_trip_through_the_reference_checkpointing(tmp_path):
+    """f2 / f3 against the UNMODIFIED reference (skipped where it is not mounted): the checkpointables the fused path hands to
+    `save_checkpoints` (drl/utils/checkpointing.py:119-143; ppo.py:295-307; random_network_distillation.py:175-184) load into
+    the reference's own DDP-wrapped networks and torch.optim.Adam with `maybe_load_checkpoints` (:85-117), and files written
+    from the reference's objects load back — same kinds, same keys (incl. the `module.` prefix), same tensors."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not mounted')
+    ref_loader.load()
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from drl.utils.checkpointing import save_checkpoints as ref_save, maybe_load_checkpoints as ref_load
+    from drl.envs.wrappers.stateful.intrinsic.random_network_distillation import _StudentNetwork, _TeacherNetwork
+    from drl.envs.wrappers.stateful.normalize_reward import ReturnAcc
+    from pytorch_drl_b200.envs.rnd import STUDENT_KEYS, STUDENT_SHAPES, TEACHER_KEYS, TEACHER_SHAPES, _views
+    from pytorch_drl_b200.utils import checkpoint as ck
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ['MASTER_PORT'] = '29731'
+        dist.init_process_group('gloo', rank=0, world_size=1)
+        created = True
+    try:
+        tc.manual_seed(5)
+        # ---- reference objects with some training history
+        r_student, r_teacher = DDP(_StudentNetwork([84, 84, 1], 1)), DDP(_TeacherNetwork([84, 84, 1]))
+        r_opt = tc.optim.Adam(r_student.parameters(), lr=1e-4, eps=1e-5)
+        for _ in range(3):
+            r_opt.zero_grad()
+            r_student(tc.randn(2, 84, 84, 1)).square().mean().backward()
+            r_opt.step()
+        # ---- mine: flat buffers presented through the checkpointables
+        n_s = sum(int(np.prod(s)) for s in STUDENT_SHAPES)
+        n_t = sum(int(np.prod(s)) for s in TEACHER_SHAPES)
+        flat_s, flat_t, m, v = tc.zeros(n_s), tc.zeros(n_t), tc.zeros(n_s), tc.zeros(n_s)
+        steps = {'n': 0}
+        mine = {'rnd_student_net': ck.ViewsCheckpointable(lambda: _views(flat_s, STUDENT_KEYS, STUDENT_SHAPES)),
+                'rnd_teacher_net': ck.ViewsCheckpointable(lambda: _views(flat_t, TEACHER_KEYS, TEACHER_SHAPES)),
+                'rnd_optimizer': ck.FlatAdamCheckpointable(STUDENT_SHAPES, m, v, lambda: steps['n'],
+                                                           lambda n: steps.__setitem__('n', n),
+                                                           lambda: dict(lr=1e-4, betas=(0.9, 0.999), eps=1e-5))}
+        ref = {'rnd_student_net': r_student, 'rnd_teacher_net': r_teacher, 'rnd_optimizer': r_opt}
+        # reference -> files -> mine (my own loader and the reference's loader agree)
+        d1 = str(tmp_path / 'from_ref')
+        ref_save(d1, ref, steps=128)
+        assert ref_load(d1, mine, 'cpu', None) == 128
+        assert ck.maybe_load_checkpoints(d1, mine) == 128
+        assert list(mine['rnd_student_net'].state_dict().keys()) == list(r_student.state_dict().keys())
+        for k, t in r_student.state_dict().items():
+            assert tc.equal(mine['rnd_student_net'].state_dict()[k], t)
+        assert steps['n'] == 3
+        for i, p in enumerate(r_student.parameters()):
+            assert tc.equal(mine['rnd_optimizer'].state_dict()['state'][i]['exp_avg'], r_opt.state[p]['exp_avg'])
+        # mine -> files -> fresh reference objects
+        d2 = str(tmp_path / 'from_mine')
+        ck.save_checkpoints(d2, mine, steps=256)
+        f_student, f_teacher = DDP(_StudentNetwork([84, 84, 1], 1)), DDP(_TeacherNetwork([84, 84, 1]))
+        f_opt = tc.optim.Adam(f_student.parameters(), lr=1e-4, eps=1e-5)
+        assert ref_load(d2, {'rnd_student_net': f_student, 'rnd_teacher_net': f_teacher, 'rnd_optimizer': f_opt}, 'cpu', None) == 256
+        for (k, a), (_, b) in zip(f_student.state_dict().items(), r_student.state_dict().items()):
+            assert tc.equal(a, b), k
+        for p, q in zip(f_student.parameters(), r_student.parameters()):
+            assert tc.equal(f_opt.state[p]['exp_avg_sq'], r_opt.state[q]['exp_avg_sq']) and float(f_opt.state[p]['step']) == 3
+        # the resumed reference optimizer continues exactly like the original
+        x = tc.randn(2, 84, 84, 1)
+        for net, opt in ((r_student, r_opt), (f_student, f_opt)):
+            opt.zero_grad()
+            net(x).square().mean().backward()
+            opt.step()
+        for a, b in zip(f_student.parameters(), r_student.parameters()):
+            assert tc.equal(a, b)
+        # misaligned steps raise like the reference (checkpointing.py:114-116)
+        ck.save_checkpoints(d2, {'rnd_teacher_net': mine['rnd_teacher_net']}, steps=512)
+        with pytest.raises(RuntimeError):
+            ck.maybe_load_checkpoints(d2, mine)
+        # policy network: the fused Agent under a DDPShim has the keys of the reference's DDP(Agent)
+        w = lambda t: tc.nn.init.orthogonal_(t, gain=2 ** 0.5)       # noqa: E731
+        ag = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4, w, tc.nn.init.zeros_),
+                          {'policy': agents.CategoricalPolicyHead(512, 6), 'value_extrinsic': agents.SimpleValueHead(512)})
+        keys = list(agents.DDPShim(ag).state_dict().keys())
+        assert all(k.startswith('module.') for k in keys) and keys[0] == 'module._architecture._network.0.weight'
+        ag.load_state_dict(agents.DDPShim(ag).state_dict())          # the prefixed form loads into the plain Agent
+        # reward normaliser keys
+        assert set(ReturnAcc(0.99, -10, 10, True).state_dict().keys()) == {'_normalizer._steps', '_normalizer._moment1', '_normalizer._moment2'}
+    finally:
+        if created:
+            dist.destroy_process_group()

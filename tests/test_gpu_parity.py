@@ -652,7 +652,8 @@ def test_error_behaviour_matches_reference_conventions():
     h = ctypes.c_void_p()
     assert L.drl_net_create(ctypes.byref(h), 0, 0, 6, 1, 1) == 1                  # max_batch 0: bad shape
     assert L.drl_net_create(ctypes.byref(h), 99, 64, 6, 1, 1) == 5                # no such device: NO_DEVICE, not a fallback
-    assert L.drl_rnd_create(ctypes.byref(h), 0, 64, 1, 1) == 6                    # bf16 RND: UNSUPPORTED, loudly
+    assert L.drl_rnd_create(ctypes.byref(h), 0, 64, 2, 1) == 6                    # RND widening != 1: UNSUPPORTED, loudly
+    assert L.drl_rnd_create(ctypes.byref(h), 0, 64, 1, 7) == 2                    # unknown precision: bad argument
     eng = LearnerEngine(6, ['value_extrinsic'], 8, 'bf16')
     obs = tc.zeros((16, 84, 84, 4), dtype=tc.uint8, device=dev())
     logits, values = tc.empty((16, 6), device=dev()), tc.empty((16, 1), device=dev())
@@ -993,3 +994,102 @@ def test_qagent_trunk_features_and_dueling_q_vs_oracle(precision, golden_dir):
     # float32 frames pre-scaled by 1/255 (the reference's rollout format) map back to the same bytes
     out2 = qa(po.scale_obs(tc.from_numpy(obs)).to(dev()), ['action_value'])
     np.testing.assert_array_equal(out2['action_value'].cpu().numpy(), q)
+
+
+# ---- checkpoint / resume: complete optimizer + RND state in the reference's formats --------------------
+def _ppo_for_resume(precision, seed=0):
+    from pytorch_drl_b200 import agents, algos
+    A, rk, T, B, n_envs = 6, ['extrinsic'], 16, 8, 2
+    agent = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4),
+                         {'policy': agents.CategoricalPolicyHead(512, A), 'value_extrinsic': agents.SimpleValueHead(512)})
+    agent.load_state_dict({k: tc.from_numpy(v) for k, v in po.init_params(A, rk, 11).items()})
+    agent.fuse(max_batch=n_envs * (T + 1), precision=precision)
+    opt = tc.optim.Adam(agent.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5)
+    sched = tc.optim.lr_scheduler.LambdaLR(opt, lambda e: 1.0 / (1 + e))
+
+    def make_algo(global_step=1):
+        return algos.PPO(rank=0, world_size=1, rollout_len=T, extra_steps=0,
+                         credit_assignment_ops={'extrinsic': algos.GAE(gamma=0.99, use_dones=True, lambda_=0.95)},
+                         global_step=global_step, max_steps=10 ** 9, policy_net=agents.DDPShim(agent), policy_optimizer=opt,
+                         policy_scheduler=sched, opt_epochs=2, learner_batch_size=B, envs_per_rank=n_envs, sampler_seed=seed)
+
+    def rollout(i):
+        st = algos.RolloutStorage(n_envs, T, rk, dev())
+        for r in range(n_envs):
+            raw = po.make_synthetic_env_rollout(r, 100 + i, T, A, rk)
+            st.load_env(r, raw['observations'], raw['actions'], raw['rewards'], raw['dones'])
+        return st.as_dict()
+    return agent, opt, sched, make_algo, rollout
+
+
+def test_checkpoint_resume_continues_the_trajectory(tmp_path):
+    """Adam moments / step count live in the engine's flat buffers but are exposed as the torch optimizer's `state`, so the
+    reference's persist / resume protocol (ppo.py:295-307, launch.py:377-383: load_state_dict on nets + optimizers BEFORE the
+    algorithm is built) carries the complete state: a resumed run continues like the uninterrupted one.  Also: the policy net
+    is saved under DDP's `module.` keys, and `optimizer.load_state_dict` in the middle of a run is adopted."""
+    from pytorch_drl_b200.utils import checkpoint as ck
+    agent, opt, sched, make_algo, rollout = _ppo_for_resume('fp32')
+    algo = make_algo()
+    algo.optimize(algo.credit_assignment(algo.annotate(rollout(0))))
+    import copy
+    sd = copy.deepcopy(opt.state_dict())          # state_dict() hands out the live (aliasing) tensors, like torch's own
+    assert len(sd['state']) == 12 and float(sd['state'][0]['step']) == 4.0          # 2 epochs x 16 / 8 steps
+    eng = agent.engine
+    assert tc.equal(sd['state'][6]['exp_avg'].reshape(-1), eng.exp_avg[eng.offsets[6]:eng.offsets[7]])
+    ckdir = str(tmp_path / 'ck')
+    ck.save_checkpoints(ckdir, algo.checkpointables, steps=32)
+    assert sorted(os.listdir(ckdir)) == ['policy_net_32.pth', 'policy_optimizer_32.pth', 'policy_scheduler_32.pth']
+    assert all(k.startswith('module.') for k in tc.load(os.path.join(ckdir, 'policy_net_32.pth')))
+    # uninterrupted continuation
+    algo.optimize(algo.credit_assignment(algo.annotate(rollout(1))))
+    want = {k: v.detach().clone() for k, v in agent.state_dict().items()}
+    want_lr = opt.param_groups[0]['lr']
+    # resumed: fresh objects, checkpoint loaded before the algorithm is built (the reference's order)
+    agent2, opt2, sched2, make_algo2, _ = _ppo_for_resume('fp32')
+    from pytorch_drl_b200 import agents
+    loaded = ck.maybe_load_checkpoints(ckdir, {'policy_net': agents.DDPShim(agent2), 'policy_optimizer': opt2,
+                                               'policy_scheduler': sched2}, map_location='cpu')
+    assert loaded == 32
+    algo2 = make_algo2(global_step=1)
+    assert agent2.engine.adam_steps == 4
+    # same permutation stream as the uninterrupted run's second optimize: replay the first call's draws
+    for s in algo2._samplers:
+        for _ in range(2):
+            s.resample()
+    algo2.optimize(algo2.credit_assignment(algo2.annotate(rollout(1))))
+    assert abs(opt2.param_groups[0]['lr'] - want_lr) < 1e-12
+    for k, v in agent2.state_dict().items():
+        assert rel_l2(v.cpu().numpy(), want[k].cpu().numpy()) < 1e-5, k
+    # mid-run load_state_dict on the live optimizer: the engine adopts it at its next step
+    opt2.load_state_dict(sd)
+    algo2.learner_step(__import__('pytorch_drl_b200').utils.MinibatchView(
+        algo2.credit_assignment(algo2.annotate(rollout(2))), tc.arange(16, device=dev(), dtype=tc.int64)))
+    assert agent2.engine.adam_steps == 5 and float(opt2.state_dict()['state'][0]['step']) == 5.0
+
+
+def test_rnd_checkpointables_restore_the_predictor(tmp_path):
+    """random_network_distillation.py:175-184: normaliser, teacher, student and optimizer round-trip through files; the restored
+    wrapper gives the same intrinsic reward and takes the same next predictor step."""
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
+    from pytorch_drl_b200.utils import checkpoint as ck
+    g = tc.Generator(device=dev())
+    g.manual_seed(1)
+    frames = tc.randint(0, 256, (24, 84, 84, 4), device=dev(), dtype=tc.uint8, generator=g)
+    rows = tc.arange(24, device=dev(), dtype=tc.int64)
+    a = RandomNetworkDistillation({'lr': 1e-3, 'eps': 1e-5}, world_size=32, max_batch=24, seed=3)
+    a.observe(tc.rand((5, 84, 84, 1), device=dev(), generator=g))
+    a._sync_normalizers_global(); a._sync_normalizers_local()
+    for _ in range(3):
+        a.learn_rows(frames, rows)
+    d = str(tmp_path / 'rnd')
+    ck.save_checkpoints(d, a.checkpointables, steps=7)
+    assert sorted(os.listdir(d)) == ['rnd_observation_normalizer_7.pth', 'rnd_optimizer_7.pth', 'rnd_student_net_7.pth', 'rnd_teacher_net_7.pth']
+    assert list(tc.load(os.path.join(d, 'rnd_student_net_7.pth')).keys())[0] == 'module._network.0._network.1.weight'
+    b = RandomNetworkDistillation({'lr': 1e-3, 'eps': 1e-5}, world_size=32, max_batch=24, seed=99)
+    assert ck.maybe_load_checkpoints(d, b.checkpointables) == 7
+    b._sync_normalizers_local()
+    assert b.adam_steps == 3 and b._synced_normalizer.steps == 5.0
+    np.testing.assert_allclose(b.intrinsic_reward(frames).cpu().numpy(), a.intrinsic_reward(frames).cpu().numpy(), rtol=1e-6)
+    la, lb = float(a.learn_rows(frames, rows).item()), float(b.learn_rows(frames, rows).item())
+    assert abs(la - lb) <= 1e-6 * abs(la)
+    assert rel_l2(b.student_params.cpu().numpy(), a.student_params.cpu().numpy()) < 1e-6
