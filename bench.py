@@ -2,15 +2,25 @@
 """bench.py — PPO update samples/sec on synthetic 84x84x4 rollouts (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
 
 A "step" is one learner step of PPO.optimize (drl/algos/ppo.py:246-257): gather a minibatch of
 B samples from each env of the GPU, NatureCNN forward, fused losses, backward, gradient
 all-reduce across GPUs, Adam.  Workload at N=1: BASELINE config[1] — 1024 envs x 128 steps per
 GPU, B=32 per env => 32 768 samples per step per GPU (weak scaling: every GPU owns 1024 envs).
-Rank 0 prints ONE JSON line (see the keys in `main`).
+Rank 0 prints ONE JSON line:
+  value      device-resident learner steps (frames already in HBM), CUDA events, max over ranks
+  sustained  the same steps for ~1 s (power-capped clocks) — the training rate; `roofline.step` is computed from it
+  e2e        whole `PPO.optimize_host` calls: the uint8 rollout is uploaded from pinned host memory once per call
+             (chunked, overlapped with the annotate forward), then GAE, opt_epochs x T/B learner steps, the per-epoch
+             metrics passes and the device-to-host read of the metrics — the same work the reference arm times
+  roofline   dominant kernel (per-launch CUDA events inside the timed region) + `step`: whole-step tensor roofline
+  extras     (N=1) the other BASELINE configs and side measurements: config0 (8 envs), config3 (RND + PPO), sweep
+             (4k..64k samples per step), optimize_call, precision modes, GAE / loss / sum-tree
+  allreduce_check (N>1) the bucketed gradient all-reduce and the 5-float metrics mean verified against all-gather + sum
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -39,6 +49,7 @@ BYTES = {  # algorithmic HBM bytes per sample: operands read onc
     'fc_fwd': 6272 + 2048, 'fc_dgrad': 1024 + 6272, 'fc_wgrad': 6272 + 1024,
 }
 STEP_FLOPS_PER_SAMPLE = 49525760          # fwd 18.69 + bwd 30.83 MFLOP (A=6, K=1), SURVEY §8d
+RND_FLOPS_PER_SAMPLE = 16.61e6            # teacher fwd + student fwd + student bwd, SURVEY §8d
 
 
 def peaks():
@@ -104,12 +115,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_steps: int = 2000, steps=None):
+# CPU side: the reference's own implementation (oracle/_ref, vendored at build time) or the oracle port
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_steps: int = 2000, steps=None):
     """Times the CPU restatement of the reference's learner step (oracle port: torch-CPU fp32 autograd
     through the same conv/linear/Adam ops the reference calls, all host threads) on a bounded sample:
-    `n_envs` ranks x B samples per step.  Returns (samples/s, steps, threads)."""
+    `n_envs` ranks x B samples per step.  Returns (samples/s, steps, threads, seconds)."""
     from oracle import ppo_oracle as po
-    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must still use all the host threads it can
     tc.set_num_threads(max(1, os.cpu_count() or 1))
     rs = np.random.RandomState(0)
     params = po.init_params(A, REWARD_KEYS, seed=11)
@@ -147,28 +159,104 @@ def cpu_reference_step_rate(n_envs: int, seconds: float, warmup: int = 1, max_st
     return n * n_envs * B / el, n, tc.get_num_threads(), el
 
 
+def cpu_baseline(seconds: float, warmup: int = 1, steps=None):
+    """The reference's CPU path on this host: the UNMODIFIED reference when a copy travels with the repository (oracle/_ref),
+    else the oracle port.  Returns the `cpu_baseline` object of the JSON line."""
+    from oracle import ref_bench
+    if ref_bench.reference_root() is not None:
+        n = steps if steps is not None else max(2, int(seconds / 1.0))
+        port = 20000 + (os.getpid() % 20000)
+        r = ref_bench.run(warmup, n, T=T, B=B, A=A, epochs=3, port=port)
+        return {'value': r['rate'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'reference', 'seconds': r['seconds'],
+                'steps': r['steps'],
+                'sample': f"{r['steps']} x (annotate + credit_assignment + PPO.optimize) of the unmodified reference: {r['world']} gloo "
+                          f"ranks (envs) x {r['threads_per_rank']} threads, T={T}, B={B}, 3 epochs incl. the per-epoch metrics "
+                          f"passes = {r['samples_per_step']} update samples per step; os.cpu_count={os.cpu_count()}, torch {r['torch']}"}
+    rate, n, threads, el = cpu_port_step_rate(8, seconds, warmup=warmup, steps=steps)
+    return {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port', 'seconds': el, 'steps': n,
+            'sample': f'{n} learner steps of 8 envs x {B} samples (oracle port of the reference CPU path, torch-CPU fp32, '
+                      f'os.cpu_count={os.cpu_count()}; no copy of the reference under oracle/_ref)'}
+
+
 def run_reference(args, rank):
-    """`--impl reference`: the reference's own CPU implementation of the path is pure PyTorch-CPU
-    Python that cannot travel to the GPU box (/root/reference is absent there and gym/moviepy are not
-    installable), so the arm times the oracle port — pinned to the reference by tests/golden — on all
-    host threads.  One step = one learner step over a bounded sample (8 ranks x 32 samples, the
-    reference's own CPU-runnable shape)."""
+    """`--impl reference`: rank 0 times the reference's own CPU implementation with all host threads; other ranks exit."""
     if rank != 0:
         return
-    n_envs = 8
-    rate, n, threads, el = cpu_reference_step_rate(n_envs, 0.0, warmup=max(1, args.warmup), steps=args.steps)
+    cb = cpu_baseline(0.0, warmup=max(1, min(args.warmup, 2)), steps=max(1, args.steps))
     line = {
-        'impl': 'reference', 'metric': 'PPO update samples/sec (84x84x4 frames)', 'value': rate, 'unit': 'samples/s',
-        'n_gpus': args.gpus, 'steps': n, 'warmup': max(1, args.warmup), 'ms_per_step': 1e3 * el / n,
+        'impl': 'reference', 'metric': 'PPO update samples/sec (84x84x4 frames)', 'value': cb['value'], 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': cb['steps'], 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': 1e3 * cb['seconds'] / cb['steps'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'PPO NatureCNN synthetic 84x84x4 rollout, 1024 envs x 128 steps, B=32 per env',
-                   'sample': f'{n_envs} envs x {B} samples per step on the host CPU'},
-        'cpu_baseline': {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{n} learner steps of {n_envs} envs x {B} samples (oracle port, torch-CPU fp32)'},
-        'e2e': {'value': rate, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                   'sample': cb['sample']},
+        'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------
+def make_agent(num_actions, reward_keys, max_batch, precision, dev):
+    from pytorch_drl_b200 import agents
+    o2, o01 = (lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5)), (lambda w: tc.nn.init.orthogonal_(w, gain=0.01))
+    preds = {'policy': agents.CategoricalPolicyHead(512, num_actions, w_init=o01, b_init=tc.nn.init.zeros_)}
+    for k in reward_keys:
+        preds[f'value_{k}'] = agents.SimpleValueHead(512, w_init=o01, b_init=tc.nn.init.zeros_)
+    agent = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4, o2, tc.nn.init.zeros_), preds)
+    agent.fuse(max_batch=max_batch, precision=precision, device=dev)
+    return agent
+
+
+def fill_synthetic(d, st, n_envs, num_actions, reward_keys, dev, seed, obs=True):
+    """SURVEY §8d synthetic inputs, generated on the device."""
+    g = tc.Generator(device=dev)
+    g.manual_seed(seed)
+    if obs:
+        for e0 in range(0, n_envs, 64):
+            e1 = min(n_envs, e0 + 64)
+            d['observations'][e0:e1] = tc.randint(0, 256, (e1 - e0, st.Tp, 84, 84, 4), device=dev, dtype=tc.uint8, generator=g)
+    d['actions'][:] = tc.randint(0, num_actions, (n_envs, st.Tp), device=dev, generator=g)
+    for k in reward_keys:
+        if k == 'extrinsic':
+            d['rewards'][k][:] = tc.randint(-1, 2, (n_envs, st.Tp), device=dev, generator=g).float()
+        else:
+            d['rewards'][k][:] = tc.rand((n_envs, st.Tp), device=dev, generator=g)
+    d['dones'][:] = (tc.rand((n_envs, st.Tp), device=dev, generator=g) < 0.01).float()
+
+
+def timed(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    tc.cuda.synchronize()
+    e0, e1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    tc.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+class SiteProfile:
+    """Per-launch-site CUDA-event times recorded by the library (drl_profile_*)."""
+
+    def __init__(self, L):
+        self.L = L
+        self.nbuf = ctypes.create_string_buffer(48 * 96)
+        self.ms, self.cnt, self.ns = (ctypes.c_float * 96)(), (ctypes.c_int * 96)(), ctypes.c_int()
+
+    def start(self):
+        self.L.drl_profile_enable(1)
+        self.L.drl_profile_read(96, self.nbuf, self.ms, self.cnt, ctypes.byref(self.ns))
+
+    def stop(self):
+        self.L.drl_profile_read(96, self.nbuf, self.ms, self.cnt, ctypes.byref(self.ns))
+        self.L.drl_profile_enable(0)
+        return {self.nbuf.raw[48 * i:48 * i + 48].split(b'\0')[0].decode(): (self.ms[i] / max(1, self.cnt[i]), self.cnt[i])
+                for i in range(self.ns.value)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -184,8 +272,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-sustained', action='store_true', help='skip the ~1 s power-capped leg')
-    ap.add_argument('--no-extras', action='store_true', help='skip the GAE / loss / metrics-pass / sum-tree side measurements')
-    ap.add_argument('--debug-flags', default='', help='kernel-variant experiments, e.g. "2=1,3=0" (drl_debug_set)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the other configs / side measurements')
+    ap.add_argument('--debug-flags', default='', help='kernel-variant experiments, e.g. "6=1,7=3" (drl_debug_set)')
     ap.add_argument('--comm', default='nccl', choices=['p2p-overlap', 'p2p', 'p2p-1', 'nccl-overlap', 'nccl', 'nccl-1'],
                     help='gradient exchange variant at N > 1: NCCL or NVLink peer-memory kernels, after the backward pass (2 buckets / -1: one) or overlapped with it')
     args = ap.parse_args()
@@ -200,7 +288,7 @@ def main():
     assert args.warmup >= 3 or args.steps <= 2, 'timing rule: W >= 3'
 
     import torch.distributed as dist
-    from pytorch_drl_b200 import _lib, agents, algos
+    from pytorch_drl_b200 import _lib, algos
     from pytorch_drl_b200.comm import Communicator
     from pytorch_drl_b200.utils.nested import MinibatchView
     tc.cuda.set_device(local_rank)
@@ -214,15 +302,12 @@ def main():
         L.drl_debug_set(int(k), int(v))
     n_envs = args.envs
     nb = n_envs * B
+    extras_on = world == 1 and not args.no_extras
+    max_batch = max(nb, 65536) if extras_on else nb         # the sweep goes up to 64k samples per step
 
     # ---- model + algo through the public drop-in API ----
     tc.manual_seed(0)
-    agent = agents.Agent(
-        [agents.ToChannelMajor()],
-        agents.NatureCNN(4, lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5), tc.nn.init.zeros_),
-        {'policy': agents.CategoricalPolicyHead(512, A, w_init=lambda w: tc.nn.init.orthogonal_(w, gain=0.01), b_init=tc.nn.init.zeros_),
-         'value_extrinsic': agents.SimpleValueHead(512, w_init=lambda w: tc.nn.init.orthogonal_(w, gain=0.01), b_init=tc.nn.init.zeros_)})
-    agent.fuse(max_batch=nb, precision=args.precision, device=dev)
+    agent = make_agent(A, REWARD_KEYS, max_batch, args.precision, dev)
     opt = tc.optim.Adam(agent.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-5)
     comm = None
     if world > 1:
@@ -239,17 +324,11 @@ def main():
     # ---- synthetic rollout, generated on the device; annotate + GAE through the API ----
     st = algos.RolloutStorage(n_envs, T, REWARD_KEYS, dev)
     d = st.as_dict()
-    g = tc.Generator(device=dev)
-    g.manual_seed(10000 * rank)
-    chunk = 64
-    for e0 in range(0, n_envs, chunk):
-        e1 = min(n_envs, e0 + chunk)
-        d['observations'][e0:e1] = tc.randint(0, 256, (e1 - e0, st.Tp, 84, 84, 4), device=dev, dtype=tc.uint8, generator=g)
-    d['actions'][:] = tc.randint(0, A, (n_envs, st.Tp), device=dev, generator=g)
-    d['rewards']['extrinsic'][:] = tc.randint(-1, 2, (n_envs, st.Tp), device=dev, generator=g).float()
-    d['dones'][:] = (tc.rand((n_envs, st.Tp), device=dev, generator=g) < 0.01).float()
+    fill_synthetic(d, st, n_envs, A, REWARD_KEYS, dev, 10000 * rank)
     rollout = algo.credit_assignment(algo.annotate(d))
     tc.cuda.synchronize()
+
+    allreduce_check = run_allreduce_check(comm, agent.engine, dev, rank, world) if world > 1 else None
 
     rs = np.random.RandomState(1234 + rank)
 
@@ -259,11 +338,19 @@ def main():
 
     total_steps = args.warmup + args.steps
     rows_list = [step_rows() for _ in range(total_steps)]
+    hyper, batch = algo._hyper(), algo._batch(rollout)
 
     def barrier():
         if world > 1:
             dist.barrier()
         tc.cuda.synchronize()
+
+    def allmax(x):
+        if world > 1:
+            t = tc.tensor([x], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
     # ---- device-resident timing (value) ----
     clocks = ClockSampler(local_rank) if rank == 0 else None     # started early: nvidia-smi needs ~0.2 s to its first sample
@@ -271,43 +358,28 @@ def main():
         clocks.wait_ready()
     t_warm0 = time.time()
     for i in range(args.warmup):
-        algo.learner_step(MinibatchView(rollout, rows_list[i]))
+        algo.learner_step(MinibatchView(rollout, rows_list[i]), hyper, batch)
     barrier()
-    L.drl_profile_enable(1)
-    names = (b'\0' * (48 * 64))
-    import ctypes
-    nbuf = ctypes.create_string_buffer(48 * 64)
-    ms = (ctypes.c_float * 64)()
-    cnt = (ctypes.c_int * 64)()
-    ns = ctypes.c_int()
-    L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))       # clear
+    prof = SiteProfile(L)
+    prof.start()
     launches0 = L.drl_launch_count()
     ev0, ev1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
     for i in range(args.steps):
-        algo.learner_step(MinibatchView(rollout, rows_list[args.warmup + i]))
+        algo.learner_step(MinibatchView(rollout, rows_list[args.warmup + i]), hyper, batch)
     ev1.record()
     barrier()
     t_wall1 = time.time()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = allmax(ev0.elapsed_time(ev1))
     launches = L.drl_launch_count() - launches0
-    L.drl_profile_read(64, nbuf, ms, cnt, ctypes.byref(ns))       # per-launch-site CUDA-event times of the timed region
-    L.drl_profile_enable(0)
-    sites = {}
-    for i in range(ns.value):
-        nm = nbuf.raw[48 * i:48 * i + 48].split(b'\0')[0].decode()
-        sites[nm] = (ms[i] / max(1, cnt[i]), cnt[i])
-    if world > 1:
-        t = tc.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    sites = prof.stop()                                            # per-launch-site CUDA-event times of the timed region
     ms_per_step = elapsed_ms / args.steps
     value = nb * world / (ms_per_step * 1e-3)
     clk = clocks.stop(t_wall0, t_wall1, [(t_warm0, t_wall0)]) if clocks else None
 
     # ---- the same steps for ~1 s: the board reaches its power cap and lowers the SM clock (MEASURED_PEAKS.json's
-    #      "sustained" regime); reported beside `value`, which is the short run at full clocks ----
+    #      "sustained" regime): the training rate ----
     sustained = None
     if not args.no_sustained:
         n_sus = max(args.steps, int(1000.0 / ms_per_step))       # same count on every rank (ms_per_step is the max over ranks)
@@ -319,22 +391,18 @@ def main():
         tw0 = time.time()
         s0.record()
         for i in range(n_sus):
-            algo.learner_step(MinibatchView(rollout, rows_list[args.warmup + i % args.steps]))
+            algo.learner_step(MinibatchView(rollout, rows_list[args.warmup + i % args.steps]), hyper, batch)
         s1.record()
         barrier()
         tw1 = time.time()
-        el = s0.elapsed_time(s1)
-        if world > 1:
-            t = tc.tensor([el], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            el = float(t.item())
+        el = allmax(s0.elapsed_time(s1))
         sustained = {'steps': n_sus, 'ms_per_step': el / n_sus, 'value': nb * world / (el / n_sus * 1e-3), 'unit': 'samples/s',
                      'clocks': clocks2.stop(tw0, tw1) if clocks2 else None}
 
-    # ---- end-to-end: host minibatches -> H2D -> learner step -> D2H loss read, every step ----
+    # ---- end to end: PPO.optimize_host on pinned host rollouts ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(algo, agent, rollout, st, n_envs, dev, world, args, rows_list)
+        e2e = run_e2e(algo, st, rollout, n_envs, dev, world, args, allmax, barrier)
 
     if rank != 0:
         if world > 1:
@@ -342,16 +410,24 @@ def main():
         return
 
     pk = peaks()
-    # tensor peak of the regime the timed region ran in: cuBLAS burst figure at full clocks, the sustained figure when
-    # nvidia-smi reported the power cap (B200_PROFILING.md: burst for a kernel timed alone, sustained inside a long step)
     capped = bool(clk and 'sw_power_cap' in (clk.get('reasons') or []))
     pk['tflops'] = pk['tflops_sustained'] if capped else pk['tflops_burst']
     pk['src'] += ', bf16 ' + ('sustained (power cap active)' if capped else 'burst (full clocks, no power cap in the timed region)')
+    step_tf = STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12
+    step_roof = {'bound': 'tensor', 'unit': 'TFLOP/s', 'flops_per_sample': STEP_FLOPS_PER_SAMPLE,
+                 'burst': {'achieved': step_tf, 'peak': pk['tflops'], 'frac': step_tf / pk['tflops']}}
     if sustained:
         cap2 = bool(sustained['clocks'] and 'sw_power_cap' in (sustained['clocks'].get('reasons') or []))
-        sustained['step_achieved_tflops'] = STEP_FLOPS_PER_SAMPLE * sustained['value'] / world / 1e12
-        sustained['step_frac'] = sustained['step_achieved_tflops'] / (pk['tflops_sustained'] if cap2 else pk['tflops_burst'])
+        stf = STEP_FLOPS_PER_SAMPLE * sustained['value'] / world / 1e12
+        speak = pk['tflops_sustained'] if cap2 else pk['tflops_burst']
+        sustained['step_achieved_tflops'] = stf
+        sustained['step_frac'] = stf / speak
         sustained['tensor_peak'] = 'sustained' if cap2 else 'burst'
+        step_roof['sustained'] = {'achieved': stf, 'peak': speak, 'frac': stf / speak}
+    # the grading quantity of SURVEY §8(d): whole learner step against the tensor roofline, sustained regime when measured
+    lead = step_roof.get('sustained', step_roof['burst'])
+    step_roof.update({'achieved': lead['achieved'], 'peak': lead['peak'], 'frac': lead['frac'],
+                      'regime': 'sustained' if 'sustained' in step_roof else 'burst'})
     # dominant kernel of the step and its roofline
     dom = max((k for k in sites if k in MACS), key=lambda k: sites[k][0] * 1.0, default=None)
     roof = None
@@ -360,35 +436,30 @@ def main():
         flops = 2.0 * MACS[dom] * nb
         ach = flops / (sites[dom][0] * 1e-3) / 1e12
         gbs = BYTES[dom] * nb / (sites[dom][0] * 1e-3) / 1e9
-        # report against the roofline that binds first for this kernel (higher fraction); the other one is kept
-        # beside it.  `traffic` = dram read+write bytes per launch from the committed ncu --set full capture of
-        # the same kernel at the same size (profiles/r01_kernel_traffic.json), null if the size differs.
+        # `traffic` = dram read+write bytes per launch from the committed ncu --set full capture of the same kernel at the same size
         traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'r01_kernel_traffic.json')
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            if tj.get('samples_per_launch') == nb and dom in tj.get('kernels', {}):
-                traffic = tj['kernels'][dom]['dram_bytes']
-        roof = {'bound': 'tensor', 'kernel': dom, 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s',
-                'frac': ach / pk['tflops'], 'traffic': traffic, 'peak_source': pk['src'],
-                'algorithmic_bytes_per_launch': BYTES[dom] * nb, 'algorithmic_flops_per_launch': flops,
-                'other': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm']},
-                'avg_launch_ms': sites[dom][0], 'kernel_share_of_step': sites[dom][0] / ms_per_step,
-                'step_achieved': STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12,
-                'step_frac': STEP_FLOPS_PER_SAMPLE * nb / (ms_per_step * 1e-3) / 1e12 / pk['tflops'],
-                'per_kernel_ms': per_kernel}
-        if roof['other']['frac'] > roof['frac']:
-            o = roof['other']
-            roof['other'] = {k: roof[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac')}
-            roof.update(o)
+        for name in ('r02_kernel_traffic.json', 'r01_kernel_traffic.json'):
+            tp = os.path.join(ROOT, 'profiles', name)
+            if os.path.exists(tp):
+                tj = json.load(open(tp))
+                if tj.get('samples_per_launch') == nb and dom in tj.get('kernels', {}):
+                    traffic = tj['kernels'][dom]['dram_bytes']
+                    break
+        tensor = {'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['tflops']}
+        hbm = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm']}
+        first, other = (hbm, tensor) if hbm['frac'] > tensor['frac'] else (tensor, hbm)     # the roofline that binds this kernel first
+        roof = dict(first)
+        roof.update({'kernel': dom, 'traffic': traffic, 'peak_source': pk['src'], 'other': other,
+                     'algorithmic_bytes_per_launch': BYTES[dom] * nb, 'algorithmic_flops_per_launch': flops,
+                     'avg_launch_ms': sites[dom][0], 'kernel_share_of_step': sites[dom][0] / ms_per_step,
+                     'step': step_roof, 'step_frac': step_roof['frac'], 'per_kernel_ms': per_kernel})
     extras = None
-    if world == 1 and not args.no_extras:
-        extras = run_extras(algo, rollout, n_envs, dev, ms_per_step, pk['hbm'])
+    if extras_on:
+        extras = run_extras(algo, agent, rollout, st, n_envs, dev, ms_per_step, pk, hyper, batch)
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, n, threads, el = cpu_reference_step_rate(8, args.cpu_seconds)
-        cpu = {'value': rate, 'unit': 'samples/s', 'cores': threads, 'kind': 'port',
-               'sample': f'{n} learner steps of 8 envs x {B} samples in {el:.1f} s (oracle port of the reference CPU path, torch-CPU fp32, os.cpu_count={os.cpu_count()})'}
+        cb = cpu_baseline(args.cpu_seconds)
+        cpu = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     line = {
         'metric': 'PPO update samples/sec (84x84x4 frames)', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -397,175 +468,283 @@ def main():
                                f'learner step = {B} samples x {n_envs} envs = {nb} samples/GPU, A={A}, K=1',
                    'parallelism': f'dp{world}', 'l2_policy': 'inputs larger than L2 (3.8 GB uint8 rollout per GPU, '
                                                              'a different random minibatch every step)'},
-        'clocks': clk, 'sustained': sustained, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'extras': extras,
+        'clocks': clk, 'sustained': sustained, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+        'allreduce_check': allreduce_check, 'extras': extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def _timed(fn, iters=20, warm=3):
-    for _ in range(warm):
-        fn()
-    tc.cuda.synchronize()
-    e0, e1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    tc.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+# ------------------------------------------------------------------------------------------------------
+def run_allreduce_check(comm, eng, dev, rank, world):
+    """a19 / a25 on the driver's record: the bucketed SUM all-reduce of a rank-seeded gradient-sized buffer (exactly representable
+    small integers, so every summation order gives the same floats) equals all-gather + fixed-order sum bit for bit, and
+    Communicator.mean_ of a 5-float vector equals the mean of the gathered vectors.  Runs before any timing."""
+    import torch.distributed as dist
+    n = eng.nparams
+    idx = tc.arange(n, device=dev, dtype=tc.int64)
+
+    def seeded(r):
+        return (((idx * 7 + r * 13) % 257) - 128).float()
+    buf = seeded(rank)
+    comm.allreduce_(buf, comm.grad_buckets(eng.offsets))
+    gathered = [tc.empty(n, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, seeded(rank))
+    want = gathered[0].clone()
+    for r in range(1, world):
+        want += gathered[r]
+    ok_grad = bool(tc.equal(buf, want))
+    one = seeded(rank)
+    comm.allreduce_(one)                                     # single bucket
+    ok_one = bool(tc.equal(one, want))
+    vec = tc.arange(5, device=dev, dtype=tc.float32) * 0.25 + rank
+    got = comm.mean_(vec.clone())
+    vg = [tc.empty(5, device=dev) for _ in range(world)]
+    dist.all_gather(vg, vec)
+    ok_mean = bool(tc.allclose(got, tc.stack(vg).sum(0) / world, rtol=0, atol=1e-6))
+    flags = tc.tensor([ok_grad, ok_one, ok_mean], device=dev, dtype=tc.int32)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ok = bool(flags.min().item())
+    return {'status': 'ok' if ok else 'FAILED', 'world': world, 'elements': int(n), 'buckets': comm.grad_buckets(eng.offsets),
+            'bit_identical_to_allgather_sum': bool(flags[0].item()) and bool(flags[1].item()), 'mean_5_floats': bool(flags[2].item()),
+            'backend': 'p2p' if comm.p2p else 'nccl'}
 
 
-def run_extras(algo, rollout, n_envs, dev, ms_per_step, hbm_peak):
-    """The side measurements SURVEY §8(d) asks for next to the headline (rank 0, N=1, a few hundred ms of GPU time):
-    GAE in (env x step)/s and HBM GB/s, the fused loss kernel in GB/s, the per-epoch forward-only metrics pass
-    (ppo.py:265-266) and the update throughput with that pass included, the PER sum-tree at 2^20 leaves / batch 512.
-    The HBM figures use inputs larger than L2 (126 MB); the config-sized calls are launch-latency bound and are
-    reported as microseconds."""
-    from pytorch_drl_b200 import ops
+# ------------------------------------------------------------------------------------------------------
+def run_e2e(algo, st, rollout, n_envs, dev, world, args, allmax, barrier):
+    """End to end through the public API: `PPO.optimize_host(host_rollout, storage)` — per call the uint8 rollout (frames, actions,
+    rewards, dones) is copied from PINNED HOST memory to the device (chunked on a copy stream; the annotate forward of a chunk
+    overlaps the upload of the next), then credit assignment, opt_epochs x T/B learner steps with the per-epoch metrics passes,
+    and the metrics are read back to the host every epoch.  Update samples per call = opt_epochs * n_envs * T."""
+    d = st.as_dict()
+    host = {'observations': d['observations'].cpu().pin_memory(), 'actions': d['actions'].cpu().pin_memory(),
+            'dones': d['dones'].cpu().pin_memory(),
+            'rewards': {k: d['rewards'][k].cpu().pin_memory() for k in st.reward_keys}}
+    h2d = host['observations'].numel() + sum(v.numel() * v.element_size() for v in (host['actions'], host['dones']))
+    h2d += sum(v.numel() * v.element_size() for v in host['rewards'].values())
+    epochs = algo._opt_epochs
+    samples = epochs * n_envs * T
+    n_calls = max(2, args.steps // 6)
+    algo.optimize_host(host, st)                          # warm-up (allocations, first-touch)
+    barrier()
+    ev0, ev1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(n_calls):
+        algo.optimize_host(host, st)
+    ev1.record()
+    tc.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    el = allmax(ev0.elapsed_time(ev1))
+    assert all(np.isfinite(list(m.values())).all() for m in algo.last_epoch_metrics)
+    steps_per_call = epochs * (T // B)
+    return {'value': samples * world / (el / n_calls * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d),
+            'd2h_bytes_per_step': 20 * epochs, 'ms_per_step': el / n_calls, 'wall_ms_per_step': 1e3 * wall / n_calls,
+            'step': f'one PPO.optimize_host call = upload + annotate + GAE + {steps_per_call} learner steps + {epochs} metrics passes',
+            'calls': n_calls, 'update_samples_per_call': samples,
+            'h2d_GBps': h2d / (el / n_calls * 1e-3) / 1e9,
+            'api': 'PPO.optimize_host(pinned host rollout, RolloutStorage)'}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_extras(algo, agent, rollout, st, n_envs, dev, ms_per_step, pk, hyper, batch):
+    """The other BASELINE configs and the side measurements SURVEY §8(d) asks for (rank 0, N=1; a few seconds of GPU time)."""
+    from pytorch_drl_b200 import _lib, algos, ops
+    from pytorch_drl_b200._lib import current_stream, ptr
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
     from pytorch_drl_b200.replay import SumTree
+    from pytorch_drl_b200.utils.nested import MinibatchView
+    L = _lib.lib()
+    hbm_peak = pk['hbm']
     out = {}
     g = tc.Generator(device=dev)
     g.manual_seed(7)
-    # GAE + vtarg + per-env standardisation: 20 B per (env, step) read+written once (+8 B for the second pass
-    # of the standardisation, counted as algorithmic traffic only where it happens)
+    nb = n_envs * B
+    all_rows = st.rows(T)
+
+    # ---- one whole PPO.optimize call on the device-resident rollout (annotate + GAE + epochs x steps + metrics passes) ----
+    def whole():
+        algo.optimize(algo.credit_assignment(algo.annotate(rollout)))
+    ms_opt = timed(whole, iters=3, warm=1)
+    out['optimize_call'] = {'ms': ms_opt, 'update_samples': 3 * n_envs * T, 'samples_per_s': 3 * n_envs * T / (ms_opt * 1e-3),
+                            'what': f'annotate ({n_envs * (T + 1)} forward samples) + GAE + 3 epochs x {T // B} learner steps + 3 metrics passes, device resident',
+                            'step_frac_of_tensor_peak': STEP_FLOPS_PER_SAMPLE * 3 * n_envs * T / (ms_opt * 1e-3) / 1e12 / pk['tflops_sustained']}
+
+    # ---- sweep (BASELINE config 5): samples per learner step 4k..64k ----
+    sweep = []
+    for n in (4096, 8192, 16384, 32768, 65536):
+        rows = all_rows[tc.randperm(all_rows.numel(), device=dev, generator=g)[:n]].contiguous()
+        mb = MinibatchView(rollout, rows)
+        ms = timed(lambda: algo.learner_step(mb, hyper, batch), iters=10, warm=3)
+        tf = STEP_FLOPS_PER_SAMPLE * n / (ms * 1e-3) / 1e12
+        sweep.append({'samples_per_step': n, 'ms_per_step': ms, 'samples_per_s': n / (ms * 1e-3), 'step_tflops': tf,
+                      'step_frac_burst_peak': tf / pk['tflops_burst']})
+    out['sweep'] = sweep
+
+    # ---- config 0 (BASELINE config[0] shapes on one GPU): 8 envs, T=128/B=32 and the shipped T=256/B=64 (SURVEY F6) ----
+    cfg0 = []
+    for (T0, B0) in ((128, 32), (256, 64)):
+        a0 = make_agent(A, REWARD_KEYS, 8 * (T0 + 1), 'bf16', dev)
+        o0 = tc.optim.Adam(a0.parameters(), lr=2.5e-4, eps=1e-5)
+        al0 = algos.PPO(rank=0, world_size=1, rollout_len=T0, extra_steps=0,
+                        credit_assignment_ops={'extrinsic': algos.GAE(gamma=0.99, use_dones=True, lambda_=0.95)}, global_step=1,
+                        max_steps=10 ** 7, policy_net=a0, policy_optimizer=o0, opt_epochs=3, learner_batch_size=B0,
+                        envs_per_rank=8, sampler_seed=0)
+        s0 = algos.RolloutStorage(8, T0, REWARD_KEYS, dev)
+        fill_synthetic(s0.as_dict(), s0, 8, A, REWARD_KEYS, dev, 99)
+        r0 = al0.credit_assignment(al0.annotate(s0.as_dict()))
+        h0, b0 = al0._hyper(), al0._batch(r0)
+        er = al0._epoch_rows(r0)
+        mbs = [MinibatchView(r0, er[i]) for i in range(er.shape[0])]
+        k = [0]
+
+        def one_step():
+            al0.learner_step(mbs[k[0] % len(mbs)], h0, b0)
+            k[0] += 1
+        ms_gpu = timed(one_step, iters=50, warm=5)
+        tc.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            one_step()
+        host_ms = (time.perf_counter() - t0) / 50 * 1e3          # time to ENQUEUE a step (python + ctypes + launches), no sync
+        tc.cuda.synchronize()
+        ms_call = timed(lambda: al0.optimize(al0.credit_assignment(al0.annotate(r0))), iters=3, warm=1)
+        cfg0.append({'envs': 8, 'T': T0, 'B': B0, 'samples_per_step': 8 * B0, 'ms_per_step': ms_gpu, 'host_enqueue_ms_per_step': host_ms,
+                     'samples_per_s': 8 * B0 / (ms_gpu * 1e-3), 'optimize_call_ms': ms_call,
+                     'optimize_call_samples_per_s': 3 * 8 * T0 / (ms_call * 1e-3),
+                     'bound': 'launch latency: ~20 kernels per step on 1-4 CTAs each; the host enqueue time is the floor when larger'})
+        del a0, al0, s0
+    out['config0'] = cfg0
+
+    # ---- config 3 (RND + PPO per models_dir/atari_rnd): A=18, K=2 (extrinsic gamma .999 / intrinsic gamma .99 no dones, weights
+    #      2.0 / 1.0), clip .1, ent .001, vf_coef .5, 4 epochs, lr 1e-4; RND predictor learn once per PPO minibatch, no row drop ----
+    rk3 = ['extrinsic', 'intrinsic_rnd']
+    a3 = make_agent(18, rk3, nb, 'bf16', dev)
+    o3 = tc.optim.Adam(a3.parameters(), lr=1e-4, eps=1e-5)
+    rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=32, widening=1, non_learning_steps=0, max_batch=nb, device=dev)
+    rnd.observe(tc.rand((8, 84, 84, 1), device=dev, generator=g))
+    rnd._sync_normalizers_global(); rnd._sync_normalizers_local()
+    al3 = algos.PPO(rank=0, world_size=1, rollout_len=T, extra_steps=0,
+                    credit_assignment_ops={'extrinsic': algos.GAE(gamma=0.999, use_dones=True, lambda_=0.95),
+                                           'intrinsic_rnd': algos.GAE(gamma=0.99, use_dones=False, lambda_=0.95)},
+                    global_step=10 ** 6, non_learning_steps=0, max_steps=5 * 10 ** 8, policy_net=a3, policy_optimizer=o3,
+                    standardize_adv=False, opt_epochs=4, learner_batch_size=B, clip_param_init=0.1, clip_param_final=0.1,
+                    ent_coef_init=0.001, ent_coef_final=0.001, vf_loss_coef=0.5, reward_weights={'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
+                    envs_per_rank=n_envs, sampler_seed=0, env=rnd)
+    s3 = algos.RolloutStorage(n_envs, T, rk3, dev)
+    d3 = s3.as_dict()
+    d3['observations'] = rollout['observations']            # the same 3.8 GB of frames
+    fill_synthetic(d3, s3, n_envs, 18, rk3, dev, 5, obs=False)
+    # intrinsic rewards come from the RND networks themselves (SURVEY §8d), batched over the rollout
+    ms_rew = timed(lambda: rnd.intrinsic_reward(d3['observations'], all_rows), iters=3, warm=1)
+    d3['rewards']['intrinsic_rnd'][:, :T] = rnd.intrinsic_reward(d3['observations'], all_rows).view(n_envs, T).clamp_(-5, 5)
+    r3 = al3.credit_assignment(al3.annotate(d3))
+    h3, b3 = al3._hyper(), al3._batch(r3)
+    er3 = al3._epoch_rows(r3)
+    mbs3 = [MinibatchView(r3, er3[i]) for i in range(er3.shape[0])]
+    k3 = [0]
+
+    def step3():
+        mb = mbs3[k3[0] % len(mbs3)]
+        al3._update_trainable_wrappers(mb)                   # RND.learn(mb): predictor MSE step + normaliser sync
+        al3.learner_step(mb, h3, b3)
+        k3[0] += 1
+    ms3 = timed(step3, iters=12, warm=4)
+    ms_rnd = timed(lambda: rnd.learn(mbs3[0]), iters=12, warm=2)
+    ms_ppo3 = timed(lambda: al3.learner_step(mbs3[1], h3, b3), iters=12, warm=2)
+    flops3 = (STEP_FLOPS_PER_SAMPLE + 3 * 2 * 512 * (12 + 1) + RND_FLOPS_PER_SAMPLE) * nb    # +12 actions, +1 value head: fwd + 2 x bwd
+    out['config3'] = {'workload': f'RND + PPO (atari_rnd shapes): A=18, K=2, {n_envs} envs x {T} steps, {nb} samples per step, RND learn per minibatch (no row drop)',
+                      'ms_per_step': ms3, 'samples_per_s': nb / (ms3 * 1e-3), 'ppo_step_ms': ms_ppo3, 'rnd_learn_ms': ms_rnd,
+                      'rnd_learn_samples_per_s': nb / (ms_rnd * 1e-3), 'rnd_learn_tflops': RND_FLOPS_PER_SAMPLE * nb / (ms_rnd * 1e-3) / 1e12,
+                      'rnd_learn_frac_burst_peak': RND_FLOPS_PER_SAMPLE * nb / (ms_rnd * 1e-3) / 1e12 / pk['tflops_burst'],
+                      'step_tflops': flops3 / (ms3 * 1e-3) / 1e12, 'step_frac_burst_peak': flops3 / (ms3 * 1e-3) / 1e12 / pk['tflops_burst'],
+                      'rnd_intrinsic_reward': {'samples': n_envs * T, 'ms': ms_rew, 'samples_per_s': n_envs * T / (ms_rew * 1e-3)},
+                      'rnd_engine': rnd.precision_name}
+    out['rnd_learn'] = {'samples': nb, 'ms': ms_rnd, 'samples_per_s': nb / (ms_rnd * 1e-3), 'engine': 'tcgen05 bf16 (csrc/umma_rnd.cu)'}
+    del a3, al3, rnd, s3, d3, r3, mbs3
+    tc.cuda.empty_cache()
+
+    # ---- precision modes: fp32 CUDA-core engine vs the tcgen05 bf16 engine at 4 096 samples (rate, gradient rel-L2) ----
+    npre = 4096
+    rows_p = all_rows[tc.randperm(all_rows.numel(), device=dev, generator=g)[:npre]].contiguous()
+    eng16 = agent.engine
+    from pytorch_drl_b200.engine import LearnerEngine
+    eng32 = LearnerEngine(A, ['value_extrinsic'], npre, 'fp32', dev)
+    eng32.load_named({k: v.clone() for k, v in eng16.named_views().items()})
+    ms16 = timed(lambda: eng16.ppo_step(rollout['observations'], rows_p, batch, hyper), iters=10, warm=3)
+    g16 = eng16.grads.double().clone()
+    ms32 = timed(lambda: eng32.ppo_step(rollout['observations'], rows_p, batch, hyper), iters=2, warm=1)
+    g32 = eng32.grads.double()
+    per = {}
+    for i, name in enumerate(eng16.names):
+        a_, b_ = g16[eng16.offsets[i]:eng16.offsets[i + 1]], g32[eng16.offsets[i]:eng16.offsets[i + 1]]
+        per[name.replace('_architecture._network.', 'trunk.').replace('_predictors.', '').replace('._network.0', '')] = float((a_ - b_).norm() / b_.norm().clamp_min(1e-30))
+    out['precision'] = {'samples': npre,
+                        'fp32': {'engine': 'CUDA cores (strict parity: <= 2e-4 rel-L2 vs torch-CPU)', 'fwd_bwd_samples_per_s': npre / (ms32 * 1e-3)},
+                        'bf16': {'engine': 'tcgen05, fp32 accumulate', 'fwd_bwd_samples_per_s': npre / (ms16 * 1e-3),
+                                 'grad_rel_l2_vs_fp32_all_params': float((g16 - g32).norm() / g32.norm()), 'grad_rel_l2_vs_fp32_per_tensor': per},
+                        'tf32': 'not built: CPU emulation (profiles/r02_precision_emulation.txt) gives 2 % gradient rel-L2 for 10-bit operands — the error is '
+                                'ReLU-mask flips, sqrt(2 x flip fraction), so tf32 would not reach rtol 1e-3 either; fp32 is the parity mode'}
+    del eng32
+
+    # ---- GAE + vtarg + per-env standardisation: 20 B per (env, step) ----
     for tag, n in (('config', n_envs), ('large', 65536)):
         r = tc.randint(-1, 2, (n, T), device=dev, generator=g).float()
         v = tc.randn((n, T + 4), device=dev, generator=g)
-        d = (tc.rand((n, T), device=dev, generator=g) < 0.01).float()
+        dn = (tc.rand((n, T), device=dev, generator=g) < 0.01).float()
         adv, vt = tc.empty((n, T), device=dev), tc.empty((n, T), device=dev)
-        ms = _timed(lambda: ops.gae(r, v, d, 0.99, 0.95, True, True, T, adv, vt))
+        ms = timed(lambda: ops.gae(r, v, dn, 0.99, 0.95, True, True, T, adv, vt))
         out[f'gae_{tag}'] = {'envs': n, 'steps': T, 'us': ms * 1e3, 'env_steps_per_s': n * T / (ms * 1e-3),
                              'GBps': 20.0 * n * T / (ms * 1e-3) / 1e9, 'frac_hbm': 20.0 * n * T / (ms * 1e-3) / 1e9 / hbm_peak,
                              'bytes_per_env_step': 20}
-        del r, v, d, adv, vt
-    # fused clipped-surrogate / value / entropy loss forward + backward on given logits: 8A + 12 + 20K B per sample
+        del r, v, dn, adv, vt
+    # ---- fused clipped-surrogate / value / entropy loss forward + backward on given logits: 8A + 12 + 20K B per sample ----
     for tag, n in (('config', n_envs * B), ('large', 1 << 22)):
         logits = tc.randn((n, A), device=dev, generator=g)
         values = tc.randn((n, 1), device=dev, generator=g)
         acts = tc.randint(0, A, (n,), device=dev, generator=g)
         lp = tc.log_softmax(logits, -1).gather(1, acts[:, None]).squeeze(1) + 0.05 * tc.randn((n,), device=dev, generator=g)
         advs, vold, vtg = (tc.randn((n,), device=dev, generator=g) for _ in range(3))
-        hyper = ops.make_hyper(A, [1.0], 0.2, 0.01, 1.0, False, True)
-        batch = ops.make_batch(acts, lp, [advs], [vold], [vtg])
+        hy = ops.make_hyper(A, [1.0], 0.2, 0.01, 1.0, False, True)
+        bt = ops.make_batch(acts, lp, [advs], [vold], [vtg])
         bytes_per = 8 * A + 12 + 20 + 8                     # + logp and entropy written back
-        import ctypes
-        from pytorch_drl_b200 import _lib
-        from pytorch_drl_b200._lib import current_stream, ptr
-        L = _lib.lib()
         losses, lpo, eno = tc.empty(5, device=dev), tc.empty(n, device=dev), tc.empty(n, device=dev)
         dl, dvv = tc.empty_like(logits), tc.empty_like(values)
 
         def call():                                          # the C-ABI entry on caller-allocated outputs
-            rc = L.drl_ppo_loss_fwd_bwd(ptr(logits), ptr(values), None, n, ctypes.byref(batch), ctypes.byref(hyper),
+            rc = L.drl_ppo_loss_fwd_bwd(ptr(logits), ptr(values), None, n, ctypes.byref(bt), ctypes.byref(hy),
                                         ptr(losses), ptr(lpo), ptr(eno), ptr(dl), ptr(dvv), current_stream())
             assert rc == 0
-        ms = _timed(call)
+        ms = timed(call)
         out[f'ppo_loss_{tag}'] = {'samples': n, 'us': ms * 1e3, 'GBps': bytes_per * n / (ms * 1e-3) / 1e9,
                                   'frac_hbm': bytes_per * n / (ms * 1e-3) / 1e9 / hbm_peak, 'bytes_per_sample': bytes_per}
-        del losses, lpo, eno, dl, dvv
-        del logits, values, acts, lp, advs, vold, vtg
-    # per-epoch metrics pass: forward + losses over the whole rollout, no gradient (ppo.py:265-266)
-    ms_metrics = _timed(lambda: algo.compute_losses_and_metrics(rollout, no_grad=True), iters=5, warm=2)
+        del losses, lpo, eno, dl, dvv, logits, values, acts, lp, advs, vold, vtg
+    # ---- per-epoch metrics pass: forward + losses over the whole rollout, no gradient (ppo.py:265-266) ----
+    ms_metrics = timed(lambda: algo.compute_losses_and_metrics(rollout, no_grad=True), iters=5, warm=2)
     steps_per_epoch = T // B
     out['metrics_pass'] = {'samples': n_envs * T, 'ms': ms_metrics, 'forward_samples_per_s': n_envs * T / (ms_metrics * 1e-3)}
     out['update_with_metrics_pass'] = {
         'samples_per_s': n_envs * T / ((steps_per_epoch * ms_per_step + ms_metrics) * 1e-3),
         'note': f'one epoch = {steps_per_epoch} learner steps ({n_envs * T} update samples) + one forward-only pass over the same {n_envs * T} samples'}
-    # PER sum-tree: 2^20 leaves, batch 512 (dependent-access latency bound; GB/s is not meaningful)
+    # ---- PER sum-tree (config 4): 2^20 leaves, batch 512 — dependent-access latency bound; parity unpinned (no reference code) ----
+    out['sumtree'] = run_sumtree_extras(dev, g)
+    return out
+
+
+def run_sumtree_extras(dev, g):
+    from pytorch_drl_b200.replay import SumTree
     cap, bs = 1 << 20, 512
     tree = SumTree(cap, device=dev)
     tree.set_leaves(tc.rand(cap, device=dev, generator=g) + 1e-3)
     idx = tc.randint(0, cap, (bs,), device=dev, generator=g)
     pr = tc.rand(bs, device=dev, generator=g) + 1e-3
     u01 = tc.rand(bs, device=dev, generator=g)
-    ms_u = _timed(lambda: tree.update(idx, pr), iters=50)
-    ms_s = _timed(lambda: tree.sample(tree.stratified_u(u01)), iters=50)
-    out['sumtree'] = {'leaves': cap, 'batch': bs, 'update_us': ms_u * 1e3, 'sample_us': ms_s * 1e3,
-                      'updates_per_s': bs / (ms_u * 1e-3), 'samples_per_s': bs / (ms_s * 1e-3)}
-    return out
-
-
-def run_e2e(algo, agent, rollout, st, n_envs, dev, world, args, rows_list):
-    """Same metric through the public API with HOST minibatches: every step copies that step's
-    minibatch (frames + per-sample scalars, pinned host memory) to the device, runs
-    PPO.learner_step on it and reads the losses back to the host.  Copies are double-buffered on a
-    side stream so that step s+1's upload overlaps step s's compute; everything is inside the timed
-    region."""
-    import torch.distributed as dist
-    from pytorch_drl_b200.utils.nested import MinibatchView
-    nb = n_envs * B
-    nbuf = 2
-    host, devb = [], []
-    names = ['observations', 'actions', 'logprobs']
-    for b in range(nbuf):
-        rows = rows_list[b]
-        h = {
-            'observations': rollout['observations'].view(-1, 84, 84, 4)[rows].cpu().pin_memory(),
-            'actions': rollout['actions'].view(-1)[rows].cpu().pin_memory(),
-            'logprobs': rollout['logprobs'].view(-1)[rows].cpu().pin_memory(),
-            'advantages': rollout['advantages']['extrinsic'].reshape(-1)[rows].cpu().pin_memory(),
-            'vpreds': rollout['vpreds']['extrinsic'].reshape(-1)[rows].cpu().pin_memory(),
-            'vtargs': rollout['vtargs']['extrinsic'].reshape(-1)[rows].cpu().pin_memory(),
-        }
-        host.append(h)
-        devb.append({k: tc.empty(v.shape, dtype=v.dtype, device=dev) for k, v in h.items()})
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    ident = tc.arange(nb, device=dev, dtype=tc.int64)
-    loss_host = tc.empty((args.steps + args.warmup, 5), dtype=tc.float32).pin_memory()
-    copy_stream = tc.cuda.Stream(device=dev)
-    main = tc.cuda.current_stream()
-    ready = [tc.cuda.Event() for _ in range(nbuf)]
-    freed = [tc.cuda.Event() for _ in range(nbuf)]
-
-    def upload(i):
-        b = i % nbuf
-        with tc.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[b])
-            for k in host[b]:
-                devb[b][k].copy_(host[b][k], non_blocking=True)
-            ready[b].record(copy_stream)
-
-    def view(b):
-        dd = devb[b]
-        return MinibatchView({'observations': dd['observations'].view(1, nb, 84, 84, 4), 'actions': dd['actions'].view(1, nb),
-                              'logprobs': dd['logprobs'].view(1, nb), 'advantages': {'extrinsic': dd['advantages'].view(1, nb)},
-                              'vpreds': {'extrinsic': dd['vpreds'].view(1, nb)}, 'vtargs': {'extrinsic': dd['vtargs'].view(1, nb)}},
-                             ident)
-
-    def run(n, offset):
-        upload(0)
-        for i in range(n):
-            b = i % nbuf
-            if i + 1 < n:
-                upload(i + 1)
-            main.wait_event(ready[b])
-            losses = algo.learner_step(view(b))
-            freed[b].record(main)
-            loss_host[offset + i].copy_(losses, non_blocking=True)
-        tc.cuda.synchronize()
-
-    for b in range(nbuf):
-        freed[b].record(main)
-    run(max(3, min(args.warmup, 5)), 0)
-    if world > 1:
-        dist.barrier()
-    tc.cuda.synchronize()
-    ev0, ev1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
-    ev0.record()
-    run(args.steps, args.warmup)
-    ev1.record()
-    tc.cuda.synchronize()
-    el = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = tc.tensor([el], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el = float(t.item())
-    assert bool(tc.isfinite(loss_host[args.warmup:args.warmup + args.steps]).all())
-    return {'value': nb * world / (el / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d),
-            'd2h_bytes_per_step': 20, 'ms_per_step': el / args.steps,
-            'api': 'PPO.learner_step(MinibatchView) on pinned-host minibatches, double-buffered uploads'}
+    ms_u = timed(lambda: tree.update(idx, pr), iters=50)
+    ms_s = timed(lambda: tree.sample(tree.stratified_u(u01)), iters=50)
+    return {'leaves': cap, 'batch': bs, 'update_us': ms_u * 1e3, 'sample_us': ms_s * 1e3,
+            'updates_per_s': bs / (ms_u * 1e-3), 'samples_per_s': bs / (ms_s * 1e-3),
+            'parity': 'bit-exact vs oracle/sumtree.c (parity unpinned: the reference has no sum-tree, SURVEY F2)'}
 
 
 if __name__ == '__main__':

@@ -171,19 +171,21 @@ class PPO:
 
     # ---- annotate / credit assignment ---------------------------------------------------------------
     @tc.no_grad()
-    def annotate(self, rollout: Dict[str, Any], no_grad: bool = True) -> Dict[str, Any]:
-        """abstract.py:371-411 for all envs at once: one no-grad forward over the T+1 frames of
+    def annotate(self, rollout: Dict[str, Any], no_grad: bool = True, envs: Optional[range] = None) -> Dict[str, Any]:
+        """abstract.py:371-411 for all envs at once (or the env slice `envs`): one no-grad forward over the T+1 frames of
         every env; fills logprobs/entropies/vpreds in place and returns the rollout."""
         obs = rollout['observations']
-        n, Tp = obs.shape[0], obs.shape[1]
+        Tp = obs.shape[1]
+        e0, e1 = (0, obs.shape[0]) if envs is None else (envs.start, envs.stop)
+        n = e1 - e0
         T1 = self._rollout_len + self._extra_steps + 1                 # T + n frames (abstract.py:383-397)
-        e = tc.arange(n, device=obs.device, dtype=tc.int64).unsqueeze(1) * Tp
+        e = tc.arange(e0, e1, device=obs.device, dtype=tc.int64).unsqueeze(1) * Tp
         rows = (e + tc.arange(T1, device=obs.device, dtype=tc.int64).unsqueeze(0)).reshape(-1)
         _, values, logp, ent = self._engine.forward(obs, rows, actions=rollout['actions'])
-        rollout['logprobs'][:, :T1] = logp.view(n, T1)
-        rollout['entropies'][:, :T1] = ent.view(n, T1)
+        rollout['logprobs'][e0:e1, :T1] = logp.view(n, T1)
+        rollout['entropies'][e0:e1, :T1] = ent.view(n, T1)
         for i, k in enumerate(self._stream_order()):
-            rollout['vpreds'][k][:, :T1] = values[:, i].reshape(n, T1)
+            rollout['vpreds'][k][e0:e1, :T1] = values[:, i].reshape(n, T1)
         return rollout
 
     @tc.no_grad()
@@ -237,19 +239,22 @@ class PPO:
         return (float(g.get('lr', 1e-3)), tuple(g.get('betas', (0.9, 0.999))), float(g.get('eps', 1e-8)))
 
     def _minibatch_rows(self, rollout, blocks_per_env: List[np.ndarray]) -> tc.Tensor:
+        """Flat row numbers of ONE minibatch given every env's index block (tests / benchmarks; optimize uses _epoch_rows)."""
         Tp = rollout['observations'].shape[1]
         idx = np.stack([b.astype(np.int64) + e * Tp for e, b in enumerate(blocks_per_env)]).reshape(-1)
         return tc.as_tensor(idx, device=self._engine.device)
 
-    def learner_step(self, minibatch) -> tc.Tensor:
+    def learner_step(self, minibatch, hyper=None, batch=None) -> tc.Tensor:
         """One learner step on a minibatch (ppo.py:250-257): forward, fused losses, backward,
         gradient all-reduce across GPUs (the DDP mean, launch.py:310), Adam.  Returns the device
-        tensor losses[5] (policy_loss, value_loss, composite_loss, meanent, clipfrac)."""
+        tensor losses[5] (policy_loss, value_loss, composite_loss, meanent, clipfrac).  `hyper` / `batch` are the C-ABI
+        argument blocks of this rollout (built once per optimize call; rebuilt here when omitted)."""
         eng = self._engine
         rows = minibatch.row_idx
         if rows.numel() > eng.max_batch:
             raise ValueError('minibatch larger than the engine max_batch')
-        losses = eng.ppo_step(minibatch['observations'], rows, self._batch(minibatch), self._hyper(), grads=True)
+        losses = eng.ppo_step(minibatch['observations'], rows, batch if batch is not None else self._batch(minibatch),
+                              hyper if hyper is not None else self._hyper(), grads=True)
         world = self._world_size if self._comm is not None else 1
         if self._comm is not None and getattr(eng, 'comm_attached', None) is not self._comm:
             self._comm.allreduce_grads(eng)          # not attached: exchange after the backward pass
@@ -257,21 +262,33 @@ class PPO:
         eng.adam_step(lr, betas, eps, grad_scale=1.0 / world)
         return losses
 
+    def _epoch_rows(self, rollout) -> tc.Tensor:
+        """Resample every env's permutation (samplers.py:60-63) and return the epoch's minibatches as ONE device tensor
+        [T/B steps, n_envs * B] of flat row numbers: a single host-to-device copy per epoch instead of one per step."""
+        for s in self._samplers:
+            s.resample()
+        Tp = rollout['observations'].shape[1]
+        B, steps = self._learner_batch_size, self._rollout_len // self._learner_batch_size
+        blocks = []
+        for e, s in enumerate(self._samplers):
+            it = iter(s)
+            blocks.append(np.stack([next(it) for _ in range(steps)]).astype(np.int64) + e * Tp)      # [steps, B]
+        idx = np.ascontiguousarray(np.stack(blocks, axis=1).reshape(steps, -1))                       # [steps, n_envs * B]
+        return tc.as_tensor(idx).to(self._engine.device, non_blocking=False)
+
     def optimize(self, rollout: Dict[str, Any]) -> None:
         """ppo.py:242-281: opt_epochs x T/B learner steps (+ the per-epoch full-rollout metrics pass
         and the scheduler step).  One learner step = B samples of each env of every GPU."""
         self.last_epoch_metrics = []
+        hyper, batch = self._hyper(), self._batch(rollout)        # global_step (the schedules' clock) is fixed during optimize
         for opt_epoch in range(self._opt_epochs):
-            for s in self._samplers:
-                s.resample()
-            iters = [iter(s) for s in self._samplers]
-            for _ in range(self._rollout_len // self._learner_batch_size):
-                rows = self._minibatch_rows(rollout, [next(it) for it in iters])
-                minibatch = MinibatchView(rollout, rows)
+            epoch_rows = self._epoch_rows(rollout)
+            for step in range(epoch_rows.shape[0]):
+                minibatch = MinibatchView(rollout, epoch_rows[step])
                 self._update_trainable_wrappers(minibatch)
                 if self._global_step <= self._non_learning_steps:
                     continue
-                self.learner_step(minibatch)
+                self.learner_step(minibatch, hyper, batch)
             metrics = self.compute_losses_and_metrics(rollout, no_grad=True)
             vec = tc.stack([metrics[n] for n in METRIC_NAMES])
             if self._comm is not None:
@@ -283,6 +300,39 @@ class PPO:
                 self.on_epoch_metrics(opt_epoch, m)
         if self._policy_scheduler:
             self._policy_scheduler.step()
+
+    def optimize_host(self, host: Mapping[str, Any], storage: 'RolloutStorage', chunk_envs: int = 128) -> Dict[str, Any]:
+        """collect() -> optimize() for a rollout the actors left in (pinned) HOST memory: the uint8 frames are uploaded ONCE per
+        rollout (not once per minibatch: a rollout is consumed opt_epochs times), in env chunks on a copy stream; each chunk's
+        annotate forward (abstract.py:383-411) runs as soon as it has landed, overlapping the rest of the upload; then
+        credit assignment and the epochs.  `host` holds observations [n_envs, >= T+1, 84, 84, 4] uint8, actions, dones and
+        rewards{key}, laid out like `storage`.  Returns the device rollout."""
+        d = storage.as_dict()
+        dev = self._engine.device
+        n = storage.n_envs
+        main = tc.cuda.current_stream(dev)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = tc.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        cs.wait_stream(main)                                            # the previous rollout's readers are done
+        events = []
+        with tc.cuda.stream(cs):
+            for k in ('actions', 'dones'):
+                d[k].copy_(host[k], non_blocking=True)
+            for k in storage.reward_keys:
+                d['rewards'][k].copy_(host['rewards'][k], non_blocking=True)
+            for e0 in range(0, n, chunk_envs):
+                e1 = min(n, e0 + chunk_envs)
+                d['observations'][e0:e1].copy_(host['observations'][e0:e1], non_blocking=True)
+                ev = tc.cuda.Event()
+                ev.record(cs)
+                events.append((e0, e1, ev))
+        for e0, e1, ev in events:
+            main.wait_event(ev)
+            self.annotate(d, envs=range(e0, e1))
+        rollout = self.credit_assignment(d)
+        self.optimize(rollout)
+        return rollout
 
     # ---- the rest of Algo's surface (drl/algos/abstract.py:173-221, ppo.py:283-307) ---------------------------------------
     @property
@@ -326,9 +376,9 @@ class PPO:
             self.persist(metadata)
 
     def _update_trainable_wrappers(self, minibatch) -> None:
-        """drl/algos/common/wrapper_ops.py:9-25."""
+        """drl/algos/common/wrapper_ops.py:9-25: every wrapper of the chain (linked through `.env`) that has a `learn`."""
         w = self._env
-        while w is not None and hasattr(w, 'env'):
+        while w is not None:
             if hasattr(w, 'learn'):
                 w.learn(minibatch)
-            w = w.env
+            w = getattr(w, 'env', None)

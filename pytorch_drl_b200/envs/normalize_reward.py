@@ -16,7 +16,8 @@ from .._lib import check, current_stream, ptr
 
 class BatchedRewardNormalizer:
     def __init__(self, n_envs: int, gamma: float, use_dones: bool, device=None, comm=None,
-                 clip_low: float = -10.0, clip_high: float = 10.0):
+                 clip_low: float = -10.0, clip_high: float = 10.0, env=None):
+        self.env = env                      # next trainable wrapper of the chain (wrapper_ops.py:21-25)
         if not tc.cuda.is_available():
             raise RuntimeError('BatchedRewardNormalizer needs a CUDA device; there is no CPU fallback')
         dev = tc.device('cuda', tc.cuda.current_device()) if device is None else tc.device(device)

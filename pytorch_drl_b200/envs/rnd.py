@@ -40,7 +40,8 @@ def _views(flat: tc.Tensor, keys, shapes) -> Dict[str, tc.Tensor]:
 class RandomNetworkDistillation:
     def __init__(self, rnd_optimizer_args: Mapping[str, float], world_size: int, widening: int = 1,
                  non_learning_steps: int = 0, max_batch: int = 1024, comm=None, device=None, seed: int = 0,
-                 precision: str = 'bf16'):
+                 precision: str = 'bf16', env=None):
+        self.env = env                      # next trainable wrapper of the chain (wrapper_ops.py:21-25), e.g. a BatchedRewardNormalizer
         if not tc.cuda.is_available():
             raise RuntimeError('RND needs a CUDA device; there is no CPU fallback')
         self.device = tc.device('cuda', tc.cuda.current_device()) if device is None else tc.device(device)
@@ -123,8 +124,11 @@ class RandomNetworkDistillation:
         nb = int(row_idx.numel() if row_idx is not None else frames_u8.shape[0])
         out = tc.empty(nb, dtype=tc.float32, device=self.device)
         nz = self._synced_normalizer
-        check(self._L.drl_rnd_reward(self._h, ptr(frames_u8), ptr(row_idx), nb, ptr(nz.moment1), ptr(nz.moment2),
-                                     ptr(out), current_stream()), 'rnd_reward')
+        for s in range(0, nb, self.max_batch):          # the handle's workspace holds max_batch frames per call
+            m = min(self.max_batch, nb - s)
+            ridx = row_idx[s:s + m] if row_idx is not None else tc.arange(s, s + m, device=self.device, dtype=tc.int64)
+            check(self._L.drl_rnd_reward(self._h, ptr(frames_u8), ptr(ridx), m, ptr(nz.moment1), ptr(nz.moment2),
+                                         ptr(out[s:s + m]), current_stream()), 'rnd_reward')
         return out
 
     def observe(self, last_channel_frames: tc.Tensor) -> None:
