@@ -146,7 +146,7 @@ extern "C" int drl_net_forward(drl_net_t* net, const uint8_t* obs, const int64_t
   if ((logp_out || entropy_out) && !actions && logp_out) return DRL_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
   DRL_TRY(net->precision == DRL_PRECISION_FP32 ? fp32_trunk_forward(net, obs, row_idx, nb, st)
-                                               : bf16_trunk_forward(net, obs, row_idx, nb, st));
+                                               : bf16_trunk_forward(net, obs, row_idx, nb, false, st));
   HeadParams hpp;
   head_params(net, net->params, nullptr, hpp);
   drl_ppo_batch_t batch{};
@@ -165,7 +165,7 @@ extern "C" int drl_net_features(drl_net_t* net, const uint8_t* obs, const int64_
   if (!feat_out) return DRL_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
   DRL_TRY(net->precision == DRL_PRECISION_FP32 ? fp32_trunk_forward(net, obs, row_idx, nb, st)
-                                               : bf16_trunk_forward(net, obs, row_idx, nb, st));
+                                               : bf16_trunk_forward(net, obs, row_idx, nb, false, st));
   DRL_CUDA(cudaMemcpyAsync(feat_out, net->feat, (size_t)nb * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return DRL_OK;
 }
@@ -182,13 +182,17 @@ static int ppo_common(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx
   const bool bf16 = net->precision == DRL_PRECISION_BF16;
   DRL_CUDA(cudaMemsetAsync(losses_out, 0, 5 * sizeof(float), st));
   if (grads) DRL_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->nparams * sizeof(float), st));
-  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
+  const bool heads_tc = bf16 && bf16_heads_on_tensor_cores(net);     // heads + losses as three MMAs per 128-sample tile
+  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, heads_tc, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
   HeadParams hpp;
   head_params(net, net->params, grads, hpp);
   {
   ProfileScope prof("heads_loss", st);
-  DRL_TRY(heads_loss_dispatch(grads ? 2 : 1, bf16, net->feat, hpp, row_idx, nb, *batch, *hyper, losses_out,
-                              nullptr, nullptr, nullptr, nullptr, net->dpre, st));
+  if (heads_tc)
+    DRL_TRY(bf16_heads_loss(net, grads ? 2 : 1, hpp, row_idx, nb, *batch, *hyper, losses_out, st));
+  else
+    DRL_TRY(heads_loss_dispatch(grads ? 2 : 1, bf16, net->feat, hpp, row_idx, nb, *batch, *hyper, losses_out,
+                                nullptr, nullptr, nullptr, nullptr, net->dpre, st));
   }
   if (grads)
     DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, /*overlap_comm=*/true, st)
@@ -213,7 +217,7 @@ extern "C" int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_
   cudaStream_t st = as_stream(stream);
   const bool bf16 = net->precision == DRL_PRECISION_BF16;
   DRL_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->nparams * sizeof(float), st));
-  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
+  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, false, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
   HeadParams hpp;
   head_params(net, net->params, grads, hpp);
   drl_ppo_batch_t batch{};

@@ -50,7 +50,11 @@ int adam_launch(float* params, const float* grads, float* exp_avg, float* exp_av
 int bf16_alloc(drl_net* n);
 void bf16_free(drl_net* n);
 int bf16_pack_params(drl_net* n, cudaStream_t st);
-int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, cudaStream_t st);
+// feat_bf16: the fc layer writes bf16 features for the tensor-core heads kernel (learner step / metrics pass) instead of fp32 `feat`
+int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, bool feat_bf16, cudaStream_t st);
+bool bf16_heads_on_tensor_cores(const drl_net* n);
+int bf16_heads_loss(drl_net* n, int mode, const HeadParams& hpp, const int64_t* row_idx, int nb, const drl_ppo_batch_t& batch,
+                    const drl_ppo_hyper_t& hp, float* losses_out, cudaStream_t st);
 int comm_allreduce_after(drl_comm* c, float* flat, int64_t lo, int64_t hi, cudaStream_t producer);
 int comm_join(drl_comm* c, cudaStream_t consumer);
 int comm_world(const drl_comm* c);

@@ -257,7 +257,7 @@ static int launch_tma_gemm(const char* site, const void* a, int M, int K, const 
   // CTA pairs: each CTA stages 128 rows of A and 128 columns of B.  Measured: fc forward (49 k-blocks per tile)
   // 0.106 -> 0.098 ms, fc data gradient (8 k-blocks per tile, heavy epilogue) 0.105 -> 0.113 ms => [6] = 1 pairs the
   // forward only, [6] = 2 both.
-  if (BN == 256 && ((g_debug_flags[6] & 3) == 2 || ((g_debug_flags[6] & 3) == 1 && EPI == EPI_BIAS_RELU_F32))) {
+  if (BN == 256 && ((g_debug_flags[6] & 3) == 2 || ((g_debug_flags[6] & 3) == 1 && (EPI == EPI_BIAS_RELU_F32 || EPI == EPI_BIAS_RELU_BF16)))) {
     DRL_TRY(make_tmap_bf16(&tb, b, (uint64_t)N_total, (uint64_t)K, 128));
     if (args.bias_grad && args.bias_mod != 64) return DRL_ERR_BAD_ARG;
     auto kern2 = tma_gemm2_kernel<EPI>;

@@ -11,6 +11,7 @@
 #include <new>
 #include "umma_launch.cuh"
 #include "umma_conv1_s2d.cuh"
+#include "umma_heads.cuh"
 
 namespace drl {
 
@@ -27,6 +28,8 @@ struct Bf16Engine {
   uint32_t* bits[3] = {nullptr, nullptr, nullptr};   // ReLU masks of act1/act2/act3, 1 bit per element
   float* b1eff = nullptr; // conv1 effective bias (last block of pack_all_kernel)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
+  void* whd = nullptr;   // heads       bf16 [8][32x64]: rows = (policy actions, value streams, zero padding)  (umma_heads.cuh)
+  __nv_bfloat16* featb = nullptr;   // [nb, 512] bf16 features of the learner step (the fp32 `feat` serves the other entry points)
   // weight-gradient scratch in GEMM order [kp = (ky, kx, ci)][co]: fc 3136 x 512, conv3 640 x 64, conv2 512 x 64.
   // All-zero between steps: wgrad_untranspose_kernel moves a layer's sums to the OIHW gradient and clears them.
   float* gt = nullptr;
@@ -35,7 +38,7 @@ constexpr int64_t kGtFc = 0, kGtConv3 = (int64_t)3136 * 512, kGtConv2 = kGtConv3
 
 
 // ---- packing -----------------------------------------------------------------------------------------
-enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_CONV1_S2D = 5 };
+enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_CONV1_S2D = 5, PK_HEADS = 6 };
 
 struct PackArgs {
   const float* w;      // reference-layout fp32 weights of the layer
@@ -43,6 +46,7 @@ struct PackArgs {
   int mode, fp16;
   int variants, KB, N; // tile grid: [variants][KB][N rows x 64]
   int Cin, KH, KW, Cout;
+  const float* wv[DRL_MAX_REWARD_STREAMS];   // PK_HEADS: value-head weight rows (Cin = A, KH = K)
 };
 
 __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n, int k) {
@@ -65,6 +69,8 @@ __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n,
       const int t = k / 64, co = k - t * 64, ty = t / 3, tx = t - ty * 3;
       return a.w[((size_t)(co * 64 + n) * 3 + (2 - ty)) * 3 + (2 - tx)];
     }
+    case PK_HEADS:                 // B[n = head][k = feature]: policy rows, value rows, zero padding
+      return n < a.Cin ? a.w[(size_t)n * 512 + k] : (n < a.Cin + a.KH ? a.wv[n - a.Cin][k] : 0.f);
     case PK_CONV1_S2D: {           // B[n=co][k = tap*64 + e], tap = (ty,tx), e = dy*16 + px*4 + ci: W1[co,ci,4ty+dy,4tx+px]
       const int tap = k >> 6, e = k & 63, ty = tap >> 1, tx = tap & 1;
       const int dy = e >> 4, px = (e >> 2) & 3, ci = e & 3;
@@ -168,6 +174,8 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&e->wfd, (size_t)3136 * 512 * 2));
   DRL_CUDA(cudaMalloc(&e->w3d, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
+  DRL_CUDA(cudaMalloc(&e->whd, kHmWBytes));
+  DRL_CUDA(cudaMalloc(&e->featb, nb * 512 * 2));
   DRL_CUDA(cudaMalloc(&e->b1eff, 32 * sizeof(float)));
   DRL_CUDA(cudaMalloc(&e->gt, kGtTotal * sizeof(float)));
   DRL_CUDA(cudaMemset(e->gt, 0, kGtTotal * sizeof(float)));
@@ -180,7 +188,7 @@ int bf16_alloc(drl_net* n) {
 void bf16_free(drl_net* n) {
   Bf16Engine* e = n->bf16;
   if (!e) return;
-  cudaFree(e->w1s); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->b1eff); cudaFree(e->gt); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
+  cudaFree(e->w1s); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->whd); cudaFree(e->featb); cudaFree(e->b1eff); cudaFree(e->gt); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
   delete e;
   n->bf16 = nullptr;
 }
@@ -193,7 +201,7 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   PackAllArgs a{};
   int nj = 0, blocks = 0;
   auto add = [&](const float* w, void* out, int mode, int fp16, int variants, int KB, int N, int Cin, int KH, int KW, int Cout) {
-    a.job[nj] = PackArgs{w, out, mode, fp16, variants, KB, N, Cin, KH, KW, Cout};
+    a.job[nj] = PackArgs{w, out, mode, fp16, variants, KB, N, Cin, KH, KW, Cout, {nullptr, nullptr, nullptr, nullptr}};
     a.first_block[nj] = blocks;
     const int64_t total = (int64_t)variants * KB * N * 64;
     int b = (int)((total + 1023) / 1024);               // ~4 elements per thread
@@ -205,6 +213,10 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   add(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64);
   add(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64);
   add(p + o[2], e->w2d, PK_CONV2_DGRAD, 0, 1, 4, 128, 32, 4, 4, 64);
+  if (n->A + n->K <= kHmNH) {
+    add(p + o[8], e->whd, PK_HEADS, 0, 1, 8, kHmNH, n->A, n->K, 1, 1);
+    for (int k = 0; k < n->K; ++k) a.job[nj - 1].wv[k] = p + o[10 + 2 * k];
+  }
   a.first_block[nj] = blocks;
   a.n_jobs = nj;
   a.wfc = p + o[6]; a.fc_fwd = (__nv_bfloat16*)e->wff; a.fc_dgrad = (__nv_bfloat16*)e->wfd; a.fc_blocks = sm_count() * 2;
@@ -222,12 +234,14 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
 //     0.232 ms, conv2 dgrad 0.253 -> 0.340 ms (it is HBM / epilogue bound: the pair only couples two epilogues) => 3.
 //     bit 8: conv3 data gradient on CTA pairs with accumulator tiles that span samples (tma_conv2s_kernel, groups of 5
 //     samples in 4 tiles): 0.235 -> 0.217 ms => default 11.
+// [9] 1 = heads + losses on the CUDA-core kernel (heads_loss.cu) instead of the tensor-core kernel (umma_heads.cuh): 0.087 vs
+//     ~0.02 ms at 32 768 samples => default 0
 // [8] heads kernel compiled for 3 resident CTAs per SM (80 registers instead of 127, 64 bytes of spill) for the exact-(A, K)
 //     training instantiations with A <= 8: 0.094 -> 0.084 ms => default 1
 // (The cp.async row-gather / im2col engines of round 1 that flags [0]-[5] used to select were measured slower and are gone.)
 int g_debug_flags[16] = {0, 0, 0, 0, 0, 0, 5, 11, 1, 0, 0, 0, 0, 0, 0, 0};
 
-int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, cudaStream_t st) {
+int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, bool feat_bf16, cudaStream_t st) {
   Bf16Engine* e = n->bf16;
   const float* p = n->params;
   const int64_t* o = n->off;
@@ -258,9 +272,55 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
     TmaGemmArgs g{};
     g.M = nb; g.N_total = 512; g.KB = 49; g.out = n->feat; g.out_ld = 512; g.bias = p + o[7]; g.mask_src = nullptr;
     g.bias_grad = nullptr; g.bias_mod = 1; g.bits_in = nullptr;
-    DRL_TRY((launch_tma_gemm<256, EPI_BIAS_RELU_F32>("fc_fwd", n->act[2], nb, 3136, e->wff, 512, g, st)));
+    if (feat_bf16) {                                  // learner step: bf16 features for the tensor-core heads kernel
+      g.out = e->featb;
+      DRL_TRY((launch_tma_gemm<256, EPI_BIAS_RELU_BF16>("fc_fwd", n->act[2], nb, 3136, e->wff, 512, g, st)));
+    } else {
+      DRL_TRY((launch_tma_gemm<256, EPI_BIAS_RELU_F32>("fc_fwd", n->act[2], nb, 3136, e->wff, 512, g, st)));
+    }
   }
   return DRL_OK;
+}
+
+// heads + losses (+ backward) on tensor cores from the bf16 features of the last bf16_trunk_forward(feat_bf16 = true)
+bool bf16_heads_on_tensor_cores(const drl_net* n) { return n->A + n->K <= kHmNH && g_debug_flags[9] == 0; }
+
+int bf16_heads_loss(drl_net* n, int mode, const HeadParams& hpp, const int64_t* row_idx, int nb, const drl_ppo_batch_t& batch,
+                    const drl_ppo_hyper_t& hp, float* losses_out, cudaStream_t st) {
+  return heads_mma_launch(mode, n->bf16->featb, n->bf16->whd, hpp, row_idx, nb, batch, hp, losses_out, n->dpre, st);
+}
+
+template <int MAXA, int MODE, int AX, int KX>
+static int heads_mma_go(const CUtensorMap& tf, const HeadsMmaArgs& a, int nb, cudaStream_t st) {
+  auto kern = heads_mma_kernel<MAXA, MODE, AX, KX>;
+  static int configured[kMaxDevices] = {0};
+  DRL_TRY(ensure_dyn_smem(kern, kHmSmem, configured));
+  const int tiles = (nb + 127) / 128;
+  kern<<<tiles < sm_count() ? tiles : sm_count(), kHmThreads, kHmSmem, st>>>(tf, a);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+int heads_mma_launch(int mode, const void* featb, const void* wpack, const HeadParams& hpp, const int64_t* row_idx, int nb,
+                     const drl_ppo_batch_t& batch, const drl_ppo_hyper_t& hp, float* losses_out, void* dpre, cudaStream_t st) {
+  CUtensorMap tf;
+  DRL_TRY(make_tmap_bf16(&tf, featb, (uint64_t)nb, 512, 128));
+  HeadsMmaArgs a{};
+  a.hp_ptrs = hpp; a.wpack = wpack; a.row_idx = row_idx; a.nb = nb; a.batch = batch; a.hp = hp; a.inv_nb = 1.0f / (float)nb;
+  a.losses_out = losses_out; a.dpre = reinterpret_cast<__nv_bfloat16*>(dpre);
+  const int A = hp.num_actions, K = hp.num_streams;
+#define HM(MAXA, AX, KX)                                                      \
+  do {                                                                        \
+    if (mode == 2) return heads_mma_go<MAXA, 2, AX, KX>(tf, a, nb, st);       \
+    return heads_mma_go<MAXA, 1, AX, KX>(tf, a, nb, st);                      \
+  } while (0)
+  if (A == 6 && K == 1) HM(8, 6, 1);          // Pong-class action sets (atari_ppo)
+  if (A == 18 && K == 2) HM(18, 18, 2);       // RND + PPO (atari_rnd)
+  if (A == 18 && K == 1) HM(18, 18, 1);
+  if (A <= 8) HM(8, 0, 0);
+  if (A <= 18) HM(18, 0, 0);
+  HM(32, 0, 0);
+#undef HM
 }
 
 int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, int nb, float* g, bool overlap_comm,

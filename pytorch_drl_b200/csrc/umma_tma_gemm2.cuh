@@ -122,7 +122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-        const int mp = tile % m_pairs, nt = tile / m_pairs;
+        const int nt = tile % n_tiles, mp = tile / n_tiles;     // N tiles of one row block adjacent: pairs p, p+1 fetch the same A rows together (one DRAM read, one L2 hit)
         for (int kb = 0; kb < args.KB; ++kb, ++it) {
           const uint32_t stage = it % S, phase = (it / S) & 1;
           mbar_wait(empty + stage, phase ^ 1);
@@ -172,11 +172,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 #pragma unroll
     for (int i = 0; i < (EPI == EPI_MASK_BF16 ? 32 * BG : 1); ++i) cs[i] = 0.f;
     for (int tile = pair; tile < num_tiles; tile += n_pairs, ++j) {
-      const int mp = tile % m_pairs, nt = tile / m_pairs;
+      const int nt = tile % n_tiles, mp = tile / n_tiles;
       const uint32_t acc = j & 1;
       const int m = mp * 256 + (int)rank * 128 + (int)(threadIdx.x & 127);
       const int n0 = nt * BN;
-      if (EPI == EPI_BIAS_RELU_F32 && nt != last_nt) {     // (re)load the bias slice of this N tile
+      if (!epi_is_mask(EPI) && nt != last_nt) {            // (re)load the bias slice of this N tile
         asm volatile("bar.sync 1, 256;");
         for (int i = threadIdx.x; i < BN; i += 256) sBias[i] = n0 + i < args.N_total ? args.bias[n0 + i] : 0.f;
         asm volatile("bar.sync 1, 256;");
@@ -205,6 +205,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(r[8 * q + i]) + sBias[ch * 32 + 8 * q + i], 0.f));
               stg_v8(o + 8 * q, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            }
+          } else if (EPI == EPI_BIAS_RELU_BF16) {        // bf16 features for the tensor-core heads kernel (umma_heads.cuh)
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(args.out) + (int64_t)m * args.out_ld + n;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                pk[i] = pack_bf16x2_relu(__uint_as_float(r[16 * q + 2 * i]) + sBias[ch * 32 + 16 * q + 2 * i],
+                                         __uint_as_float(r[16 * q + 2 * i + 1]) + sBias[ch * 32 + 16 * q + 2 * i + 1]);
+              stg_v8(o + 16 * q, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             }
           } else {
             const int64_t off = (int64_t)m * args.out_ld + n;

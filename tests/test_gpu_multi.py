@@ -63,8 +63,19 @@ def _worker(rank, world, port, out_dir):
         for _ in range(3):                                                                  # repeated: buffers are reused
             eng.ppo_step(d['observations'], rows, batch, hyper)
         tc.cuda.synchronize()
-        result[precision] = dict(local=local.cpu().numpy(), plain=plain.cpu().numpy(), fused=eng.grads.cpu().numpy(),
-                                 nccl=nccl.cpu().numpy(), small=small.cpu().numpy(), p2p=np.array([int(comm.p2p)]))
+        fused = eng.grads.clone()
+        # the network's vector-Jacobian product (drl_net_backward, the autograd path of Agent.forward) with the communicator
+        # still ATTACHED must stay a purely local computation: no collective is started on the caller's scratch buffer
+        dl = tc.full((n_envs * B, A), 0.01 * (rank + 1), device=dev)
+        dv = tc.full((n_envs * B, 1), -0.02 * (rank + 1), device=dev)
+        vjp_attached = eng.backward(d['observations'], rows, dl, dv).clone()
+        check_ok = __import__('pytorch_drl_b200')._lib.lib().drl_net_set_comm(eng._h, None)
+        assert check_ok == 0
+        vjp_detached = eng.backward(d['observations'], rows, dl, dv).clone()
+        tc.cuda.synchronize()
+        result[precision] = dict(local=local.cpu().numpy(), plain=plain.cpu().numpy(), fused=fused.cpu().numpy(),
+                                 nccl=nccl.cpu().numpy(), small=small.cpu().numpy(), p2p=np.array([int(comm.p2p)]),
+                                 vjp_a=vjp_attached.cpu().numpy(), vjp_d=vjp_detached.cpu().numpy())
         del eng
     np.savez(os.path.join(out_dir, f'rank{rank}.npz'), **{f'{p}_{k}': v for p, r in result.items() for k, v in r.items()})
     dist.barrier()
@@ -88,4 +99,8 @@ def test_overlapped_gradient_exchange_matches_plain_allreduce(tmp_path):
             # order, so compare as a whole (a missing or doubled range would show up as O(1))
             f, p = r[i][f'{precision}_fused'].astype(np.float64), r[i][f'{precision}_plain'].astype(np.float64)
             assert np.linalg.norm(f - p) <= 1e-5 * np.linalg.norm(p), precision
+            va, vd = r[i][f'{precision}_vjp_a'].astype(np.float64), r[i][f'{precision}_vjp_d'].astype(np.float64)
+            assert np.linalg.norm(va - vd) <= 1e-5 * np.linalg.norm(vd), (precision, 'drl_net_backward exchanged gradients')
+        # ... and the two ranks' (different) cotangents gave different local results: nothing was summed across ranks
+        assert np.linalg.norm(r[0][f'{precision}_vjp_a'] - r[1][f'{precision}_vjp_a']) > 1e-3 * np.linalg.norm(r[0][f'{precision}_vjp_a'])
         assert np.abs(total).max() > 0
