@@ -732,18 +732,67 @@ def run_extras(algo, agent, rollout, st, n_envs, dev, ms_per_step, pk, hyper, ba
     return out
 
 
+def graph_timed(fn, iters=50):
+    """GPU time per call with the launches replayed from a CUDA graph (host launch overhead removed); eager timing if the
+    capture is refused."""
+    try:
+        fn()
+        tc.cuda.synchronize()
+        gr = tc.cuda.CUDAGraph()
+        with tc.cuda.graph(gr):
+            for _ in range(iters):
+                fn()
+        gr.replay()
+        tc.cuda.synchronize()
+        e0, e1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gr.replay()
+        e1.record()
+        tc.cuda.synchronize()
+        return e0.elapsed_time(e1) / (5 * iters), 'cuda graph replay'
+    except Exception as ex:                                   # noqa: BLE001
+        tc.cuda.synchronize()
+        return timed(fn, iters=iters), f'eager launches ({type(ex).__name__})'
+
+
 def run_sumtree_extras(dev, g):
+    """BASELINE config 4: 2^20-leaf sum-tree, batch 512 priority update + prioritized sample (+ a 64 k-update batch on the
+    multi-CTA path), next to the dependent-access floor: levels x measured L2 latency of a pointer chase."""
+    from pytorch_drl_b200 import _lib
+    from pytorch_drl_b200._lib import current_stream, ptr
     from pytorch_drl_b200.replay import SumTree
+    L = _lib.lib()
     cap, bs = 1 << 20, 512
     tree = SumTree(cap, device=dev)
     tree.set_leaves(tc.rand(cap, device=dev, generator=g) + 1e-3)
     idx = tc.randint(0, cap, (bs,), device=dev, generator=g)
     pr = tc.rand(bs, device=dev, generator=g) + 1e-3
     u01 = tc.rand(bs, device=dev, generator=g)
-    ms_u = timed(lambda: tree.update(idx, pr), iters=50)
-    ms_s = timed(lambda: tree.sample(tree.stratified_u(u01)), iters=50)
-    return {'leaves': cap, 'batch': bs, 'update_us': ms_u * 1e3, 'sample_us': ms_s * 1e3,
+    big_idx = tc.randint(0, cap, (65536,), device=dev, generator=g)
+    big_pr = tc.rand(65536, device=dev, generator=g) + 1e-3
+    idx_o, pr_o, w_o = tc.empty(bs, dtype=tc.int64, device=dev), tc.empty(bs, device=dev), tc.empty(bs, device=dev)
+    ms_u, how = graph_timed(lambda: tree.update(idx, pr))
+    ms_s, _ = graph_timed(lambda: L.drl_per_sample(ptr(tree.tree), cap, ptr(u01), bs, float(cap), 0.4, ptr(idx_o), ptr(pr_o), ptr(w_o),
+                                                   current_stream()))
+    ms_b, _ = graph_timed(lambda: tree.update(big_idx, big_pr), iters=10)
+    # dependent-load latency: a random cyclic permutation over 8 MB of int32 (the tree's size: L2 resident)
+    n_ring = 1 << 21
+    perm = tc.randperm(n_ring, device=dev, generator=g)
+    ring = tc.empty(n_ring, dtype=tc.int32, device=dev)
+    ring[perm] = tc.roll(perm, -1).to(tc.int32)
+    cyc = tc.zeros(2, device=dev)
+    L.drl_probe_dependent_latency(ptr(ring), 4096, ptr(cyc), current_stream())
+    tc.cuda.synchronize()
+    sm_mhz = tc.cuda.clock_rate() if hasattr(tc.cuda, 'clock_rate') else 1965
+    hop_ns = float(cyc[0].item()) / (sm_mhz * 1e-3)
+    return {'leaves': cap, 'batch': bs, 'update_us': ms_u * 1e3, 'sample_us': ms_s * 1e3, 'timing': how,
             'updates_per_s': bs / (ms_u * 1e-3), 'samples_per_s': bs / (ms_s * 1e-3),
+            'update_64k': {'batch': 65536, 'us': ms_b * 1e3, 'updates_per_s': 65536 / (ms_b * 1e-3), 'path': '128 CTAs (depth-7 subtrees) + top pass'},
+            'sample': 'fused: stratified masses + descent + importance weights (drl_per_sample)',
+            'dependent_latency': {'cycles_per_level': float(cyc[0].item()), 'ns_per_level': hop_ns, 'levels': 20,
+                                  'walk_floor_us': 20 * hop_ns * 1e-3,
+                                  'note': 'one pointer chase over 8 MB (L2 resident); update / sample walk 20 dependent levels'},
             'parity': 'bit-exact vs oracle/sumtree.c (parity unpinned: the reference has no sum-tree, SURVEY F2)'}
 
 

@@ -292,7 +292,8 @@ int drl_rnd_learn(drl_rnd_t* rnd, const uint8_t* obs, const int64_t* row_idx, in
  * updated) so results are bit-reproducible.
  * ============================================================================================= */
 /* Set leaf idx[j] = prio[j] for j in [0,n) (last writer wins on duplicates: the highest j), then
- * recompute every affected ancestor level by level. idx int64 in [0,cap). */
+ * recompute every affected ancestor level by level.  idx int64; entries outside [0,cap) are ignored.
+ * n <= 2048: one CTA (in-kernel sort by leaf); larger batches: 128 CTAs, one per depth-7 subtree, + a 7-level top pass. */
 int drl_sumtree_update(float* tree, int64_t cap, const int64_t* idx, const float* prio, int64_t n,
                        void* stream);
 /* Rebuild all internal nodes from the leaves. */
@@ -305,6 +306,19 @@ int drl_sumtree_sample(const float* tree, int64_t cap, const float* u, int64_t n
  * on device in fp32 from caller-supplied uniforms so the host RNG stays the seed authority. */
 int drl_sumtree_stratified_u(const float* tree, const float* uniform01, int64_t n, float* u_out,
                              void* stream);
+/* One batch (n <= 1024) of proportional prioritized sampling in one launch (Schaul et al. 2015, Algorithm 1 lines 9-10):
+ * stratified masses from uniform01, prefix-sum descent, importance weights w_j = (size * p_j / total)^-beta / max_k w_k
+ * (0 for an empty tree / zero-priority leaf).  idx_out / prio_out bit-identical to stratified_u + sample. */
+int drl_per_sample(const float* tree, int64_t cap, const float* uniform01, int64_t n, float size, float beta,
+                   int64_t* idx_out, float* prio_out, float* weights_out, void* stream);
+/* out[i] = ring[(idx[i] + shift) mod cap] for rows of row_bytes (multiple of 16, 16-byte aligned buffers): the sampled
+ * transitions of a device-resident replay ring (uint8 frame stacks: shift 0 = observation, 1 = successor); n <= 65535. */
+int drl_ring_gather(const void* ring, int64_t cap, int64_t row_bytes, const int64_t* idx, int64_t n, int shift, void* out,
+                    void* stream);
+/* Measurement aid: cycles per dependent load when one thread chases `hops` links through `ring` (int32 next-slot indices of a
+ * cyclic permutation prepared by the caller; its size decides whether the chain lives in L2 or HBM).
+ * cycles_per_hop_out[0] (device) receives the figure: levels x this is the latency floor of the sum-tree walks. */
+int drl_probe_dependent_latency(const int* ring, int hops, float* cycles_per_hop_out, void* stream);
 
 /* =============================================================================================
  * Gradient exchange — replaces the DistributedDataParallel wrapper (drl/utils/launch.py:310;

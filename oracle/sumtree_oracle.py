@@ -16,7 +16,8 @@ def build():
 
 
 def _lib():
-    if not os.path.exists(_SO):
+    src = os.path.join(_HERE, 'sumtree.c')
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         build()
     lib = ctypes.CDLL(_SO)
     return lib
@@ -56,6 +57,17 @@ class SumTree:
         self._lib.st_stratified_u(_p(self.tree, ctypes.c_float), _p(uni, ctypes.c_float),
                                   ctypes.c_int64(uni.size), _p(out, ctypes.c_float))
         return out
+
+
+    def per_sample(self, uniform01, size, beta):
+        uni = np.ascontiguousarray(uniform01, np.float32)
+        idx = np.empty(uni.size, np.int64)
+        pr = np.empty(uni.size, np.float32)
+        w = np.empty(uni.size, np.float32)
+        self._lib.st_per_sample(_p(self.tree, ctypes.c_float), ctypes.c_int64(self.cap), _p(uni, ctypes.c_float),
+                                ctypes.c_int64(uni.size), ctypes.c_float(size), ctypes.c_float(beta),
+                                _p(idx, ctypes.c_int64), _p(pr, ctypes.c_float), _p(w, ctypes.c_float))
+        return idx, pr, w
 
 
 # ---- numpy twin (pure python loops: small cases only) -------------------------------------------

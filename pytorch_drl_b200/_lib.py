@@ -87,6 +87,9 @@ PROTOTYPES = {
     'drl_sumtree_rebuild': (c_int, [c_void_p, c_int64, c_void_p]),
     'drl_sumtree_sample': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'drl_sumtree_stratified_u': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'drl_per_sample': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'drl_ring_gather': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    'drl_probe_dependent_latency': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'drl_nstep_advantages_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64,
                                          c_float, c_int, c_void_p, c_void_p]),
     'drl_bellman_backups_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64,

@@ -1,3 +1,3 @@
-from .sumtree import SumTree, PrioritizedReplayIndex
+from .sumtree import PrioritizedReplayBuffer, PrioritizedReplayIndex, SumTree
 
-__all__ = ['SumTree', 'PrioritizedReplayIndex']
+__all__ = ['SumTree', 'PrioritizedReplayIndex', 'PrioritizedReplayBuffer']

@@ -1,10 +1,10 @@
-"""Prioritized-replay sum-tree on the GPU (Schaul et al. 2015, proportional variant).
+"""Prioritized replay on the GPU (Schaul et al. 2015, proportional variant): sum-tree, index, transition ring.
 
 The reference lists the paper as supported (README.md:15) but ships no replay buffer, sum-tree or
 DQN learner, so this API is the builder's; its arithmetic contract is
 `oracle/sumtree.c` and results are bit-exact against it ("parity unpinned" w.r.t. the reference).
 """
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch as tc
 
@@ -37,12 +37,15 @@ class SumTree:
         self.tree[self.capacity:self.capacity + priorities.numel()] = priorities.to(self.device, tc.float32)
         check(self._L.drl_sumtree_rebuild(ptr(self.tree), self.capacity, current_stream()), 'sumtree_rebuild')
 
-    def update(self, idx: tc.Tensor, priorities: tc.Tensor) -> None:
-        """leaf[idx[j]] = priorities[j] (highest j wins on duplicates) + ancestor recompute."""
+    def update(self, idx: tc.Tensor, priorities: tc.Tensor, validate: bool = False) -> None:
+        """leaf[idx[j]] = priorities[j] (highest j wins on duplicates) + ancestor recompute.  Indices outside [0, capacity)
+        are ignored by the kernel; `validate=True` raises instead (one host synchronisation)."""
         if idx.dtype != tc.int64 or priorities.dtype != tc.float32 or not idx.is_cuda or not priorities.is_cuda:
             raise TypeError('idx must be int64 CUDA, priorities float32 CUDA')
         if idx.numel() != priorities.numel():
             raise ValueError('idx and priorities differ in length')
+        if validate and idx.numel() and bool(((idx < 0) | (idx >= self.capacity)).any().item()):
+            raise ValueError('leaf index out of range')
         check(self._L.drl_sumtree_update(ptr(self.tree), self.capacity, ptr(idx.contiguous()),
                                          ptr(priorities.contiguous()), idx.numel(), current_stream()),
               'sumtree_update')
@@ -63,10 +66,22 @@ class SumTree:
                                                ptr(out), current_stream()), 'sumtree_stratified_u')
         return out
 
+    def per_sample(self, uniform01: tc.Tensor, size: float, beta: float) -> Tuple[tc.Tensor, tc.Tensor, tc.Tensor]:
+        """One fused launch: stratified masses, descent, importance weights (size * p / total)^-beta / max (batch <= 1024)."""
+        if uniform01.dtype != tc.float32 or not uniform01.is_cuda:
+            raise TypeError('uniform01 must be float32 CUDA')
+        n = uniform01.numel()
+        idx = tc.empty(n, dtype=tc.int64, device=self.device)
+        pr = tc.empty(n, dtype=tc.float32, device=self.device)
+        w = tc.empty(n, dtype=tc.float32, device=self.device)
+        check(self._L.drl_per_sample(ptr(self.tree), self.capacity, ptr(uniform01.contiguous()), n, float(size), float(beta),
+                                     ptr(idx), ptr(pr), ptr(w), current_stream()), 'per_sample')
+        return idx, pr, w
+
 
 class PrioritizedReplayIndex:
     """Index side of proportional prioritized replay: priorities p_i^alpha in a SumTree, stratified
-    sampling of a batch, importance weights (N * P(i))^-beta / max_w, priority updates."""
+    sampling of a batch with importance weights (N * P(i))^-beta / max_w in one kernel, priority updates."""
 
     def __init__(self, capacity: int, alpha: float = 0.6, eps: float = 1e-6, device=None,
                  generator: Optional[tc.Generator] = None):
@@ -75,20 +90,84 @@ class PrioritizedReplayIndex:
         self.size = 0
         self._gen = generator
 
-    def add(self, idx: tc.Tensor, td_error: Optional[tc.Tensor] = None, max_priority: float = 1.0) -> None:
+    def add(self, idx: tc.Tensor, td_error: Optional[tc.Tensor] = None, max_priority: float = 1.0,
+            count: Optional[int] = None) -> None:
+        """New transitions enter with the maximal priority (Algorithm 1 line 6) unless TD errors are given.  `count` = number of
+        valid transitions afterwards when the caller tracks it (avoids the host read of idx.max())."""
         pr = tc.full((idx.numel(),), max_priority, dtype=tc.float32, device=self.tree.device) \
             if td_error is None else (td_error.abs() + self.eps).pow(self.alpha).float()
         self.tree.update(idx, pr)
-        self.size = min(self.tree.capacity, max(self.size, int(idx.max().item()) + 1))
+        if count is None:
+            count = int(idx.max().item()) + 1
+        self.size = min(self.tree.capacity, max(self.size, count))
 
     def sample(self, batch_size: int, beta: float = 0.4, uniform01: Optional[tc.Tensor] = None):
         if uniform01 is None:
             uniform01 = tc.rand(batch_size, device=self.tree.device, generator=self._gen)
-        u = self.tree.stratified_u(uniform01.float())
-        idx, pr = self.tree.sample(u)
-        prob = pr / self.tree.total
-        w = (self.size * prob).pow(-beta)
-        return idx, pr, w / w.max()
+        return self.tree.per_sample(uniform01.float(), max(self.size, 1), beta)
 
     def update_priorities(self, idx: tc.Tensor, td_error: tc.Tensor) -> None:
         self.tree.update(idx, (td_error.abs() + self.eps).pow(self.alpha).float())
+
+
+class PrioritizedReplayBuffer:
+    """Device-resident transition ring + prioritized index (BASELINE config 4: 1 M transitions, batch 512).
+
+    Transition i = (observation stack frames[i] uint8 [84, 84, 4], action, reward, done); its successor stack is frames[i + 1]
+    (consecutive writes of one environment stream; at 28 224 B per stack a 2^20-entry ring is 29.6 GB of the B200's 180 GB).
+    `sample` returns the batch's indices, importance weights and scalars, the frame ring itself (the fused NatureCNN trunk
+    gathers rows by index: no copy is needed to run `QAgent` on the batch) and, on request, gathered copies of the
+    observation / successor stacks (`drl_ring_gather`)."""
+
+    def __init__(self, capacity: int, alpha: float = 0.6, eps: float = 1e-6, device=None, generator=None,
+                 frame_shape=(84, 84, 4)):
+        self.index = PrioritizedReplayIndex(capacity, alpha, eps, device, generator)
+        dev = self.index.tree.device
+        self.capacity, self.frame_shape = capacity, tuple(frame_shape)
+        self.frames = tc.zeros((capacity,) + self.frame_shape, dtype=tc.uint8, device=dev)
+        self.actions = tc.zeros(capacity, dtype=tc.int64, device=dev)
+        self.rewards = tc.zeros(capacity, dtype=tc.float32, device=dev)
+        self.dones = tc.zeros(capacity, dtype=tc.float32, device=dev)
+        self.cursor, self.count = 0, 0
+        self._L = _lib.lib()
+
+    def add(self, frames: tc.Tensor, actions: tc.Tensor, rewards: tc.Tensor, dones: tc.Tensor) -> tc.Tensor:
+        """Append n transitions at the ring cursor (wrapping); they get the maximal priority.  Returns their slots."""
+        n = frames.shape[0]
+        if n > self.capacity:
+            raise ValueError('more transitions than the ring holds')
+        dev = self.frames.device
+        slots = (tc.arange(n, device=dev, dtype=tc.int64) + self.cursor) % self.capacity
+        first = min(n, self.capacity - self.cursor)
+        for dst, src in ((self.frames, frames), (self.actions, actions), (self.rewards, rewards), (self.dones, dones)):
+            src = src.to(dev, dst.dtype)
+            dst[self.cursor:self.cursor + first] = src[:first]
+            if first < n:
+                dst[:n - first] = src[first:]
+        self.cursor = (self.cursor + n) % self.capacity
+        self.count = min(self.capacity, self.count + n)
+        self.index.add(slots, count=self.count)
+        return slots
+
+    def gather_frames(self, idx: tc.Tensor, shift: int = 0) -> tc.Tensor:
+        row = 1
+        for d in self.frame_shape:
+            row *= d
+        out = tc.empty((idx.numel(),) + self.frame_shape, dtype=tc.uint8, device=self.frames.device)
+        check(self._L.drl_ring_gather(ptr(self.frames), self.capacity, row, ptr(idx.contiguous()), idx.numel(), shift, ptr(out),
+                                      current_stream()), 'ring_gather')
+        return out
+
+    def sample(self, batch_size: int, beta: float = 0.4, uniform01: Optional[tc.Tensor] = None,
+               gather: bool = False) -> Dict[str, tc.Tensor]:
+        idx, pr, w = self.index.sample(batch_size, beta, uniform01)
+        nxt = (idx + 1) % self.capacity
+        out = {'idx': idx, 'next_idx': nxt, 'priorities': pr, 'weights': w, 'frames': self.frames,
+               'actions': self.actions[idx], 'rewards': self.rewards[idx], 'dones': self.dones[idx]}
+        if gather:
+            out['observations'] = self.gather_frames(idx, 0)
+            out['next_observations'] = self.gather_frames(idx, 1)
+        return out
+
+    def update_priorities(self, idx: tc.Tensor, td_error: tc.Tensor) -> None:
+        self.index.update_priorities(idx, td_error)

@@ -239,7 +239,9 @@ def test_checkpoint_objects_round_trip_through_the_reference_checkpointing(tmp_p
     created = False
     if not dist.is_initialized():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ['MASTER_PORT'] = '29731'
+        import socket
+        sock = socket.socket(); sock.bind(('127.0.0.1', 0)); free_port = sock.getsockname()[1]; sock.close()
+        os.environ['MASTER_PORT'] = str(free_port)
         dist.init_process_group('gloo', rank=0, world_size=1)
         created = True
     try:

@@ -1093,3 +1093,82 @@ def test_rnd_checkpointables_restore_the_predictor(tmp_path):
     la, lb = float(a.learn_rows(frames, rows).item()), float(b.learn_rows(frames, rows).item())
     assert abs(la - lb) <= 1e-6 * abs(la)
     assert rel_l2(b.student_params.cpu().numpy(), a.student_params.cpu().numpy()) < 1e-6
+
+
+# ---- prioritized replay (BASELINE config 4; parity unpinned: the reference has no sum-tree / replay) ------------
+@pytest.mark.parametrize('cap,n', [(1 << 20, 2049), (1 << 20, 5000), (1 << 20, 70000), (1 << 12, 9000), (256, 3000)])
+def test_sumtree_large_batches_multi_cta_bit_exact(cap, n):
+    """Batches beyond one CTA's 2048 slots: 128 CTAs (one per depth-7 subtree) + the 7-level top pass must leave exactly the
+    tree sequential in-order writes leave (oracle/sumtree.c), duplicates (highest j wins), out-of-range indices ignored."""
+    from pytorch_drl_b200.replay import SumTree
+    rs = np.random.RandomState(cap % 97 + n)
+    t, ref = SumTree(cap), so.SumTree(cap)
+    base = rs.uniform(0.0, 1.0, size=cap).astype(F32)
+    t.set_leaves(cu(base)); ref.tree[cap:] = base; ref.rebuild()
+    idx = rs.randint(0, cap, size=n).astype(np.int64)
+    idx[rs.randint(0, n, size=n // 4)] = idx[rs.randint(0, n, size=n // 4)]        # plenty of duplicates
+    idx[::17] = rs.randint(0, min(cap, 300), size=idx[::17].size)                    # hot leaves: many writers each
+    pr = rs.uniform(0.01, 5.0, size=n).astype(F32)
+    bad = idx.copy()
+    bad[5], bad[n // 2] = -3, cap + 7                                                # ignored by the kernel
+    keep = (bad >= 0) & (bad < cap)
+    ref.update(bad[keep], pr[keep])
+    t.update(cu(bad), cu(pr))
+    assert np.array_equal(t.tree.cpu().numpy().view(np.uint32), ref.tree.view(np.uint32))
+    with pytest.raises(ValueError):
+        t.update(cu(bad), cu(pr), validate=True)
+
+
+def test_prioritized_replay_buffer_vs_oracle():
+    """Ring writes with wrap-around, max-priority insertion, the fused stratified sample + importance weights kernel against
+    oracle/sumtree.c (indices / priorities bit-exact, weights through powf: rtol 2e-6), gathered transitions = ring rows,
+    priority updates, empty-tree / zero-priority guards."""
+    from pytorch_drl_b200.replay import PrioritizedReplayBuffer, PrioritizedReplayIndex
+    cap, alpha, eps, beta = 1 << 10, 0.6, 1e-6, 0.4
+    rs = np.random.RandomState(2)
+    buf = PrioritizedReplayBuffer(cap, alpha, eps, frame_shape=(8, 8, 4))
+    ref = so.SumTree(cap)
+    frames_ref = np.zeros((cap, 8, 8, 4), np.uint8)
+    act_ref, rew_ref = np.zeros(cap, np.int64), np.zeros(cap, F32)
+    # empty buffer: weights 0, no NaN
+    e = buf.sample(16, beta, cu(np.full(16, 0.5, F32)))
+    assert tc.isfinite(e['weights']).all() and float(e['weights'].abs().sum()) == 0.0
+    cursor = 0
+    for n in (700, 500):                                           # the second add wraps around
+        fr = rs.randint(0, 256, size=(n, 8, 8, 4)).astype(np.uint8)
+        ac, rw, dn = rs.randint(0, 6, size=n).astype(np.int64), rs.standard_normal(n).astype(F32), (rs.uniform(size=n) < 0.1).astype(F32)
+        slots = buf.add(cu(fr), cu(ac), cu(rw), cu(dn)).cpu().numpy()
+        want = (np.arange(n) + cursor) % cap
+        assert np.array_equal(slots, want)
+        frames_ref[want], act_ref[want], rew_ref[want] = fr, ac, rw
+        ref.update(want, np.ones(n, F32))
+        cursor = (cursor + n) % cap
+    assert buf.count == cap and buf.cursor == 1200 % cap
+    assert np.array_equal(buf.index.tree.tree.cpu().numpy().view(np.uint32), ref.tree.view(np.uint32))
+    # TD-error priorities for a batch, then a sampled batch
+    upd = rs.permutation(cap)[:300].astype(np.int64)
+    td = rs.standard_normal(300).astype(F32)
+    buf.update_priorities(cu(upd), cu(td))
+    pr_dev = buf.index.tree.leaves[cu(upd)].cpu().numpy()                     # (|td| + eps)^alpha as the device computed it
+    np.testing.assert_allclose(pr_dev, (np.abs(td.astype(np.float64)) + eps) ** alpha, rtol=2e-6)
+    ref.update(upd, pr_dev)                                                   # same priorities -> same tree, bit for bit
+    assert np.array_equal(buf.index.tree.tree.cpu().numpy().view(np.uint32), ref.tree.view(np.uint32))
+    uni = rs.uniform(size=512).astype(F32)
+    s = buf.sample(512, beta, cu(uni), gather=True)
+    i_ref, p_ref, w_ref = ref.per_sample(uni, float(cap), beta)
+    idx = s['idx'].cpu().numpy()
+    assert np.array_equal(idx, i_ref) and np.array_equal(s['priorities'].cpu().numpy(), p_ref)
+    np.testing.assert_allclose(s['weights'].cpu().numpy(), w_ref, rtol=2e-6)
+    assert float(s['weights'].max()) == 1.0
+    assert np.array_equal(s['observations'].cpu().numpy(), frames_ref[idx])
+    assert np.array_equal(s['next_observations'].cpu().numpy(), frames_ref[(idx + 1) % cap])
+    assert np.array_equal(s['actions'].cpu().numpy(), act_ref[idx]) and np.array_equal(s['rewards'].cpu().numpy(), rew_ref[idx])
+    # the unfused path gives the same indices
+    i2, p2 = buf.index.tree.sample(buf.index.tree.stratified_u(cu(uni)))
+    assert np.array_equal(i2.cpu().numpy(), i_ref)
+    # zero-priority leaves are never given an infinite weight
+    ix = PrioritizedReplayIndex(64)
+    ix.add(cu(np.arange(8, dtype=np.int64)))
+    ix.tree.update(cu(np.array([3], np.int64)), cu(np.array([0.0], F32)))
+    _, _, w = ix.sample(32, 1.0, cu(rs.uniform(size=32).astype(F32)))
+    assert tc.isfinite(w).all()
