@@ -17,14 +17,28 @@ def library_path() -> str:
 
 
 def register(drl_module=None):
-    """Expose the fused classes under new `cls_name`s in the reference's lookup namespaces
-    (script.py:55-58 algos, launch.py:174-176 architectures, credit_assignment.py:40-42), so that a
-    YAML config selects them by name."""
+    """Expose the fused classes under new `cls_name`s in the reference's lookup namespaces, so that a YAML config selects
+    them by name:
+      algos            getattr(drl.algos, cls_name)                              script.py:55-58         FusedPPO
+      credit ops       getattr(drl.algos.common.credit_assignment, cls_name)      credit_assignment.py:40-42  FusedGAE, FusedNStepAdvantageEstimator
+      architectures    getattr(drl.agents.architectures, cls_name)                launch.py:174-176       FusedNatureCNN, FusedLinear
+      heads            getattr(drl.agents.heads, cls_name)                        launch.py:232-233       FusedCategoricalPolicyHead, FusedSimpleValueHead
+      preprocessing    getattr(drl.agents.preprocessing, cls_name)                launch.py:140-142       FusedToChannelMajor
+    The reference's own names stay untouched."""
     from . import algos, agents
-    if drl_module is None:
-        import drl as drl_module  # the reference package, if importable
+    from .algos import credit_assignment as ca
     import importlib
-    importlib.import_module('drl.algos').FusedPPO = algos.PPO
-    importlib.import_module('drl.algos.common.credit_assignment').FusedGAE = algos.GAE
-    importlib.import_module('drl.agents.architectures').FusedNatureCNN = agents.NatureCNN
+    if drl_module is None:
+        drl_module = importlib.import_module('drl')  # the reference package, if importable
+    table = {
+        'drl.algos': {'FusedPPO': algos.PPO},
+        'drl.algos.common.credit_assignment': {'FusedGAE': algos.GAE, 'FusedNStepAdvantageEstimator': ca.NStepAdvantageEstimator},
+        'drl.agents.architectures': {'FusedNatureCNN': agents.NatureCNN, 'FusedLinear': agents.Linear},
+        'drl.agents.heads': {'FusedCategoricalPolicyHead': agents.CategoricalPolicyHead, 'FusedSimpleValueHead': agents.SimpleValueHead},
+        'drl.agents.preprocessing': {'FusedToChannelMajor': agents.ToChannelMajor},
+    }
+    for mod, names in table.items():
+        m = importlib.import_module(mod)
+        for name, cls in names.items():
+            setattr(m, name, cls)
     return drl_module

@@ -1,5 +1,6 @@
 """Runs a few full-size learner steps (32 768 samples) on cuda:0 — the target of the ncu captures
-whose summaries live under profiles/.  Usage: python scripts/one_step.py [steps] [precision] [debug flags "2=1,3=0"]"""
+whose summaries live under profiles/.  Usage: python scripts/one_step.py [steps] [precision] [debug flags "6=1,7=3"] [ppo|rnd]
+`rnd`: RND predictor steps (RandomNetworkDistillation.learn_rows) on the same frames instead of PPO learner steps."""
 import os
 import sys
 
@@ -37,6 +38,16 @@ hyper = ops.make_hyper(A, [1.0], 0.2, 0.01, 1.0, False, True)
 batch = ops.make_batch(d['actions'], d['logprobs'], [d['advantages']['extrinsic']], [d['vpreds']['extrinsic']],
                        [d['vtargs']['extrinsic']])
 rs = np.random.RandomState(0)
+if len(sys.argv) > 4 and sys.argv[4] == 'rnd':
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
+    rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=32, max_batch=n_envs * B, device=dev, precision=precision)
+    rnd._synced_normalizer.moment2.fill_(1.0)
+    for s in range(steps):
+        rows = np.concatenate([rs.permutation(T)[:B] + e * st.Tp for e in range(n_envs)]).astype(np.int64)
+        loss = rnd.learn_rows(d['observations'], tc.as_tensor(rows, device=dev))
+    tc.cuda.synchronize()
+    print('rnd loss', float(loss.item()))
+    sys.exit(0)
 for s in range(steps):
     rows = np.concatenate([rs.permutation(T)[:B] + e * st.Tp for e in range(n_envs)]).astype(np.int64)
     losses = eng.ppo_step(d['observations'], tc.as_tensor(rows, device=dev), batch, hyper)

@@ -309,3 +309,40 @@ def test_checkpoint_objects_round_trip_through_the_reference_checkpointing(tmp_p
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_register_resolves_fused_classes_through_the_reference_lookups():
+    """INTEGRATION.md §3 end to end (reference mounted; skipped elsewhere): after `pytorch_drl_b200.register()` the reference's
+    OWN lookup functions — script.py:55-58 `get_algo_cls`, launch.py:174-176 `get_architecture_cls`, launch.py:140-142
+    `get_preprocessing`, credit_assignment.py:40-42 `get_credit_assignment_op(s)` — resolve the Fused* names to the drop-ins,
+    build them from YAML-style cls_args, and the reference's own names still resolve to the reference's classes."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not mounted')
+    drl = ref_loader.load()
+    import importlib.util
+    assert pkg.register() is drl
+    spec = importlib.util.spec_from_file_location('ref_script', os.path.join(ref_loader.REFERENCE_ROOT, 'script.py'))
+    script = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(script)                                  # defines get_algo_cls; `main` is guarded
+    from drl.utils import launch
+    from drl.algos.common import credit_assignment as ref_ca
+    from drl.algos import PPO as RefPPO
+    assert script.get_algo_cls('FusedPPO') is algos.PPO and script.get_algo_cls('PPO') is RefPPO
+    assert launch.get_architecture_cls('FusedNatureCNN') is agents.NatureCNN
+    assert launch.get_architecture_cls('NatureCNN') is not agents.NatureCNN
+    assert isinstance(launch.get_preprocessing('FusedToChannelMajor', {}), agents.ToChannelMajor)
+    ops_ = ref_ca.get_credit_assignment_ops({'extrinsic': {'cls_name': 'FusedGAE', 'cls_args': {'gamma': 0.99, 'lambda_': 0.95, 'use_dones': True}},
+                                             'intrinsic_rnd': {'cls_name': 'FusedGAE', 'cls_args': {'gamma': 0.99, 'lambda_': 0.95, 'use_dones': False}}})
+    assert all(isinstance(o, algos.GAE) for o in ops_.values()) and isinstance(ref_ca.get_credit_assignment_op('GAE', dict(gamma=0.9, lambda_=0.9, use_dones=True)), ref_ca.GAE)
+    # the architecture / head factories of launch.py feed YAML cls_args + initialisers verbatim: the drop-ins accept them
+    import importlib
+    heads = importlib.import_module('drl.agents.heads')
+    arch = launch.get_architecture_cls('FusedNatureCNN')(img_channels=4, w_init=lambda w: tc.nn.init.orthogonal_(w, gain=1.4142),
+                                                         b_init=tc.nn.init.zeros_)
+    pol = heads.FusedCategoricalPolicyHead(num_features=512, num_actions=6, head_architecture_cls=launch.get_architecture_cls('FusedLinear'),
+                                           head_architecture_cls_args={}, w_init=None, b_init=None)
+    val = heads.FusedSimpleValueHead(num_features=512, head_architecture_cls=launch.get_architecture_cls('FusedLinear'),
+                                     head_architecture_cls_args={}, w_init=None, b_init=None)
+    ag = agents.Agent([launch.get_preprocessing('FusedToChannelMajor', {})], arch, {'policy': pol, 'value_extrinsic': val})
+    assert list(ag.state_dict().keys()) == param_names(['value_extrinsic'])
