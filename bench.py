@@ -539,12 +539,38 @@ def run_e2e(algo, st, rollout, n_envs, dev, world, args, allmax, barrier):
     el = allmax(ev0.elapsed_time(ev1))
     assert all(np.isfinite(list(m.values())).all() for m in algo.last_epoch_metrics)
     steps_per_call = epochs * (T // B)
-    return {'value': samples * world / (el / n_calls * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d),
-            'd2h_bytes_per_step': 20 * epochs, 'ms_per_step': el / n_calls, 'wall_ms_per_step': 1e3 * wall / n_calls,
-            'step': f'one PPO.optimize_host call = upload + annotate + GAE + {steps_per_call} learner steps + {epochs} metrics passes',
-            'calls': n_calls, 'update_samples_per_call': samples,
-            'h2d_GBps': h2d / (el / n_calls * 1e-3) / 1e9,
-            'api': 'PPO.optimize_host(pinned host rollout, RolloutStorage)'}
+    out = {'value': samples * world / (el / n_calls * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d),
+           'd2h_bytes_per_step': 20 * epochs, 'ms_per_step': el / n_calls, 'wall_ms_per_step': 1e3 * wall / n_calls,
+           'step': f'one PPO.optimize_host call = upload + annotate + GAE + {steps_per_call} learner steps + {epochs} metrics passes',
+           'calls': n_calls, 'update_samples_per_call': samples,
+           'h2d_GBps': h2d / (el / n_calls * 1e-3) / 1e9,
+           'api': 'PPO.optimize_host(pinned host rollout, RolloutStorage)'}
+    # Secondary figure, NOT the reference's strictly on-policy schedule: the next rollout is uploaded (double-buffered storage)
+    # while the current one is optimised — what an actor-learner pipeline that streams frames to the device during collection
+    # achieves.  Every call still contains one full upload; reported beside, never instead of, the sequential number above.
+    try:
+        from pytorch_drl_b200 import algos
+        st2 = algos.RolloutStorage(n_envs, T, st.reward_keys, dev)
+        stores = [st, st2]
+        pending = algo.upload_rollout(host, stores[0])
+        barrier()
+        p0, p1 = tc.cuda.Event(enable_timing=True), tc.cuda.Event(enable_timing=True)
+        p0.record()
+        for c in range(n_calls):
+            cur = stores[c % 2]
+            rollout_c = algo.annotate_uploaded(cur, pending)
+            pending = algo.upload_rollout(host, stores[(c + 1) % 2])     # next rollout's upload overlaps this rollout's epochs
+            algo.optimize(rollout_c)
+        p1.record()
+        tc.cuda.synchronize()
+        elp = allmax(p0.elapsed_time(p1))
+        out['pipelined'] = {'value': samples * world / (elp / n_calls * 1e-3), 'ms_per_step': elp / n_calls,
+                            'note': 'upload of rollout k+1 overlapped with optimize of rollout k (two device storages); off-policy by one rollout, '
+                                    'so it is a secondary figure'}
+        del st2
+    except Exception as ex:                                   # noqa: BLE001
+        out['pipelined'] = {'error': repr(ex)[:200]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------

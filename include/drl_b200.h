@@ -178,6 +178,9 @@ int drl_net_ppo_metrics(drl_net_t* net, const uint8_t* obs, const int64_t* row_i
 int drl_net_activation(drl_net_t* net, int which, const void** ptr, int64_t* elems, int* dtype_bytes);
 /* device-to-device copy on `stream` (lets a binding read handle-owned buffers). */
 int drl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* Copy done by a kernel (no copy engine): src may be pinned host memory; bytes and both pointers multiples of 4.  Used for the
+ * per-epoch minibatch indices so that they never queue behind a bulk rollout upload. */
+int drl_copy_by_kernel(void* dst, const void* src, size_t bytes, void* stream);
 
 /* =============================================================================================
  * Optimiser — replaces torch.optim.Adam.step as configured by drl/utils/optimization.py:9-35

@@ -65,6 +65,7 @@ PROTOTYPES = {
                                     POINTER(PpoHyper), c_void_p, c_void_p]),
     'drl_net_activation': (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]),
     'drl_memcpy_d2d': (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    'drl_copy_by_kernel': (c_int, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     'drl_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                               c_double, c_double, c_int64, c_float, c_void_p]),
     'drl_net_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,

@@ -274,7 +274,26 @@ class PPO:
             it = iter(s)
             blocks.append(np.stack([next(it) for _ in range(steps)]).astype(np.int64) + e * Tp)      # [steps, B]
         idx = np.ascontiguousarray(np.stack(blocks, axis=1).reshape(steps, -1))                       # [steps, n_envs * B]
-        return tc.as_tensor(idx).to(self._engine.device, non_blocking=False)
+        # pinned staging (two buffers: an epoch's host sync at its metrics read separates the reuses) + a copy KERNEL: the copy
+        # engines stay free for rollout uploads, and nothing here synchronises the host
+        from .. import _lib
+        ring = getattr(self, '_idx_ring', None)
+        if ring is None or ring[0].numel() != idx.size:
+            ring = [tc.empty(idx.size, dtype=tc.int64).pin_memory() for _ in range(2)]
+            self._idx_ring, self._idx_turn = ring, 0
+            self._idx_events = [None, None]
+        slot = self._idx_turn % 2
+        self._idx_turn += 1
+        if self._idx_events[slot] is not None:
+            self._idx_events[slot].synchronize()      # the kernel that read this staging buffer two epochs ago has run
+        host = ring[slot]
+        host.numpy()[:] = idx.reshape(-1)
+        dev = tc.empty(idx.shape, dtype=tc.int64, device=self._engine.device)
+        _lib.check(_lib.lib().drl_copy_by_kernel(_lib.ptr(dev), host.data_ptr(), idx.size * 8, _lib.current_stream()), 'copy_by_kernel')
+        ev = tc.cuda.Event()
+        ev.record()
+        self._idx_events[slot] = ev
+        return dev
 
     def optimize(self, rollout: Dict[str, Any]) -> None:
         """ppo.py:242-281: opt_epochs x T/B learner steps (+ the per-epoch full-rollout metrics pass
@@ -301,36 +320,52 @@ class PPO:
         if self._policy_scheduler:
             self._policy_scheduler.step()
 
-    def optimize_host(self, host: Mapping[str, Any], storage: 'RolloutStorage', chunk_envs: int = 128) -> Dict[str, Any]:
-        """collect() -> optimize() for a rollout the actors left in (pinned) HOST memory: the uint8 frames are uploaded ONCE per
-        rollout (not once per minibatch: a rollout is consumed opt_epochs times), in env chunks on a copy stream; each chunk's
-        annotate forward (abstract.py:383-411) runs as soon as it has landed, overlapping the rest of the upload; then
-        credit assignment and the epochs.  `host` holds observations [n_envs, >= T+1, 84, 84, 4] uint8, actions, dones and
-        rewards{key}, laid out like `storage`.  Returns the device rollout."""
+    def upload_rollout(self, host: Mapping[str, Any], storage: 'RolloutStorage', chunk_envs: int = 128):
+        """Start the host-to-device copy of a rollout the actors left in (pinned) HOST memory: scalars first, then the uint8 frames
+        in env chunks on a copy stream.  Returns the per-chunk events `annotate_uploaded` waits on.  The copy stream first waits
+        for the work already queued on the current stream (earlier readers of `storage`)."""
         d = storage.as_dict()
         dev = self._engine.device
-        n = storage.n_envs
         main = tc.cuda.current_stream(dev)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = tc.cuda.Stream(device=dev)
         cs = self._copy_stream
-        cs.wait_stream(main)                                            # the previous rollout's readers are done
+        cs.wait_stream(main)
         events = []
         with tc.cuda.stream(cs):
             for k in ('actions', 'dones'):
                 d[k].copy_(host[k], non_blocking=True)
             for k in storage.reward_keys:
                 d['rewards'][k].copy_(host['rewards'][k], non_blocking=True)
-            for e0 in range(0, n, chunk_envs):
-                e1 = min(n, e0 + chunk_envs)
-                d['observations'][e0:e1].copy_(host['observations'][e0:e1], non_blocking=True)
+            for e0 in range(0, storage.n_envs, chunk_envs):
+                e1 = min(storage.n_envs, e0 + chunk_envs)
+                # copies of <= 32 MB: the host-to-device copy engine serves one copy at a time, so anything else that needs it (the
+                # per-epoch index upload of an optimize() running concurrently) waits for at most one of these, not for 0.5 GB
+                for c0 in range(e0, e1, 8):
+                    c1 = min(e1, c0 + 8)
+                    d['observations'][c0:c1].copy_(host['observations'][c0:c1], non_blocking=True)
                 ev = tc.cuda.Event()
                 ev.record(cs)
                 events.append((e0, e1, ev))
+        return events
+
+    def annotate_uploaded(self, storage: 'RolloutStorage', events) -> Dict[str, Any]:
+        """annotate (abstract.py:383-411) chunk by chunk as the uploads land, then credit assignment."""
+        d = storage.as_dict()
+        main = tc.cuda.current_stream(self._engine.device)
         for e0, e1, ev in events:
             main.wait_event(ev)
             self.annotate(d, envs=range(e0, e1))
-        rollout = self.credit_assignment(d)
+        return self.credit_assignment(d)
+
+    def optimize_host(self, host: Mapping[str, Any], storage: 'RolloutStorage', chunk_envs: int = 128) -> Dict[str, Any]:
+        """collect() -> optimize() for a rollout in pinned host memory: the uint8 frames are uploaded ONCE per rollout (not once
+        per minibatch: a rollout is consumed opt_epochs times); each env chunk's annotate forward runs as soon as it has landed,
+        overlapping the rest of the upload; then credit assignment and the epochs.  `host` holds observations
+        [n_envs, >= T+1, 84, 84, 4] uint8, actions, dones and rewards{key}, laid out like `storage`.  Returns the device rollout.
+        (The learner steps cannot start earlier: every step draws B samples of EVERY env, and the advantages need the whole
+        trajectory's value predictions.)"""
+        rollout = self.annotate_uploaded(storage, self.upload_rollout(host, storage, chunk_envs))
         self.optimize(rollout)
         return rollout
 

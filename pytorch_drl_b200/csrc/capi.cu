@@ -50,3 +50,24 @@ extern "C" int drl_memcpy_d2d(void* dst, const void* src, size_t bytes, void* st
   DRL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, drl::as_stream(stream)));
   return DRL_OK;
 }
+
+// Copy by a kernel instead of a copy engine: `src` may be PINNED HOST memory (unified addressing: the SMs read it over PCIe).  For
+// small host-to-device transfers that must not queue behind bulk uploads on the host-to-device copy engine (the per-epoch
+// minibatch indices of PPO.optimize while the next rollout is being uploaded).
+namespace drl {
+__global__ void __launch_bounds__(256) copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace drl
+
+extern "C" int drl_copy_by_kernel(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return DRL_ERR_BAD_ARG;
+  if ((bytes & 3) || (reinterpret_cast<uintptr_t>(dst) & 3) || (reinterpret_cast<uintptr_t>(src) & 3)) return DRL_ERR_MISALIGNED;
+  if (bytes == 0) return DRL_OK;
+  const int64_t n = (int64_t)(bytes / 4);
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 296) blocks = 296;
+  drl::copy_words_kernel<<<blocks, 256, 0, drl::as_stream(stream)>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), n);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}

@@ -198,9 +198,9 @@ static int ppo_common(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx
     DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, /*overlap_comm=*/true, st)
                  : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
   if (grads && net->comm && comm_world(net->comm) > 1) {
-    // bf16 engine: the fc + heads range is already in flight (queued after the fc weight gradient); here the rest.
-    // fp32 engine: the whole buffer.
-    const int64_t lo = 0, hi = bf16 ? net->off[6] : net->nparams;
+    // bf16 engine: the fc + heads range (queued after the fc weight gradient) and the conv2 + conv3 range (after conv2's weight
+    // gradient) are already in flight; here conv1's.  fp32 engine: the whole buffer.
+    const int64_t lo = 0, hi = bf16 ? net->off[2] : net->nparams;
     DRL_TRY(comm_allreduce_after(net->comm, grads, lo, hi, st));
     DRL_TRY(comm_join(net->comm, st));
   }

@@ -398,6 +398,9 @@ int bf16_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, 
     DRL_TRY((launch_wgrad_conv<64, 4, 4, 6>("conv2_wgrad", n->act[0], 20, 10, 10, 20, n->dact[1], 9, 9, 10, 10, nb, w, st)));
     DRL_TRY(wgrad_untranspose("conv2_wgrad_t", w.gt, g + o[2], 32, 16, 64, st));
   }
+  // conv2 + conv3 weights and biases are final (conv2's bias gradient came from conv3's data gradient): second overlapped
+  // bucket; only conv1's 8 224 floats remain for the exchange after the last kernel
+  if (overlap_comm && n->comm && comm_world(n->comm) > 1) DRL_TRY(comm_allreduce_after(n->comm, g, o[2], o[6], st));
   {
     // the four parity classes of the stride-2 transposed convolution share their 2x2-tap gather over dY2:
     // ONE GEMM with N = 4 classes x 32 ci; column chunk `cls` lands on output pixel (2u + cls/2, 2v + cls%2).
