@@ -753,6 +753,9 @@ def run_extras(algo, agent, rollout, st, n_envs, dev, ms_per_step, pk, hyper, ba
     out['update_with_metrics_pass'] = {
         'samples_per_s': n_envs * T / ((steps_per_epoch * ms_per_step + ms_metrics) * 1e-3),
         'note': f'one epoch = {steps_per_epoch} learner steps ({n_envs * T} update samples) + one forward-only pass over the same {n_envs * T} samples'}
+    # ---- actor side: one environment step of all envs of a rank = frames H2D into the ring + policy forward
+    #      + draw + actions D2H; the reference does one batch-1 forward per environment step (rollout.py:280-288) ----
+    out['actor'] = run_actor_extras(agent, n_envs, dev)
     # ---- PER sum-tree (config 4): 2^20 leaves, batch 512 — dependent-access latency bound; parity unpinned (no reference code) ----
     out['sumtree'] = run_sumtree_extras(dev, g)
     return out
@@ -780,6 +783,48 @@ def graph_timed(fn, iters=50):
     except Exception as ex:                                   # noqa: BLE001
         tc.cuda.synchronize()
         return timed(fn, iters=iters), f'eager launches ({type(ex).__name__})'
+
+
+def run_actor_extras(agent, n_envs, dev):
+    from pytorch_drl_b200 import _lib, algos
+    from pytorch_drl_b200._lib import current_stream, ptr
+    L = _lib.lib()
+    eng = agent.engine
+    r = algos.DeviceRollout(n_envs, 7, 0, REWARD_KEYS, dev)
+    d = r.storage.data
+    r.staging_frames()[...] = np.random.RandomState(3).randint(0, 256, size=(n_envs, 84, 84, 4), dtype=np.uint8)
+    acts = tc.empty(n_envs, dtype=tc.int64, device=dev)
+    h_acts = tc.empty(n_envs, dtype=tc.int64).pin_memory()
+    rows = [r.rows_at(t) for t in range(8)]
+    k = [0]
+
+    def upload():
+        r.write_frames(k[0] % 8, r.staging_frames())
+
+    def act():
+        k[0] += 1
+        rc = L.drl_net_act(eng._h, ptr(d['observations']), ptr(rows[k[0] % 8]), n_envs, None, 1, k[0], ptr(acts), None, None, None,
+                           current_stream())
+        assert rc == 0
+    ms_up = timed(upload, iters=20, warm=3)
+    ms_act = timed(act, iters=50, warm=5)
+
+    def tick():                                     # what BatchedRolloutManager does per time step, minus env.step itself
+        upload()
+        act()
+        h_acts.copy_(acts, non_blocking=True)
+        tc.cuda.current_stream().synchronize()
+    for _ in range(3):
+        tick()
+    t0 = time.perf_counter()
+    for _ in range(30):
+        tick()
+    ms_tick = (time.perf_counter() - t0) / 30 * 1e3
+    return {'envs': n_envs, 'frames_h2d_ms': ms_up, 'frames_h2d_GBps': n_envs * 28224 / (ms_up * 1e-3) / 1e9,
+            'policy_forward_and_draw_ms': ms_act, 'forward_samples_per_s': n_envs / (ms_act * 1e-3),
+            'tick_wall_ms': ms_tick, 'env_steps_per_s_ceiling': n_envs / (ms_tick * 1e-3),
+            'what': 'per time step of all envs: pinned frames -> their ring slot (one strided H2D copy), drl_net_act on those rows (bf16 engine, '
+                    'in-kernel Philox draw), actions D2H + sync; env.step itself (host) not included'}
 
 
 def run_sumtree_extras(dev, g):

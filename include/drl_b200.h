@@ -324,6 +324,32 @@ int drl_ring_gather(const void* ring, int64_t cap, int64_t row_bytes, const int6
 int drl_probe_dependent_latency(const int* ring, int hops, float* cycles_per_hop_out, void* stream);
 
 /* =============================================================================================
+ * Actor side — the steps immediately before the learner path, for all environments of a rank per call.
+ *
+ * drl_sample_actions_f32 / drl_net_act replace RolloutManager._choose_action (drl/algos/common/rollout.py:280-288: one
+ * batch-1 forward + Categorical.sample() per environment step).  Categorical.sample() is torch.multinomial(probs, 1), i.e.
+ * argmax_a probs[a] / q[a] with q ~ Exp(1): `noise` [n, A] supplies the q variates (then the draw equals the reference's draw
+ * for the same generator state); noise == NULL generates them in the kernel with Philox4x32-10 keyed by `seed`, counter =
+ * (row, `counter`) — pass the environment step number.  logp_out (nullable) receives log pi(a|s).
+ * drl_net_act = drl_net_forward on rows `row_idx` of the frame store + the draw; logits_out / values_out are nullable.
+ * --------------------------------------------------------------------------------------------- */
+int drl_sample_actions_f32(const float* logits, int64_t n, int num_actions, const float* noise, uint64_t seed,
+                           uint64_t counter, int64_t* actions_out, float* logp_out, void* stream);
+int drl_net_act(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* noise, uint64_t seed,
+                uint64_t counter, int64_t* actions_out, float* logp_out, float* logits_out, float* values_out, void* stream);
+/* Rollout.record / record_nexts (rollout.py:159-195) for all n_envs environments of a rank: writes time step `t` of the
+ * device-resident stores laid out [n_envs, pitch_steps, ...] (uint8 frames 84x84x4, int64 actions, float dones and one float
+ * array per reward stream).  Every source pointer is nullable (record_nexts passes frames + actions only) and may be device
+ * memory or pinned host memory; obs_on_host != 0 copies the frames with one strided host-to-device copy straight into place. */
+int drl_rollout_record(uint8_t* obs_store, int64_t* act_store, float* done_store, float* const* reward_stores, int n_streams,
+                       int n_envs, int64_t pitch_steps, int t, const uint8_t* obs_t, const int64_t* a_t, const float* d_t,
+                       const float* const* r_t, int obs_on_host, void* stream);
+/* The extra_steps carry-over of Rollout.report (rollout.py:213-223): `count` time steps [src_t0, src_t0+count) of every
+ * environment of one [n_envs, pitch, step_bytes] array to steps [dst_t0, ...) of another (step_bytes a multiple of 4). */
+int drl_rollout_copy_steps(void* dst, const void* src, int n_envs, int64_t dst_pitch_steps, int64_t src_pitch_steps,
+                           int64_t step_bytes, int dst_t0, int src_t0, int count, void* stream);
+
+/* =============================================================================================
  * Gradient exchange — replaces the DistributedDataParallel wrapper (drl/utils/launch.py:310;
  * allreduce inside backward, drl/algos/ppo.py:233) and global_mean
  * (drl/algos/common/metrics.py:8-26).  One process per GPU; the communicator is created from

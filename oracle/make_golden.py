@@ -19,6 +19,8 @@ What is pinned (all from reference code, never from the oracle):
   dueling.npz    DuelingArchitecture.forward through SimpleDiscreteActionValueHead, and the probabilities of
                  EpsilonGreedyCategoricalPolicyHead  (dueling.py:50-57, action_value_heads.py:124-140,
                  policy_heads.py:197-226)
+  actor_rollout.npz RolloutManager.generate with the reference Agent on seeded synthetic environments: actions drawn,
+                 rewards / dones / frames recorded, extra_steps carry-over, episode metadata (rollout.py:105-357)
 Large tensors are stored as (sum, l2, strided sample) summaries to keep fixtures small.
 """
 import os
@@ -416,6 +418,53 @@ def gen_dueling():
     np.savez_compressed(os.path.join(GOLD, 'dueling.npz'), **out)
 
 
+def gen_actor_rollout():
+    """The reference RolloutManager (rollout.py:227-357) + Agent, one manager per synthetic environment under
+    torch.manual_seed(env_seed(e)): two consecutive generate() calls (extra_steps > 0: carry-over) per environment."""
+    from oracle import actor_oracle as ao
+    from drl.algos.common.rollout import RolloutManager
+    from drl.agents.integration.agent import Agent
+    from drl.agents.preprocessing import ToChannelMajor
+    from drl.agents.architectures import NatureCNN, Linear
+    from drl.agents.heads import CategoricalPolicyHead, SimpleValueHead
+    import gym
+    c = ao.CFG
+    A = c['A']
+    preds = {'policy': CategoricalPolicyHead(512, A, Linear, {}, None, None),
+             'value_extrinsic': SimpleValueHead(512, Linear, {}, None, None)}
+    agent = Agent([ToChannelMajor()], NatureCNN(4, None, None), preds)
+    init = po.init_params(A, ['extrinsic'], seed=c['param_seed'])
+    agent.load_state_dict({k: tc.from_numpy(v.copy()) for k, v in init.items()}, strict=True)
+
+    class Env(ao.SynthActorEnv, gym.core.Env):
+        def __init__(self, e):
+            ao.SynthActorEnv.__init__(self, e, A, as_float=True)
+            self.observation_space = gym.spaces.Box(0., 1., (84, 84, 4), np.float32)
+            self.action_space = gym.spaces.Discrete(A)
+
+        @property
+        def reward_spec(self):
+            from drl.envs.wrappers.stateless.abstract import RewardSpec
+            return RewardSpec(keys=['extrinsic_raw', 'extrinsic'])
+
+    out = {'cfg': np.array([c['E'], c['T'], c['extra_steps'], A, c['rollouts'], c['param_seed']])}
+    for e in range(c['E']):
+        tc.manual_seed(ao.env_seed(e))
+        env = Env(e)
+        mgr = RolloutManager(env, agent, c['T'], c['extra_steps'])
+        for k in range(c['rollouts']):
+            res = mgr.generate()
+            obs = np.rint(res['observations'].numpy() * 255.0).astype(np.uint8)
+            out[f'r{k}_e{e}_actions'] = res['actions'].numpy().astype(np.int64)
+            out[f'r{k}_e{e}_rew'] = res['rewards']['extrinsic'].numpy()
+            out[f'r{k}_e{e}_raw'] = res['rewards']['extrinsic_raw'].numpy()
+            out[f'r{k}_e{e}_dones'] = res['dones'].numpy()
+            out[f'r{k}_e{e}_obs_sum'] = ao.frame_checksums(obs)
+            for key, vals in res['metadata'].items():
+                out[f'r{k}_e{e}_md_{key}'] = np.asarray(vals, np.float64)
+    np.savez_compressed(os.path.join(GOLD, 'actor_rollout.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_loader.load()
@@ -428,6 +477,7 @@ def main():
     gen_reward_norm()
     gen_nstep_bellman()
     gen_dueling()
+    gen_actor_rollout()
     gen_ppo('ppo_2rank', ['extrinsic'], {'extrinsic': 1.0}, False, 29611)
     gen_ppo('ppo_2rank_rnd', ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},
             True, 29612)

@@ -8,7 +8,7 @@ everything else -> RuntimeError.
 import ctypes
 import os
 from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint8,
-                    c_void_p)
+                    c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libdrl_b200.so')
@@ -91,6 +91,12 @@ PROTOTYPES = {
     'drl_per_sample': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'drl_ring_gather': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'drl_probe_dependent_latency': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'drl_sample_actions_f32': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
+    'drl_net_act': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p]),
+    'drl_rollout_record': (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int64, c_int, c_void_p,
+                                   c_void_p, c_void_p, POINTER(c_void_p), c_int, c_void_p]),
+    'drl_rollout_copy_steps': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     'drl_nstep_advantages_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64,
                                          c_float, c_int, c_void_p, c_void_p]),
     'drl_bellman_backups_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64,

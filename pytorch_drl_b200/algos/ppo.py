@@ -388,10 +388,15 @@ class PPO:
         `rollout_source()` -> (RolloutStorage dict with frames / actions / rewards / dones filled, metadata); annotate and
         credit assignment run here, on the device."""
         src = getattr(self, 'rollout_source', None)
-        if src is None:
-            raise NotImplementedError('set algo.rollout_source = callable returning (rollout, metadata): the fused path replaces '
-                                      'the learner half; env stepping stays with the reference\'s RolloutManager')
-        rollout, metadata = src()
+        mgr = getattr(self, 'rollout_mgr', None)
+        if src is not None:
+            rollout, metadata = src()
+        elif mgr is not None:                      # a BatchedRolloutManager (algos/rollout.py), like self._rollout_mgr of the reference
+            rollout = mgr.generate()
+            metadata = rollout.pop('metadata')
+        else:
+            raise NotImplementedError('set algo.rollout_mgr = BatchedRolloutManager(envs, policy_net, ...) or algo.rollout_source = '
+                                      'callable returning (rollout, metadata)')
         rollout = self.credit_assignment(self.annotate(rollout))
         self._global_step += self._world_size * self._envs_per_rank * self._rollout_len        # abstract.py:185
         return rollout, metadata

@@ -1172,3 +1172,180 @@ def test_prioritized_replay_buffer_vs_oracle():
     ix.tree.update(cu(np.array([3], np.int64)), cu(np.array([0.0], F32)))
     _, _, w = ix.sample(32, 1.0, cu(rs.uniform(size=32).astype(F32)))
     assert tc.isfinite(w).all()
+
+
+# ---- actor side: batched policy sampling + the rollout ring ---------------------------------------------
+@pytest.mark.parametrize('A', [6, 18])
+def test_sample_actions_with_supplied_noise_equals_torch_multinomial_draw(A):
+    """argmax(probs / q): bit-exact vs the oracle's restatement of torch.multinomial (index work); log-probabilities 1e-6."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(A)
+    n = 5000
+    logits = (rs.standard_normal((n, A)) * 2).astype(F32)
+    noise = tc.empty(n, A).exponential_(1, generator=tc.Generator().manual_seed(3)).numpy()
+    acts = tc.empty(n, dtype=tc.int64, device=dev())
+    logp = tc.empty(n, dtype=tc.float32, device=dev())
+    d_logits, d_noise = cu(logits), cu(noise)
+    st = L.drl_sample_actions_f32(d_logits.data_ptr(), n, A, d_noise.data_ptr(), 0, 0, acts.data_ptr(), logp.data_ptr(), None)
+    assert st == 0
+    ref = ao.sample_actions(logits, noise)
+    got = acts.cpu().numpy()
+    # expf on the device vs the host differs in the last ulp: a draw can only differ where the two best scores tie to 1e-6
+    p = tc.softmax(tc.from_numpy(logits), -1).numpy() / noise
+    top2 = np.sort(p, axis=1)[:, -2:]
+    near_tie = (top2[:, 1] - top2[:, 0]) <= 1e-5 * top2[:, 1]
+    assert ((got == ref) | near_tie).all() and near_tie.sum() < 5
+    ref_logp = tc.log_softmax(tc.from_numpy(logits), -1).numpy()[np.arange(n), got]
+    np.testing.assert_allclose(logp.cpu().numpy(), ref_logp, rtol=1e-5, atol=2e-6)
+    # argument errors like the rest of the ABI
+    assert L.drl_sample_actions_f32(None, n, A, None, 0, 0, acts.data_ptr(), None, None) == 2
+    assert L.drl_sample_actions_f32(d_logits.data_ptr(), n, 0, None, 0, 0, acts.data_ptr(), None, None) == 1
+
+
+def test_sample_actions_in_kernel_philox_follows_the_policy_distribution():
+    from pytorch_drl_b200 import _lib
+    L = _lib.lib()
+    A, n = 6, 400000
+    row = np.array([0.3, -1.2, 2.0, 0.0, 1.1, -3.0], F32)
+    logits = cu(np.tile(row, (n, 1)))
+    p = np.exp(row - row.max()); p /= p.sum()
+
+    def draw(seed, counter):
+        acts = tc.empty(n, dtype=tc.int64, device=dev())
+        assert L.drl_sample_actions_f32(logits.data_ptr(), n, A, None, seed, counter, acts.data_ptr(), None, None) == 0
+        return acts.cpu().numpy()
+    a0, a0b, a1, a2 = draw(5, 0), draw(5, 0), draw(5, 1), draw(6, 0)
+    assert (a0 == a0b).all()                                         # a pure function of (seed, counter, row)
+    assert (a0 != a1).mean() > 0.3 and (a0 != a2).mean() > 0.3       # new step / new seed -> new draws
+    freq = np.bincount(a0, minlength=A) / n
+    sigma = np.sqrt(p * (1 - p) / n)
+    assert (np.abs(freq - p) < 5 * sigma + 1e-6).all(), (freq, p)
+    # rows are independent: neighbouring rows agree no more often than sum p^2
+    assert abs((a0[1:] == a0[:-1]).mean() - (p * p).sum()) < 5e-3
+
+
+def _fused_agent(precision, A, max_batch, seed):
+    from pytorch_drl_b200 import agents
+    agent = agents.Agent([agents.ToChannelMajor()], agents.NatureCNN(4),
+                         {'policy': agents.CategoricalPolicyHead(512, A), 'value_extrinsic': agents.SimpleValueHead(512)})
+    agent.load_state_dict({k: tc.from_numpy(v) for k, v in po.init_params(A, ['extrinsic'], seed).items()})
+    return agent.fuse(max_batch=max_batch, precision=precision)
+
+
+def test_batched_rollout_manager_vs_reference_rollout_manager_golden(golden_dir):
+    """All environments of a rank through ONE BatchedRolloutManager == one reference RolloutManager per environment (the
+    golden was written by the unmodified reference): actions drawn, rewards, dones, frames, carry-over, episode metadata.
+    Integer / index / byte work: bit-exact.  The policy runs on the fp32 engine (a bf16 logit can flip a draw)."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200 import algos
+    g = np.load(os.path.join(golden_dir, 'actor_rollout.npz'))
+    E, T, extra, A, n_rollouts, pseed = [int(v) for v in g['cfg']]
+    agent = _fused_agent('fp32', A, 64, pseed)
+    envs = [ao.SynthActorEnv(e, A, as_float=(e == 1)) for e in range(E)]      # one env hands out float frames in [0, 1]
+    gens = [tc.Generator().manual_seed(ao.env_seed(e)) for e in range(E)]
+    mgr = algos.BatchedRolloutManager(envs, agent, T, extra,
+                                      noise=lambda step: tc.cat([ao.exponential_noise(gens[e], A) for e in range(E)]))
+    steps = T + extra
+    for k in range(n_rollouts):
+        res = mgr.generate()
+        md = res['metadata']
+        obs = res['observations'].cpu().numpy()
+        for e in range(E):
+            np.testing.assert_array_equal(res['actions'][e, :steps + 1].cpu().numpy(), g[f'r{k}_e{e}_actions'])
+            np.testing.assert_array_equal(res['rewards']['extrinsic'][e, :steps].cpu().numpy(), g[f'r{k}_e{e}_rew'])
+            np.testing.assert_array_equal(res['dones'][e, :steps].cpu().numpy(), g[f'r{k}_e{e}_dones'])
+            np.testing.assert_array_equal(ao.frame_checksums(obs[e, :steps + 1]), g[f'r{k}_e{e}_obs_sum'])
+        for key in ('ep_len', 'ep_ret', 'ep_len_raw', 'ep_ret_raw'):
+            want = np.concatenate([g[f'r{k}_e{e}_md_{key}'] for e in range(E)])
+            np.testing.assert_allclose(np.asarray(md[key], np.float64), want, rtol=1e-12, atol=1e-9)
+
+
+def test_batched_rollout_manager_vs_oracle_more_envs_no_extra_steps():
+    """17 environments, extra_steps = 0, three rollouts, against the oracle's restatement of the manager (pinned to the
+    reference by the golden above)."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200 import algos
+    E, T, A, n_rollouts, pseed = 17, 5, 6, 3, 4
+    agent = _fused_agent('fp32', A, 32, pseed)
+    params = po.init_params(A, ['extrinsic'], pseed)
+    envs = [ao.SynthActorEnv(e, A, as_float=False) for e in range(E)]
+    gens = [tc.Generator().manual_seed(ao.env_seed(e)) for e in range(E)]
+    mgr = algos.BatchedRolloutManager(envs, agent, T, 0,
+                                      noise=lambda step: tc.cat([ao.exponential_noise(gens[e], A) for e in range(E)]))
+    want = [ao.rollouts_oracle(params, e, T, 0, A, n_rollouts, ao.env_seed(e)) for e in range(E)]
+    for k in range(n_rollouts):
+        res = mgr.generate()
+        obs = res['observations'].cpu().numpy()
+        for e in range(E):
+            np.testing.assert_array_equal(res['actions'][e, :T + 1].cpu().numpy(), want[e][k]['actions'], err_msg=f'env {e}')
+            np.testing.assert_array_equal(res['rewards']['extrinsic'][e, :T].cpu().numpy(), want[e][k]['rewards'])
+            np.testing.assert_array_equal(res['dones'][e, :T].cpu().numpy(), want[e][k]['dones'])
+            np.testing.assert_array_equal(obs[e, :T + 1], want[e][k]['observations'])
+
+
+def test_device_rollout_record_report_like_the_reference_rollout():
+    """DeviceRollout.record / record_nexts / report (rollout.py:159-224) from host AND device sources against a numpy
+    emulation of the reference's per-environment buffers, including the extra_steps carry-over and the erased remainder."""
+    from pytorch_drl_b200.algos import DeviceRollout
+    N, T, extra = 5, 4, 3
+    steps = T + extra
+    r = DeviceRollout(N, T, extra, ['extrinsic', 'intrinsic'])
+    rs = np.random.RandomState(0)
+    ref = dict(obs=np.zeros((N, steps + 1, 84, 84, 4), np.uint8), act=np.zeros((N, steps + 1), np.int64),
+               ext=np.zeros((N, steps), F32), intr=np.zeros((N, steps), F32), done=np.zeros((N, steps), F32))
+    for k in range(3):
+        start = 0 if k == 0 else extra
+        for t in range(start, steps):
+            o = rs.randint(0, 256, size=(N, 84, 84, 4)).astype(np.uint8)
+            a = rs.randint(0, 6, size=N)
+            re, ri, d = rs.standard_normal(N).astype(F32), rs.uniform(size=N).astype(F32), (rs.uniform(size=N) < 0.3).astype(F32)
+            ref['obs'][:, t], ref['act'][:, t], ref['ext'][:, t], ref['intr'][:, t], ref['done'][:, t] = o, a, re, ri, d
+            if t % 2:       # device sources
+                r.record(t, cu(o), cu(a.astype(np.int64)), {'extrinsic': cu(re), 'intrinsic': cu(ri)}, cu(d))
+            else:           # host sources (numpy / lists)
+                r.record(t, o, a.tolist(), {'extrinsic': re, 'intrinsic': tc.from_numpy(ri)}, d)
+        o, a = rs.randint(0, 256, size=(N, 84, 84, 4)).astype(np.uint8), rs.randint(0, 6, size=N)
+        ref['obs'][:, steps], ref['act'][:, steps] = o, a
+        r.record_nexts(o, a)
+        res = r.report()
+        np.testing.assert_array_equal(res['observations'][:, :steps + 1].cpu().numpy(), ref['obs'])
+        np.testing.assert_array_equal(res['actions'][:, :steps + 1].cpu().numpy(), ref['act'])
+        np.testing.assert_array_equal(res['rewards']['extrinsic'][:, :steps].cpu().numpy(), ref['ext'])
+        np.testing.assert_array_equal(res['rewards']['intrinsic'][:, :steps].cpu().numpy(), ref['intr'])
+        np.testing.assert_array_equal(res['dones'][:, :steps].cpu().numpy(), ref['done'])
+        keep = {n: v[:, T:steps].copy() for n, v in ref.items()}          # rollout.py:213-223
+        for n in ref:
+            ref[n][:, :extra] = keep[n]
+        cur = r.storage.data                                              # the store now being recorded into
+        np.testing.assert_array_equal(cur['observations'][:, :extra].cpu().numpy(), ref['obs'][:, :extra])
+        np.testing.assert_array_equal(cur['actions'][:, :extra].cpu().numpy(), ref['act'][:, :extra])
+        np.testing.assert_array_equal(cur['dones'][:, :extra].cpu().numpy(), ref['done'][:, :extra])
+    with pytest.raises(ValueError):
+        r.record(0, np.zeros((N, 84, 84, 3), np.uint8), [0] * N, {'extrinsic': [0.] * N, 'intrinsic': [0.] * N}, [0.] * N)
+    with pytest.raises(KeyError):
+        r.record(0, np.zeros((N, 84, 84, 4), np.uint8), [0] * N, {'extrinsic': [0.] * N}, [0.] * N)
+
+
+@pytest.mark.parametrize('precision', _precisions())
+def test_training_loop_collects_through_the_batched_manager(precision, tmp_path):
+    """abstract.py:211-221 end to end on the device: collect (BatchedRolloutManager.generate + annotate + credit assignment)
+    -> optimize -> persist, two iterations, in-kernel Philox draws; the policy must have moved and a checkpoint must exist."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200 import agents, algos
+    A, T, B, E = 6, 8, 4, 6
+    agent = _fused_agent(precision, A, E * (T + 1), 3)
+    before = {k: v.clone() for k, v in agent.state_dict().items()}
+    opt = tc.optim.Adam(agent.parameters(), lr=1e-3, eps=1e-5)
+    algo = algos.PPO(rank=0, world_size=1, rollout_len=T, extra_steps=0,
+                     credit_assignment_ops={'extrinsic': algos.GAE(gamma=0.99, use_dones=True, lambda_=0.95)},
+                     global_step=0, max_steps=2 * E * T, checkpoint_frequency=E * T, checkpoint_dir=str(tmp_path),
+                     policy_net=agents.DDPShim(agent), policy_optimizer=opt, opt_epochs=2, learner_batch_size=B,
+                     envs_per_rank=E, sampler_seed=0)
+    algo.rollout_mgr = algos.BatchedRolloutManager([ao.SynthActorEnv(e, A, as_float=False) for e in range(E)], agent, T, 0, seed=11)
+    algo.training_loop()
+    assert algo._global_step == 2 * E * T
+    moved = max(float((agent.state_dict()[k].cpu() - before[k].cpu()).abs().max()) for k in before)
+    assert moved > 1e-5
+    assert any(f.endswith('.pth') for f in os.listdir(tmp_path))

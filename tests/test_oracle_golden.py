@@ -264,3 +264,22 @@ def test_dueling_and_epsilon_greedy_oracle_vs_reference_golden(golden_dir):
     # ties: the first maximum is the greedy action (torch.argmax)
     pr = do.epsilon_greedy_probs(np.array([[1., 3., 3., 0.]], np.float32), 0.2)
     np.testing.assert_allclose(pr, [[0.05, 0.85, 0.05, 0.05]], rtol=1e-6)
+
+
+def test_actor_rollout_oracle_vs_reference_rollout_manager_golden(golden_dir):
+    """oracle/actor_oracle.py (the RolloutManager / Rollout / Categorical.sample restatement) against the golden written by
+    the unmodified reference RolloutManager + Agent (oracle/make_golden.py::gen_actor_rollout): bit-exact."""
+    from oracle import actor_oracle as ao, ppo_oracle as po
+    g = np.load(os.path.join(golden_dir, 'actor_rollout.npz'))
+    E, T, extra, A, n_rollouts, pseed = [int(v) for v in g['cfg']]
+    params = po.init_params(A, ['extrinsic'], seed=pseed)
+    for e in range(E):
+        ros = ao.rollouts_oracle(params, e, T, extra, A, n_rollouts, ao.env_seed(e))
+        for k, ro in enumerate(ros):
+            np.testing.assert_array_equal(ro['actions'], g[f'r{k}_e{e}_actions'])
+            np.testing.assert_array_equal(ro['rewards'], g[f'r{k}_e{e}_rew'])
+            np.testing.assert_array_equal(ro['raw'], g[f'r{k}_e{e}_raw'])
+            np.testing.assert_array_equal(ro['dones'], g[f'r{k}_e{e}_dones'])
+            np.testing.assert_array_equal(ao.frame_checksums(ro['observations']), g[f'r{k}_e{e}_obs_sum'])
+            for key in ('ep_len', 'ep_ret', 'ep_len_raw', 'ep_ret_raw'):
+                np.testing.assert_allclose(np.asarray(ro['metadata'][key], np.float64), g[f'r{k}_e{e}_md_{key}'], rtol=1e-12, atol=1e-9)
