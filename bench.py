@@ -820,7 +820,29 @@ def run_actor_extras(agent, n_envs, dev):
     for _ in range(30):
         tick()
     ms_tick = (time.perf_counter() - t0) / 30 * 1e3
-    return {'envs': n_envs, 'frames_h2d_ms': ms_up, 'frames_h2d_GBps': n_envs * 28224 / (ms_up * 1e-3) / 1e9,
+    # frame_stack mode: single newest frames (7 KB per env) read by the stacking kernel straight from pinned host memory
+    newest, modes = r.staging_newest()
+    newest[...] = np.random.RandomState(4).randint(0, 256, size=newest.shape, dtype=np.uint8)
+    modes[...] = 0
+
+    def stack():
+        r.stack_frames(k[0] % 8, (k[0] + 1) % 8)
+    ms_stack = timed(stack, iters=20, warm=3)
+
+    def tick_fs():
+        stack()
+        act()
+        h_acts.copy_(acts, non_blocking=True)
+        tc.cuda.current_stream().synchronize()
+    for _ in range(3):
+        tick_fs()
+    t0 = time.perf_counter()
+    for _ in range(30):
+        tick_fs()
+    ms_tick_fs = (time.perf_counter() - t0) / 30 * 1e3
+    return {'envs': n_envs, 'frame_stack_on_device': {'stack_kernel_ms': ms_stack, 'pcie_bytes_per_env_step': 7056, 'tick_wall_ms': ms_tick_fs,
+                                                      'env_steps_per_s_ceiling': n_envs / (ms_tick_fs * 1e-3)},
+            'frames_h2d_ms': ms_up, 'frames_h2d_GBps': n_envs * 28224 / (ms_up * 1e-3) / 1e9,
             'policy_forward_and_draw_ms': ms_act, 'forward_samples_per_s': n_envs / (ms_act * 1e-3),
             'tick_wall_ms': ms_tick, 'env_steps_per_s_ceiling': n_envs / (ms_tick * 1e-3),
             'what': 'per time step of all envs: pinned frames -> their ring slot (one strided H2D copy), drl_net_act on those rows (bf16 engine, '

@@ -344,6 +344,13 @@ int drl_net_act(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int 
 int drl_rollout_record(uint8_t* obs_store, int64_t* act_store, float* done_store, float* const* reward_stores, int n_streams,
                        int n_envs, int64_t pitch_steps, int t, const uint8_t* obs_t, const int64_t* a_t, const float* d_t,
                        const float* const* r_t, int obs_on_host, void* stream);
+/* FrameStackWrapper (drl/envs/wrappers/stateless/frame_stack.py:50-59, num_stack = 4) on the device: slot t_dst of every
+ * environment = slot t_src shifted by one channel + the newest single frame (newest [n_envs, 84, 84] uint8, device or pinned
+ * host memory) as channel 3; reset_mask[e] (nullable): 1 = four copies of the newest frame (the environment was reset),
+ * 2 = leave environment e untouched, 0 = shift + append.  t_src == t_dst is allowed (in place).
+ * The environments hand over 7 KB per step instead of the 28 KB stack. */
+int drl_rollout_stack_frames(uint8_t* obs_store, int n_envs, int64_t pitch_steps, int t_src, int t_dst, const uint8_t* newest,
+                             const uint8_t* reset_mask, void* stream);
 /* The extra_steps carry-over of Rollout.report (rollout.py:213-223): `count` time steps [src_t0, src_t0+count) of every
  * environment of one [n_envs, pitch, step_bytes] array to steps [dst_t0, ...) of another (step_bytes a multiple of 4). */
 int drl_rollout_copy_steps(void* dst, const void* src, int n_envs, int64_t dst_pitch_steps, int64_t src_pitch_steps,

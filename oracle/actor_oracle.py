@@ -136,3 +136,35 @@ def rollouts_oracle(params: Dict[str, np.ndarray], e: int, T: int, extra_steps: 
         if extra_steps:
             obs[:extra_steps], act[:extra_steps], rew[:extra_steps], raw[:extra_steps], dones[:extra_steps] = keep
     return out
+
+
+class SingleFrameEnv(SynthActorEnv):
+    """SynthActorEnv handing out SINGLE frames [84, 84, 1] (an environment chain without its FrameStackWrapper)."""
+
+    def _frame(self):
+        f = self._rs.randint(0, 256, size=(84, 84, 1)).astype(np.uint8)
+        self.frames.append(f)
+        return (f.astype(F32) / F32(255.0)) if self._as_float else f
+
+
+class HostFrameStack:
+    """FrameStackWrapper with num_stack frames (drl/envs/wrappers/stateless/frame_stack.py:50-59), restated: reset fills the
+    window with copies of the first frame, step appends the newest one; the observation is their concatenation on the last
+    axis, oldest first."""
+
+    def __init__(self, env, num_stack: int = 4):
+        self.env, self._n, self._frames = env, num_stack, []
+
+    @property
+    def reward_spec(self):
+        return self.env.reward_spec
+
+    def reset(self):
+        o = self.env.reset()
+        self._frames = [o] * self._n
+        return np.concatenate(self._frames, axis=-1)
+
+    def step(self, a):
+        o, r, d, info = self.env.step(a)
+        self._frames = self._frames[1:] + [o]
+        return np.concatenate(self._frames, axis=-1), r, d, info

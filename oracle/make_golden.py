@@ -462,6 +462,17 @@ def gen_actor_rollout():
             out[f'r{k}_e{e}_obs_sum'] = ao.frame_checksums(obs)
             for key, vals in res['metadata'].items():
                 out[f'r{k}_e{e}_md_{key}'] = np.asarray(vals, np.float64)
+    # FrameStackWrapper (frame_stack.py:14-59) over a single-frame environment: a reset, five steps, a reset, three steps
+    from drl.envs.wrappers.stateless.frame_stack import FrameStackWrapper
+
+    class OneFrame(ao.SingleFrameEnv, gym.core.Env):
+        def __init__(self):
+            ao.SingleFrameEnv.__init__(self, 9, A, as_float=False)
+            self.observation_space = gym.spaces.Box(0, 255, (84, 84, 1), np.uint8)
+            self.action_space = gym.spaces.Discrete(A)
+    fs = FrameStackWrapper(OneFrame(), num_stack=4)
+    stacks = [fs.reset()] + [fs.step(k % A)[0] for k in range(5)] + [fs.reset()] + [fs.step(k % A)[0] for k in range(3)]
+    out['framestack_sums'] = ao.frame_checksums(np.stack(stacks).astype(np.uint8))
     np.savez_compressed(os.path.join(GOLD, 'actor_rollout.npz'), **out)
 
 

@@ -96,6 +96,7 @@ PROTOTYPES = {
                             c_void_p, c_void_p]),
     'drl_rollout_record': (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int64, c_int, c_void_p,
                                    c_void_p, c_void_p, POINTER(c_void_p), c_int, c_void_p]),
+    'drl_rollout_stack_frames': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'drl_rollout_copy_steps': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     'drl_nstep_advantages_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_int64,
                                          c_float, c_int, c_void_p, c_void_p]),

@@ -23,6 +23,7 @@ from ..ops import current_stream, ptr
 from .ppo import RolloutStorage
 
 OBS_SHAPE = (84, 84, 4)
+INTRINSIC_KEY = 'intrinsic_rnd'       # random_network_distillation.py:131
 
 
 class MetadataManager:
@@ -90,6 +91,8 @@ class DeviceRollout:
         self._h_done = tc.empty(n_envs, dtype=tc.float32).pin_memory()
         self._h_rew = {k: tc.empty(n_envs, dtype=tc.float32).pin_memory() for k in self.reward_keys}
         self._h_obs_np = self._h_obs.numpy()
+        self._h_new = tc.empty((n_envs, 84, 84), dtype=tc.uint8).pin_memory()        # single newest frames (stack_frames)
+        self._h_mask = tc.empty(n_envs, dtype=tc.uint8).pin_memory()
         self._staged = tc.cuda.Event()
         self._staged.record()
 
@@ -167,6 +170,29 @@ class DeviceRollout:
     def write_outcome(self, t: int, rewards: Mapping[str, Any], dones) -> None:
         self._record(t, rewards=rewards, dones=dones)
 
+    def staging_newest(self):
+        """Pinned ([n_envs, 84, 84] uint8 newest frames, [n_envs] uint8 modes) for `stack_frames`, free to be overwritten."""
+        self._staged.synchronize()
+        return self._h_new.numpy(), self._h_mask.numpy()
+
+    def stack_frames(self, t_src: int, t_dst: int, newest=None, modes=None) -> None:
+        """FrameStackWrapper (frame_stack.py:50-59, num_stack = 4) on the device: slot `t_dst` = slot `t_src` shifted by one
+        channel + `newest` [n_envs, 84, 84] as the last channel; `modes` [n_envs]: 1 = the environment was reset (four copies of
+        its newest frame), 2 = leave it untouched.  None = the pinned buffers of `staging_newest()` were filled in place."""
+        new_np, mask_np = self.staging_newest()
+        if newest is not None and newest is not new_np:
+            if isinstance(newest, tc.Tensor) and newest.is_cuda:
+                raise ValueError('stack_frames takes host frames (the environments render on the host)')
+            new_np[...] = _frames_u8(newest).reshape(self.n_envs, 84, 84)
+        if modes is not None and modes is not mask_np:
+            mask_np[...] = np.asarray(modes, dtype=np.uint8).reshape(self.n_envs)
+        elif modes is None and newest is not None:
+            mask_np[...] = 0
+        d = self.storage.data
+        check(self._L.drl_rollout_stack_frames(ptr(d['observations']), self.n_envs, self.Tp, int(t_src), int(t_dst), ptr(self._h_new),
+                                               ptr(self._h_mask), current_stream()), 'rollout_stack_frames')
+        self._staged.record()
+
     def report(self) -> Dict[str, Any]:
         """rollout.py:197-224: returns the filled store (a `RolloutStorage` dict: uint8 frames and per-step scalars laid out
         [n_envs, Tp, ...]) and continues in the other store of the ring, whose first `extra_steps` steps receive the last
@@ -196,14 +222,17 @@ class BatchedRolloutManager:
     rollout_net  a fused `agents.Agent` (or its `DDPShim`)
     noise        optional callable (step_number) -> float32 [n_envs, A] tensor of Exp(1) variates for the draw (the variates
                  `torch.multinomial` would have drawn); default: generated in the kernel from (`seed`, step number)
-    intrinsic    optional `envs.RandomNetworkDistillation`: adds reward key 'intrinsic' from the new frames, batched
+    intrinsic    optional `envs.RandomNetworkDistillation`: adds reward key 'intrinsic_rnd' (:131) from the new frames, batched
                  (random_network_distillation.py:186-201)
     reward_normalizers  optional {reward key: envs.BatchedRewardNormalizer} applied after that (normalize_reward.py:171-194)
+    frame_stack  True: the environments return SINGLE frames ([84,84] or [84,84,1]; no FrameStackWrapper in their chain) and
+                 the 4-frame stacks are built on the device (frame_stack.py:50-59): 7 KB per environment step cross PCIe
+                 instead of 28 KB
     """
 
     def __init__(self, envs: Sequence[Any], rollout_net, rollout_len: int, extra_steps: int,
                  reward_keys: Optional[Sequence[str]] = None, noise: Optional[Callable[[int], tc.Tensor]] = None, seed: int = 0,
-                 intrinsic=None, reward_normalizers: Optional[Mapping[str, Any]] = None, device=None):
+                 intrinsic=None, reward_normalizers: Optional[Mapping[str, Any]] = None, device=None, frame_stack: bool = False):
         assert rollout_len > 0
         assert extra_steps >= 0
         self._envs = list(envs)
@@ -212,6 +241,7 @@ class BatchedRolloutManager:
         self._rollout_len, self._extra_steps = rollout_len, extra_steps
         self._noise, self._seed, self._step_no = noise, int(seed), 0
         self._intrinsic, self._reward_normalizers = intrinsic, dict(reward_normalizers or {})
+        self._frame_stack = bool(frame_stack)
         self._L = _lib.lib()
         n = len(self._envs)
         if n > self._engine.max_batch:
@@ -224,7 +254,11 @@ class BatchedRolloutManager:
         self._metadata = [MetadataManager({'ep_len': 0, 'ep_ret': 0., 'ep_len_raw': 0, 'ep_ret_raw': 0.}) for _ in range(n)]
         # o_0 into slot 0 and a_0 for it (rollout.py:253-254)
         self._t = 0
-        self._rollout.write_frames(0, np.stack([_frames_u8(e.reset()) for e in self._envs]))
+        first = np.stack([_frames_u8(e.reset()) for e in self._envs])
+        if self._frame_stack:
+            self._rollout.stack_frames(0, 0, first, np.ones(n, np.uint8))
+        else:
+            self._rollout.write_frames(0, first)
         self._a_t = self._choose_actions(0)
         self.generate(initial=True)
 
@@ -233,8 +267,8 @@ class BatchedRolloutManager:
         if spec is None:                                                     # rollout.py:271-276
             raise ValueError('Reward spec cannot be None.\nWrap environment with RewardToDict wrapper to fix.')
         keys = list(spec.keys)
-        if self._intrinsic is not None and 'intrinsic' not in keys:
-            keys.append('intrinsic')
+        if self._intrinsic is not None and INTRINSIC_KEY not in keys:
+            keys.append(INTRINSIC_KEY)
         return keys
 
     @property
@@ -272,9 +306,15 @@ class BatchedRolloutManager:
             start_t, end_t = self._extra_steps, self._rollout_len + self._extra_steps
         r, n = self._rollout, len(self._envs)
         for t in range(start_t, end_t):
-            frames = r.staging_frames()                         # pinned: each frame is copied once on the host, once to the device
+            # pinned staging: each frame is copied once on the host, once to the device
+            if self._frame_stack:
+                frames, modes = r.staging_newest()
+                modes[...] = 0
+            else:
+                frames, modes = r.staging_frames(), None
             rewards = {k: np.zeros(n, dtype=np.float32) for k in self._stored_keys}
             dones = np.zeros(n, dtype=np.float32)
+            resets: List[Any] = []
             for e, env in enumerate(self._envs):
                 o_tp1, r_t, done_t, info_t = env.step(self._a_t[e])
                 md = self._metadata[e]
@@ -284,19 +324,36 @@ class BatchedRolloutManager:
                     was_real_done = info_t['ale.lives'] == 0 if 'ale.lives' in info_t else True   # rollout.py:330-336
                     if was_real_done:
                         md.present_done('ep_len_raw', 'ep_ret_raw')
-                    o_tp1 = env.reset()
-                frames[e] = _frames_u8(o_tp1)
+                    if self._intrinsic is not None:           # the intrinsic reward is taken on the frame step() returned
+                        resets.append((e, _frames_u8(env.reset())))
+                    else:
+                        o_tp1 = env.reset()
+                        if modes is not None:
+                            modes[e] = 1
+                frames[e] = _frames_u8(o_tp1).reshape(frames.shape[1:])
                 dones[e] = float(done_t)
                 for k in self._stored_keys:
                     if k in r_t:
                         rewards[k][e] = float(r_t[k])
-            r.write_frames(t + 1, frames)                       # o_{t+1}: uploaded once, straight into its slot
+            if self._frame_stack:
+                r.stack_frames(t, t + 1)                        # o_{t+1} = shift(o_t) + newest frame, built in its slot
+            else:
+                r.write_frames(t + 1, frames)                   # o_{t+1}: uploaded once, straight into its slot
             step_rewards: Dict[str, Any] = dict(rewards)
             if self._intrinsic is not None:                     # on the NEW frames, like the wrapper's step()
                 obs = r.storage.data['observations']
                 rows = r.rows_at(t + 1)
-                step_rewards['intrinsic'] = self._intrinsic.intrinsic_reward(obs, rows)
-                self._intrinsic.observe(obs.view(-1, 84, 84, 4)[rows][..., -1:].float())
+                step_rewards[INTRINSIC_KEY] = self._intrinsic.intrinsic_reward(obs, rows)
+                self._intrinsic.observe(obs.view(-1, 84, 84, 4)[rows][..., -1:].float() * float(np.float32(1.0 / 255.0)))  # :191-192
+                if resets and self._frame_stack:                # then the finished environments continue from their reset frame
+                    frames, modes = r.staging_newest()
+                    modes[...] = 2
+                    for e, f in resets:
+                        frames[e], modes[e] = f.reshape(84, 84), 1
+                    r.stack_frames(t + 1, t + 1)
+                elif resets:
+                    idx = tc.as_tensor([e for e, _ in resets], device=r.device, dtype=tc.int64)
+                    obs.view(-1, 84, 84, 4)[rows[idx]] = tc.from_numpy(np.stack([f for _, f in resets])).to(r.device)
             for k, nz in self._reward_normalizers.items():
                 raw = tc.as_tensor(step_rewards[k], device=r.device, dtype=tc.float32).reshape(n, 1)
                 step_rewards[k] = nz.step_block(raw, tc.as_tensor(dones, device=r.device).reshape(n, 1)).reshape(n).contiguous()

@@ -96,6 +96,42 @@ __global__ void __launch_bounds__(256) record_frames_kernel(uint8_t* __restrict_
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) d[i] = s[i];
 }
 
+// FrameStackWrapper (drl/envs/wrappers/stateless/frame_stack.py:50-59, num_stack = 4) on the device: the stack of slot t_dst is
+// the stack of slot t_src shifted by one channel with the newest frame appended (channel 3 = newest, what np.concatenate of
+// the deque gives), or four copies of the newest frame where the environment was reset.  One 32-bit word per pixel:
+// out = (prev >> 8) | (newest << 24).  The environments then hand over 7 KB per step instead of 28 KB.
+__global__ void __launch_bounds__(256) stack_frames_kernel(uint8_t* __restrict__ store, const uint8_t* __restrict__ newest,
+                                                           const uint8_t* __restrict__ reset, int n_envs, int64_t pitch_steps, int t_src,
+                                                           int t_dst, int slices) {
+  constexpr int kPix4 = 84 * 84 / 4;                   // 4 pixels per thread step: one uint32 of new pixels, one uint4 of stacks
+  const int e = blockIdx.x / slices, sl = blockIdx.x % slices;
+  if (e >= n_envs) return;
+  const uint32_t* nw = reinterpret_cast<const uint32_t*>(newest + (size_t)e * 84 * 84);
+  const uint4* src = reinterpret_cast<const uint4*>(store + ((size_t)e * pitch_steps + t_src) * kObsBytes);
+  uint4* dst = reinterpret_cast<uint4*>(store + ((size_t)e * pitch_steps + t_dst) * kObsBytes);
+  const int mode = reset != nullptr ? reset[e] : 0;  // 0 shift + append, 1 reset (four copies), 2 leave this environment alone
+  if (mode == 2) return;
+  const bool fresh = mode == 1;
+  const int per = (kPix4 + slices - 1) / slices, lo = sl * per, hi = min(kPix4, lo + per);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint32_t n4 = nw[i];
+    uint4 o;
+    if (fresh) {
+      o.x = (n4 & 0xffu) * 0x01010101u;
+      o.y = ((n4 >> 8) & 0xffu) * 0x01010101u;
+      o.z = ((n4 >> 16) & 0xffu) * 0x01010101u;
+      o.w = (n4 >> 24) * 0x01010101u;
+    } else {
+      const uint4 p = src[i];
+      o.x = (p.x >> 8) | (n4 << 24);
+      o.y = (p.y >> 8) | ((n4 >> 8) << 24);
+      o.z = (p.z >> 8) | ((n4 >> 16) << 24);
+      o.w = (p.w >> 8) | ((n4 >> 24) << 24);
+    }
+    dst[i] = o;
+  }
+}
+
 struct RecordScalars {
   int64_t* act_store; float* done_store; float* rew_store[DRL_MAX_REWARD_STREAMS];
   const int64_t* a_t; const float* d_t; const float* r_t[DRL_MAX_REWARD_STREAMS];
@@ -201,6 +237,18 @@ extern "C" int drl_rollout_copy_steps(void* dst, const void* src, int n_envs, in
   if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
   copy_steps_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src), n_envs,
                                                            dst_pitch_steps, src_pitch_steps, step_bytes / 4, dst_t0, src_t0, count);
+  DRL_LAUNCH_CHECK();
+  return DRL_OK;
+}
+
+extern "C" int drl_rollout_stack_frames(uint8_t* obs_store, int n_envs, int64_t pitch_steps, int t_src, int t_dst,
+                                        const uint8_t* newest, const uint8_t* reset_mask, void* stream) {
+  if (!obs_store || !newest) return DRL_ERR_BAD_ARG;
+  if (n_envs < 1 || pitch_steps < 1 || t_src < 0 || t_dst < 0 || t_src >= pitch_steps || t_dst >= pitch_steps) return DRL_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(obs_store) & 15) || (reinterpret_cast<uintptr_t>(newest) & 3)) return DRL_ERR_MISALIGNED;
+  int slices = 1;
+  while (n_envs * slices < 2 * sm_count() && slices < 8) slices *= 2;
+  stack_frames_kernel<<<n_envs * slices, 256, 0, as_stream(stream)>>>(obs_store, newest, reset_mask, n_envs, pitch_steps, t_src, t_dst, slices);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
 }

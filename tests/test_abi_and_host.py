@@ -346,3 +346,13 @@ def test_register_resolves_fused_classes_through_the_reference_lookups():
                                      head_architecture_cls_args={}, w_init=None, b_init=None)
     ag = agents.Agent([launch.get_preprocessing('FusedToChannelMajor', {})], arch, {'policy': pol, 'value_extrinsic': val})
     assert list(ag.state_dict().keys()) == param_names(['value_extrinsic'])
+
+
+def test_in_tree_library_was_built_from_the_current_sources():
+    """The in-tree .so travels to the GPU box as is: a stale one would silently test old kernels there."""
+    import json
+    from pytorch_drl_b200 import build as b
+    stamp = os.path.join(b.OBJ, 'stamp.json')
+    if not (os.path.exists(b.LIB) and os.path.exists(stamp)):
+        pytest.skip('library not built in this tree yet')
+    assert json.load(open(stamp)).get('digest') == b._digest(), 'run `python -m pytorch_drl_b200.build`: csrc/ or include/ changed since the build'

@@ -1349,3 +1349,121 @@ def test_training_loop_collects_through_the_batched_manager(precision, tmp_path)
     moved = max(float((agent.state_dict()[k].cpu() - before[k].cpu()).abs().max()) for k in before)
     assert moved > 1e-5
     assert any(f.endswith('.pth') for f in os.listdir(tmp_path))
+
+
+def test_batched_rollout_manager_intrinsic_and_normalised_rewards():
+    """The RND reward and the reward normaliser inside the batched manager (random_network_distillation.py:186-201,
+    normalize_reward.py:171-194) equal the already-pinned batched pieces applied to the recorded rollout afterwards:
+    reward of the NEW frame of each step, raw value fed to the running return statistics, normalised value recorded."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200 import algos
+    from pytorch_drl_b200.envs import BatchedRewardNormalizer, RandomNetworkDistillation
+    E, T, A = 4, 6, 6
+    agent = _fused_agent('fp32', A, 32, 9)
+
+    def make_rnd():
+        rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=1, max_batch=64, precision='fp32', seed=3)
+        rnd.observe(tc.rand((16, 84, 84, 1), device=dev(), generator=tc.Generator(device=dev()).manual_seed(1)))
+        rnd._sync_normalizers_global(); rnd._sync_normalizers_local()
+        return rnd
+
+    def make_nz():
+        nz = BatchedRewardNormalizer(E, 0.5, False)          # trace length 10: the 40 warm-up steps fill the return statistics
+        nz.step_block(cu(np.random.RandomState(2).uniform(size=(E, 40)).astype(F32)), cu(np.zeros((E, 40), F32)))
+        nz.learn()
+        return nz
+    rnd, nz = make_rnd(), make_nz()
+    mgr = algos.BatchedRolloutManager([ao.SynthActorEnv(e, A, as_float=False) for e in range(E)], agent, T, 0, seed=5, intrinsic=rnd,
+                                      reward_normalizers={'intrinsic_rnd': nz})
+    res = mgr.generate()
+    assert sorted(res['rewards'].keys()) == ['extrinsic', 'intrinsic_rnd']
+    steps_before = float(rnd._unsynced_normalizer.steps)
+    rnd2, nz2 = make_rnd(), make_nz()
+    rows_next = (tc.arange(E, device=dev())[:, None] * mgr.rollout.Tp + tc.arange(1, T + 1, device=dev())[None, :]).reshape(-1)
+    # where an episode ended the store holds the reset frame: the reward was taken on the terminal frame step() returned
+    envs2 = [ao.SynthActorEnv(e, A, as_float=False) for e in range(E)]
+    acts, dn = res['actions'].cpu().numpy(), res['dones'].cpu().numpy()
+    stepped = np.zeros((E, T, 84, 84, 4), np.uint8)
+    for e, env in enumerate(envs2):
+        env.reset()
+        for t in range(T):
+            stepped[e, t] = env.step(acts[e, t])[0]
+            if dn[e, t]:
+                env.reset()
+    assert dn[:, :T].sum() > 0
+    raw = rnd2.intrinsic_reward(cu(stepped.reshape(E * T, 84, 84, 4))).view(E, T)
+    np.testing.assert_array_equal(res['observations'].view(-1, 84, 84, 4)[rows_next].cpu().numpy()[dn[:, :T].reshape(-1) == 0],
+                                  stepped.reshape(E * T, 84, 84, 4)[dn[:, :T].reshape(-1) == 0])
+    want = nz2.step_block(raw, res['dones'][:, :T].contiguous())
+    got = res['rewards']['intrinsic_rnd'][:, :T]
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    assert float(got.abs().max()) > 0
+    np.testing.assert_allclose(nz.moment1.cpu().numpy(), nz2.moment1.cpu().numpy(), rtol=1e-6)
+    assert steps_before == float(rnd2._unsynced_normalizer.steps) + E * T      # every new frame was observed once
+
+
+def test_device_frame_stack_equals_reference_frame_stack_wrapper(golden_dir):
+    """drl_rollout_stack_frames == FrameStackWrapper (frame_stack.py:50-59): byte work, bit-exact vs the golden written by the
+    reference's wrapper (environment 0) and vs the oracle's restatement (all environments, in-place and slot-to-slot)."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200.algos import DeviceRollout
+    g = np.load(os.path.join(golden_dir, 'actor_rollout.npz'))
+    N, A = 3, 6
+    r = DeviceRollout(N, 12, 0, ['extrinsic'])
+    hosts = [ao.HostFrameStack(ao.SingleFrameEnv(9 + e, A, False)) for e in range(N)]
+    singles = [ao.SingleFrameEnv(9 + e, A, False) for e in range(N)]
+    want, t = [], 0
+    want.append(np.stack([h.reset() for h in hosts]))
+    r.stack_frames(0, 0, np.stack([s.reset() for s in singles]), np.ones(N, np.uint8))
+    for k in list(range(5)) + ['reset'] + list(range(3)):
+        if k == 'reset':
+            want.append(np.stack([h.reset() for h in hosts]))
+            r.stack_frames(t, t + 1, np.stack([s.reset() for s in singles]), np.ones(N, np.uint8))
+        else:
+            want.append(np.stack([h.step(k % A)[0] for h in hosts]))
+            r.stack_frames(t, t + 1, np.stack([s.step(k % A)[0] for s in singles]))
+        t += 1
+    got = r.storage.data['observations'][:, :t + 1].cpu().numpy()
+    np.testing.assert_array_equal(got, np.stack(want, axis=1))
+    np.testing.assert_array_equal(ao.frame_checksums(got[0]), g['framestack_sums'])
+    # mode 2 leaves an environment untouched; a float frame in [0, 1] is taken as rint(255 x)
+    before = r.storage.data['observations'][:, t].cpu().numpy().copy()
+    newest = np.stack([s.step(0)[0] for s in singles])
+    r.stack_frames(t, t, newest.astype(np.float32) / np.float32(255.0), np.array([2, 0, 2], np.uint8))
+    after = r.storage.data['observations'][:, t].cpu().numpy()
+    np.testing.assert_array_equal(after[[0, 2]], before[[0, 2]])
+    np.testing.assert_array_equal(after[1], np.concatenate([before[1][..., 1:], newest[1]], axis=-1))
+
+
+@pytest.mark.parametrize('with_intrinsic', [False, True])
+def test_batched_rollout_manager_device_frame_stack_equals_host_frame_stack(with_intrinsic):
+    """frame_stack=True (single frames over PCIe, stacks built on the device) gives the rollout of the same environments
+    behind a host-side FrameStackWrapper, bit for bit: frames, draws, rewards (incl. the RND reward on terminal frames), dones."""
+    from oracle import actor_oracle as ao
+    from pytorch_drl_b200 import algos
+    from pytorch_drl_b200.envs import RandomNetworkDistillation
+    E, T, extra, A = 5, 6, 1, 6
+    agent = _fused_agent('fp32', A, 64, 2)
+    out = []
+    for device_stack in (False, True):
+        rnd = None
+        if with_intrinsic:
+            rnd = RandomNetworkDistillation({'lr': 1e-4, 'eps': 1e-5}, world_size=1, max_batch=64, precision='fp32', seed=3)
+            rnd.observe(tc.rand((16, 84, 84, 1), device=dev(), generator=tc.Generator(device=dev()).manual_seed(1)))
+            rnd._sync_normalizers_global(); rnd._sync_normalizers_local()
+        envs = [ao.SingleFrameEnv(20 + e, A, as_float=False) for e in range(E)]
+        if not device_stack:
+            envs = [ao.HostFrameStack(e) for e in envs]
+        mgr = algos.BatchedRolloutManager(envs, agent, T, extra, seed=9, intrinsic=rnd, frame_stack=device_stack)
+        res = [mgr.generate() for _ in range(2)]
+        out.append([{k: (v.clone() if isinstance(v, tc.Tensor) else {kk: vv.clone() for kk, vv in v.items()} if k == 'rewards' else v)
+                     for k, v in ro.items() if k in ('observations', 'actions', 'rewards', 'dones', 'metadata')} for ro in res])
+    steps = T + extra
+    for a, b in zip(*out):
+        assert a['dones'][:, :steps].sum() > 0
+        np.testing.assert_array_equal(a['observations'][:, :steps + 1].cpu().numpy(), b['observations'][:, :steps + 1].cpu().numpy())
+        np.testing.assert_array_equal(a['actions'][:, :steps + 1].cpu().numpy(), b['actions'][:, :steps + 1].cpu().numpy())
+        np.testing.assert_array_equal(a['dones'][:, :steps].cpu().numpy(), b['dones'][:, :steps].cpu().numpy())
+        for k in a['rewards']:
+            np.testing.assert_array_equal(a['rewards'][k][:, :steps].cpu().numpy(), b['rewards'][k][:, :steps].cpu().numpy())
+        assert a['metadata'] == b['metadata']

@@ -283,3 +283,7 @@ def test_actor_rollout_oracle_vs_reference_rollout_manager_golden(golden_dir):
             np.testing.assert_array_equal(ao.frame_checksums(ro['observations']), g[f'r{k}_e{e}_obs_sum'])
             for key in ('ep_len', 'ep_ret', 'ep_len_raw', 'ep_ret_raw'):
                 np.testing.assert_allclose(np.asarray(ro['metadata'][key], np.float64), g[f'r{k}_e{e}_md_{key}'], rtol=1e-12, atol=1e-9)
+    # the FrameStackWrapper restatement against the reference's wrapper (reset, 5 steps, reset, 3 steps)
+    fs = ao.HostFrameStack(ao.SingleFrameEnv(9, A, False))
+    stacks = [fs.reset()] + [fs.step(k % A)[0] for k in range(5)] + [fs.reset()] + [fs.step(k % A)[0] for k in range(3)]
+    np.testing.assert_array_equal(ao.frame_checksums(np.stack(stacks)), g['framestack_sums'])
