@@ -93,6 +93,7 @@ class DeviceRollout:
         self._h_obs_np = self._h_obs.numpy()
         self._h_new = tc.empty((n_envs, 84, 84), dtype=tc.uint8).pin_memory()        # single newest frames (stack_frames)
         self._h_mask = tc.empty(n_envs, dtype=tc.uint8).pin_memory()
+        self._d_new = tc.empty((n_envs, 84, 84), dtype=tc.uint8, device=self.device)  # the copy engine moves them at full PCIe rate
         self._staged = tc.cuda.Event()
         self._staged.record()
 
@@ -189,7 +190,8 @@ class DeviceRollout:
         elif modes is None and newest is not None:
             mask_np[...] = 0
         d = self.storage.data
-        check(self._L.drl_rollout_stack_frames(ptr(d['observations']), self.n_envs, self.Tp, int(t_src), int(t_dst), ptr(self._h_new),
+        self._d_new.copy_(self._h_new, non_blocking=True)
+        check(self._L.drl_rollout_stack_frames(ptr(d['observations']), self.n_envs, self.Tp, int(t_src), int(t_dst), ptr(self._d_new),
                                                ptr(self._h_mask), current_stream()), 'rollout_stack_frames')
         self._staged.record()
 
