@@ -128,6 +128,29 @@ __device__ __forceinline__ void mma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uin
   }
 }
 
+// Integer form: u8 / s8 operands (formats in the instruction descriptor), s32 accumulators, K = 32 bytes per instruction.
+template <bool ACC>
+__device__ __forceinline__ void mma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc) {
+  if (ACC) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+        : "memory");
+  }
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (K-major only) is read from tensor memory — lane = tile row,
 // one 32-bit column = two consecutive 16-bit K elements, 8 columns per K=16 instruction.
 template <bool ACC>
@@ -190,6 +213,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -203,216 +203,4 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// conv1 FORWARD on the same block image.  The converters write 1024-biased fp16 (one PRMT per pixel pair, the
-// constant is folded into the effective bias), the image is the K-major A operand: GEMM row r = oy*21 + ox,
-// tap (ty, tx) reads image rows r + ty*21 + tx through a shifted descriptor; 4 taps x 64 = K 256.  Four 128-row
-// tiles cover r < 512 (420 are outputs; x = 20 and r >= 420 are discarded).  Weights: [4 taps][32 co x 64] fp16
-// tile images in the block element order e = dy*16 + px*4 + ci (PK_CONV1_S2D).
-// Per sample: every pixel is converted once (441 x 32 PRMT instead of 3.1 tiles x 512 x 32 for the im2col /
-// tensor-memory kernel).  The two taps of the block row itself, (0,0) and (0,1), take their A operand from TENSOR
-// MEMORY (written by the converters from the registers they already hold, a 6-slot ring of tiles); only the two
-// taps of the next block row are fetched from the shared-memory image.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kS2dFImgRows = 4 * 128 + 22;                                   // last tile + largest tap shift
-constexpr int kS2dFImgBytes = (kS2dFImgRows * 128 + 1023) / 1024 * 1024;     // 68 608 B = 67 KB
-constexpr int kS2dFNAcc = 4;                                                 // accumulators: TMEM columns [0, 128)
-constexpr int kS2dFNSlot = 6;                                                // A-operand tile slots of 64 columns: [128, 512)
-constexpr int kS2dFEpiWG = 2;
-constexpr int kS2dFThreads = 32 * (4 * kS2dFEpiWG + 1 + 8 + 1);
-constexpr int kS2dFwdSmem = 16384 + 2 * kS2dFImgBytes + 2 * kS2dRawBytes + 256 + 1024;
-
-__global__ void __launch_bounds__(kS2dFThreads, 1) conv1_fwd_s2d_kernel(const Conv1Args args) {
-  using namespace umma;
-  constexpr int NCONV = 256;
-  constexpr int W_MMA = 4 * kS2dFEpiWG, W_CONV = W_MMA + 1, W_TMA = W_CONV + 8;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;
-  uint8_t* sImg = smem + 16384;
-  uint8_t* sRaw = sImg + 2 * kS2dFImgBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + 2 * kS2dRawBytes);
-  uint64_t* raw_full = bars;          // [2]
-  uint64_t* raw_empty = bars + 2;     // [2]
-  uint64_t* img_full = bars + 4;      // [2]
-  uint64_t* img_empty = bars + 6;     // [2]
-  uint64_t* tfull = bars + 8;         // [4]
-  uint64_t* tempty = bars + 12;       // [4]
-  uint64_t* a_empty = bars + 16;      // [6] tensor-memory A slot consumed by its tile's MMAs
-  uint64_t* b_full = bars + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, NCONV);
-      mbar_init(img_full + s, NCONV); mbar_init(img_empty + s, 1);
-    }
-    for (int a = 0; a < kS2dFNAcc; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
-    for (int a = 0; a < kS2dFNSlot; ++a) mbar_init(a_empty + a, 1);
-    mbar_init(b_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);     // [0,128) 4 accumulators, [128,512) six A tile slots (taps (0,0) and (0,1))
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int n_mine = (int)blockIdx.x < args.nb ? (args.nb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-  if (warp == W_TMA) {
-    if (lane == 0 && n_mine > 0) {
-      mbar_arrive_expect_tx(b_full, 16384);
-      tma_bulk_g2s(sB, args.bpack, 16384, b_full);
-      for (int j = 0; j < n_mine; ++j) {
-        const int b = blockIdx.x + j * gridDim.x;
-        const uint32_t s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(raw_empty + s, ph ^ 1);
-        const int64_t srow = args.row_idx ? args.row_idx[b] : (int64_t)b;
-        mbar_arrive_expect_tx(raw_full + s, kC1FrameBytes);
-        tma_bulk_g2s(sRaw + s * kS2dRawBytes, args.obs + srow * kC1FrameBytes, kC1FrameBytes, raw_full + s);
-      }
-    }
-    __syncwarp();
-  } else if (warp >= W_CONV) {
-    // ================= converters: raw uint8 frame -> 1024-biased fp16 block image ======================
-    // Thread (quarter = warp & 3, lane) converts blocks q = tile*128 + quarter*32 + lane for two tiles.  For tap
-    // (0,0) the A row of GEMM row r IS image row r, and tile row q % 128 lives in this thread's own TMEM lane: the
-    // 32 registers it just produced also go to tensor memory (tcgen05.st).  Tap (0,1) needs image row r + 1: the
-    // thread converts that block too.  Both taps are then issued in TS form, so half of the A operand never
-    // crosses the shared-memory port.
-    const int quarter = warp & 3, half = (warp - W_CONV) >> 2;
-    const uint32_t t_lane = (uint32_t)(quarter * 32) << 16;
-    auto convert_block = [&](uint32_t raw, int q, uint32_t (&r)[32]) {
-      const int by = (q * 3121) >> 16;                   // q / 21
-      const int bx = q - by * 21;
-      const uint32_t src = raw + (uint32_t)(by * 4 * kC1RowBytes + bx * 16);
-      uint4 v[4];
-#pragma unroll
-      for (int dy = 0; dy < 4; ++dy) v[dy] = lds_v4(src + (uint32_t)(dy * kC1RowBytes));
-#pragma unroll
-      for (int dy = 0; dy < 4; ++dy) {
-        const uint4 a = u8x8_to_f16x8_biased(make_uint2(v[dy].x, v[dy].y)), b = u8x8_to_f16x8_biased(make_uint2(v[dy].z, v[dy].w));
-        r[8 * dy] = a.x; r[8 * dy + 1] = a.y; r[8 * dy + 2] = a.z; r[8 * dy + 3] = a.w;
-        r[8 * dy + 4] = b.x; r[8 * dy + 5] = b.y; r[8 * dy + 6] = b.z; r[8 * dy + 7] = b.w;
-      }
-    };
-    for (int j = 0; j < n_mine; ++j) {
-      const uint32_t s = j & 1, ph = (j >> 1) & 1;
-      mbar_wait(raw_full + s, ph);
-      mbar_wait(img_empty + s, ph ^ 1);
-      const uint32_t raw = smem_u32(sRaw + s * kS2dRawBytes), img = smem_u32(sImg + s * kS2dFImgBytes);
-#pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        const int tile = 2 * half + rep;
-        const uint32_t it = (uint32_t)(4 * j + tile), slot = it % kS2dFNSlot;
-        const int q = tile * 128 + quarter * 32 + lane;    // block index by*21 + bx
-        uint32_t r[32];
-        if (q < 441) {
-          convert_block(raw, q, r);
-          const uint32_t dst = img + (uint32_t)q * 128u;
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            st_shared_v4(dst + (((uint32_t)c ^ ((uint32_t)q & 7u)) << 4), make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
-        }
-        mbar_wait(a_empty + slot, ((it / kS2dFNSlot) & 1) ^ 1);       // the MMAs of the tile that used this slot are done
-        tc_fence_after();
-        const uint32_t t_a = tmem_base + t_lane + 128 + slot * 64;
-        tmem_st_32x32b_x32(t_a, r);                                   // tap (0,0)
-        // tap (0,1) = image row r + 1: converted again from the raw frame (4 LDS.128 + 32 PRMT) — cheaper on the
-        // L1/shared data pipe than 32 shuffles (ncu: the LSU wavefronts of a shuffle version ate the saving)
-        if (q + 1 < 441) convert_block(raw, q + 1, r);
-        else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0u;
-        }
-        tmem_st_32x32b_x32(t_a + 32, r);                              // tap (0,1)
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(img_full + s);
-      mbar_arrive(raw_empty + s);
-    }
-  } else if (warp == W_MMA) {
-    constexpr uint32_t idesc = make_idesc_f16(0u, 128, 32, 0, 0);     // fp16 operands, both K-major
-    constexpr uint32_t hi = desc_hi(1024, LAYOUT_SW128);
-    const uint32_t b_lo0 = desc_lo(smem_u32(sB), 0);
-    const uint32_t a_lo0 = desc_lo(smem_u32(sImg), 0);
-    if (n_mine > 0) mbar_wait(b_full, 0);
-    uint32_t it = 0;
-    for (int j = 0; j < n_mine; ++j) {
-      const uint32_t s = j & 1, ph = (j >> 1) & 1;
-      mbar_wait(img_full + s, ph);
-#pragma unroll 1
-      for (int tile = 0; tile < 4; ++tile, ++it) {
-        const uint32_t acc = it % kS2dFNAcc, slot = it % kS2dFNSlot;
-        mbar_wait(tempty + acc, ((it / kS2dFNAcc) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t a_tile = a_lo0 + s * (kS2dFImgBytes >> 4) + tile * ((128 * 128) >> 4);
-        const uint32_t t_d = tmem_base + acc * 32;
-        const uint32_t t_a = tmem_base + 128 + slot * 64;                // taps (0,0), (0,1): A rows straight from the converters
-        if (elect_one()) {
-#pragma unroll
-          for (int tap = 0; tap < 2; ++tap) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (tap == 0 && k == 0) mma_f16_ts<false>(t_d, t_a, b_lo0, hi, idesc);
-              else mma_f16_ts<true>(t_d, t_a + tap * 32 + k * 8, b_lo0 + tap * (4096 >> 4) + k * 2, hi, idesc);
-            }
-          }
-#pragma unroll
-          for (int tap = 2; tap < 4; ++tap) {
-            const uint32_t a_lo = a_tile + (((tap >> 1) * 21 + (tap & 1)) * 128 >> 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16_lohi<true>(t_d, a_lo + k * 2, hi, b_lo0 + tap * (4096 >> 4) + k * 2, hi, idesc);
-          }
-          mma_commit(tfull + acc);
-          mma_commit(a_empty + slot);
-          if (tile == 3) mma_commit(img_empty + s);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ================= epilogue warpgroups: tiles round-robin =========================================
-    const int wg = warp >> 2, trow = threadIdx.x & 127;
-    float bias[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) bias[i] = __ldg(args.bias + i);
-    uint32_t it = 0;
-    for (int j = 0; j < n_mine; ++j) {
-      const int b = blockIdx.x + j * gridDim.x;
-#pragma unroll 1
-      for (int tile = 0; tile < 4; ++tile, ++it) {
-        if ((int)(it % kS2dFEpiWG) != wg) continue;
-        const uint32_t acc = it % kS2dFNAcc;
-        const int r = tile * 128 + trow;
-        const int y = (r * 3121) >> 16, x = r - y * 21;
-        mbar_wait(tfull + acc, (it / kS2dFNAcc) & 1);
-        tc_fence_after();
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * 32, rr);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(tempty + acc);
-        if (y < 20 && x < 20) {
-          const int64_t m = (int64_t)b * 400 + y * 20 + x;
-          c1_store_row(rr, bias, args.scale, args.out + m * 32, args.mask_bits + m);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 }  // namespace drl

@@ -87,6 +87,22 @@ static int make_tmap_dy1(CUtensorMap* m, const void* base, uint64_t nb) {
   return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
 }
 
+// uint8 frame store [rows, 84, 84, 4] seen as 32-bit words [rows][21 row groups][4 row phases][84 words]: a (84, 1, 21, 1) box is
+// one ROW PHASE of a frame (image rows p, p + 4, ...) as 21 contiguous 336-byte rows, no swizzle (umma_conv1_i8.cuh).  The
+// store's row count is not known here (rows are addressed through row_idx): the sample dimension is given its maximum.
+static int make_tmap_frame_phases(CUtensorMap* m, const void* base) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return DRL_ERR_CUDA;
+  const cuuint64_t dims[4] = {84, 4, 21, 1ull << 24};
+  const cuuint64_t strides[3] = {336, 4 * 336, 84 * 336};
+  const cuuint32_t box[4] = {84, 1, 21, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DRL_OK : DRL_ERR_CUDA;
+}
+
 template <int N, int EPI, int NR, int NACC, int NEPI, int MROWS, int KB, int KBX, int SHIFT_RW, int PLANES>
 static int launch_tma_conv(const char* site, const void* src, int nb, int H, int W, int BW, int BH, TmaConvArgs a, cudaStream_t st,
                            int pair_bit = 0) {

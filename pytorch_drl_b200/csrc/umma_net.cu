@@ -12,6 +12,7 @@
 #include "umma_launch.cuh"
 #include "umma_conv1_s2d.cuh"
 #include "umma_heads.cuh"
+#include "umma_conv1_i8.cuh"
 
 namespace drl {
 
@@ -19,14 +20,14 @@ static const float kInv255 = [] { const uint32_t u = 0x3b808081u; float f; memcp
 
 struct Bf16Engine {
   // packed B operands (tile images)
-  void* w1s = nullptr;   // conv1 fwd   fp16 [4 taps][32x64] in space-to-depth block order (PK_CONV1_S2D)
   void* w2f = nullptr;   // conv2 fwd   bf16 [8][64x64]
   void* w3f = nullptr;   // conv3 fwd   bf16 [9][64x64]
   void* wff = nullptr;   // fc fwd      bf16 row-major [512][3136], k = (hw, c)  (TMA tensor map)
   void* wfd = nullptr;   // fc dgrad    bf16 row-major [3136][512] = the transpose      (TMA tensor map)
   void* w3d = nullptr;   // conv3 dgrad bf16 [9][64x64]   (flipped taps)
   uint32_t* bits[3] = {nullptr, nullptr, nullptr};   // ReLU masks of act1/act2/act3, 1 bit per element
-  float* b1eff = nullptr; // conv1 effective bias (last block of pack_all_kernel)
+  int8_t* w1q = nullptr;  // conv1 fwd, integer kernel: s8 [8 taps][64 rows = (hi, lo) x 32 co][32 B = (kx, ci)] core-matrix images (umma_conv1_i8.cuh)
+  float* c1scale = nullptr; // [32] per-channel step of the 16-bit fixed-point weights x float32(1/255)
   void* w2d = nullptr;   // conv2 dgrad bf16 [4][128x64]: rows = (parity class, ci)
   void* whd = nullptr;   // heads       bf16 [8][32x64]: rows = (policy actions, value streams, zero padding)  (umma_heads.cuh)
   __nv_bfloat16* featb = nullptr;   // [nb, 512] bf16 features of the learner step (the fp32 `feat` serves the other entry points)
@@ -38,7 +39,7 @@ constexpr int64_t kGtFc = 0, kGtConv3 = (int64_t)3136 * 512, kGtConv2 = kGtConv3
 
 
 // ---- packing -----------------------------------------------------------------------------------------
-enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_CONV1_S2D = 5, PK_HEADS = 6 };
+enum { PK_CONV_FWD = 0, PK_FC_FWD = 1, PK_FC_DGRAD = 2, PK_CONV3_DGRAD = 3, PK_CONV2_DGRAD = 4, PK_HEADS = 6 };
 
 struct PackArgs {
   const float* w;      // reference-layout fp32 weights of the layer
@@ -71,11 +72,6 @@ __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n,
     }
     case PK_HEADS:                 // B[n = head][k = feature]: policy rows, value rows, zero padding
       return n < a.Cin ? a.w[(size_t)n * 512 + k] : (n < a.Cin + a.KH ? a.wv[n - a.Cin][k] : 0.f);
-    case PK_CONV1_S2D: {           // B[n=co][k = tap*64 + e], tap = (ty,tx), e = dy*16 + px*4 + ci: W1[co,ci,4ty+dy,4tx+px]
-      const int tap = k >> 6, e = k & 63, ty = tap >> 1, tx = tap & 1;
-      const int dy = e >> 4, px = (e >> 2) & 3, ci = e & 3;
-      return a.w[((size_t)(n * 4 + ci) * 8 + (4 * ty + dy)) * 8 + (4 * tx + px)];
-    }
     default: {                     // PK_CONV2_DGRAD: row n = (class (py,px), ci); B[n][k=(ty,tx,co)] = W2[co,ci,py+2(1-ty),px+2(1-tx)]
       const int cls = n >> 5, ci = n & 31, py = cls >> 1, px = cls & 1;
       const int t = k / 64, co = k - t * 64, ty = t >> 1, tx = t & 1;
@@ -86,13 +82,13 @@ __device__ __forceinline__ float pack_src(const PackArgs& a, int variant, int n,
 
 // ---- all operand layouts of one Adam step in ONE launch ---------------------------------------------------
 // Block ranges: [0, fc_blocks) the two plain fc matrices, then one range per tile-image job, the last block
-// computes conv1's effective bias.
+// quantises conv1's weights for the integer forward kernel.
 struct PackAllArgs {
   PackArgs job[8];
   int first_block[9];     // job j owns blocks [first_block[j], first_block[j+1])
   int n_jobs;
   const float* wfc; __nv_bfloat16* fc_fwd; __nv_bfloat16* fc_dgrad; int fc_blocks;
-  const float* w1; const float* b1; float scale; float* b1eff;
+  const float* w1; float scale; int8_t* w1q; float* c1scale;      // conv1 forward: 16-bit fixed-point weights (umma_conv1_i8.cuh)
 };
 
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackAllArgs a) {
@@ -124,14 +120,27 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackAllArgs a) {
     return;
   }
   const int jb = blk - a.fc_blocks;
-  if (jb >= a.first_block[a.n_jobs]) {          // last block: conv1 effective bias, one warp per 4 output channels
+  if (jb >= a.first_block[a.n_jobs]) {          // last block: conv1's fixed-point weights, one warp per 4 output channels
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int n = warp; n < 32; n += 8) {
-      double s = 0.0;
-      for (int k = lane; k < 256; k += 32) s += (double)__half2float(__float2half_rn(a.w1[n * 256 + k]));
+      // integer conv1: channel n as 16-bit fixed point q * delta, q = 256 hi + lo (hi, lo in s8); B tile of tap ky:
+      // byte (row, k = kx*4 + ci) at ky*2048 + (row/8)*256 + (k/16)*128 + (row%8)*16 + k%16, rows n (hi) and 32 + n (lo)
+      float mx = 0.f;
+      for (int k = lane; k < 256; k += 32) mx = fmaxf(mx, fabsf(a.w1[n * 256 + k]));
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-      if (lane == 0) a.b1eff[n] = (float)((double)a.b1[n] - 1024.0 * (double)a.scale * s);
+      for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float delta = mx > 0.f ? mx / 32639.f : 1.f;      // |q| <= 127 * 256 + 127: hi = (q + 128) >> 8 stays in s8
+      for (int k = lane; k < 256; k += 32) {
+        const int ci = k >> 6, ky = (k >> 3) & 7, kx = k & 7;
+        int q = __float2int_rn(a.w1[n * 256 + k] / delta);
+        q = q > 32639 ? 32639 : (q < -32639 ? -32639 : q);
+        const int hi = (q + 128) >> 8, lo = q - hi * 256;
+        const int kb = kx * 4 + ci;
+        const int base = ky * 2048 + (kb >> 4) * 128 + (kb & 15);
+        a.w1q[base + (n >> 3) * 256 + (n & 7) * 16] = (int8_t)hi;
+        a.w1q[base + ((32 + n) >> 3) * 256 + ((32 + n) & 7) * 16] = (int8_t)lo;
+      }
+      if (lane == 0) a.c1scale[n] = (float)((double)delta * (double)a.scale);
     }
     return;
   }
@@ -167,7 +176,6 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&n->dact[2], nb * 3136 * 2));
   DRL_CUDA(cudaMalloc(&n->feat, nb * 512 * 4));
   DRL_CUDA(cudaMalloc(&n->dpre, nb * 512 * 2));
-  DRL_CUDA(cudaMalloc(&e->w1s, 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->w2f, 8 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->w3f, 9 * 64 * 128));
   DRL_CUDA(cudaMalloc(&e->wff, (size_t)512 * 3136 * 2));
@@ -176,7 +184,8 @@ int bf16_alloc(drl_net* n) {
   DRL_CUDA(cudaMalloc(&e->w2d, 4 * 4 * 32 * 128));
   DRL_CUDA(cudaMalloc(&e->whd, kHmWBytes));
   DRL_CUDA(cudaMalloc(&e->featb, nb * 512 * 2));
-  DRL_CUDA(cudaMalloc(&e->b1eff, 32 * sizeof(float)));
+  DRL_CUDA(cudaMalloc(&e->w1q, kI8WBytes));
+  DRL_CUDA(cudaMalloc(&e->c1scale, 32 * sizeof(float)));
   DRL_CUDA(cudaMalloc(&e->gt, kGtTotal * sizeof(float)));
   DRL_CUDA(cudaMemset(e->gt, 0, kGtTotal * sizeof(float)));
   DRL_CUDA(cudaMalloc(&e->bits[0], nb * 12800 / 8));
@@ -188,7 +197,7 @@ int bf16_alloc(drl_net* n) {
 void bf16_free(drl_net* n) {
   Bf16Engine* e = n->bf16;
   if (!e) return;
-  cudaFree(e->w1s); cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->whd); cudaFree(e->featb); cudaFree(e->b1eff); cudaFree(e->gt); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
+  cudaFree(e->w2f); cudaFree(e->w3f); cudaFree(e->wff); cudaFree(e->wfd); cudaFree(e->w3d); cudaFree(e->w2d); cudaFree(e->whd); cudaFree(e->featb); cudaFree(e->w1q); cudaFree(e->c1scale); cudaFree(e->gt); cudaFree(e->bits[0]); cudaFree(e->bits[1]); cudaFree(e->bits[2]);
   delete e;
   n->bf16 = nullptr;
 }
@@ -208,7 +217,6 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
     blocks += b < 1 ? 1 : b;
     ++nj;
   };
-  add(p + o[0], e->w1s, PK_CONV1_S2D, 1, 1, 4, 32, 4, 8, 8, 32);
   add(p + o[2], e->w2f, PK_CONV_FWD, 0, 1, 8, 64, 32, 4, 4, 64);
   add(p + o[4], e->w3f, PK_CONV_FWD, 0, 1, 9, 64, 64, 3, 3, 64);
   add(p + o[4], e->w3d, PK_CONV3_DGRAD, 0, 1, 9, 64, 64, 3, 3, 64);
@@ -220,7 +228,7 @@ int bf16_pack_params(drl_net* n, cudaStream_t st) {
   a.first_block[nj] = blocks;
   a.n_jobs = nj;
   a.wfc = p + o[6]; a.fc_fwd = (__nv_bfloat16*)e->wff; a.fc_dgrad = (__nv_bfloat16*)e->wfd; a.fc_blocks = sm_count() * 2;
-  a.w1 = p + o[0]; a.b1 = p + o[1]; a.scale = kInv255; a.b1eff = e->b1eff;
+  a.w1 = p + o[0]; a.scale = kInv255; a.w1q = e->w1q; a.c1scale = e->c1scale;
   pack_all_kernel<<<a.fc_blocks + blocks + 1, 256, 0, st>>>(a);
   DRL_LAUNCH_CHECK();
   return DRL_OK;
@@ -245,15 +253,19 @@ int bf16_trunk_forward(drl_net* n, const uint8_t* obs, const int64_t* row_idx, i
   Bf16Engine* e = n->bf16;
   const float* p = n->params;
   const int64_t* o = n->off;
-  // conv1: uint8 frames -> 1024-biased fp16 block image (space-to-depth); y = relu(acc * (1/255) + b)   (scale_observations.py:35 fused)
+  // conv1 on the raw bytes: u8 x s8 integer MMAs over TMA-staged row phases of the frame, 16-bit fixed-point weights;
+  // y = relu(acc * delta_c * (1/255) + b)   (scale_observations.py:35 fused; umma_conv1_i8.cuh)
   {
+    if (reinterpret_cast<uintptr_t>(obs) & 15) return DRL_ERR_BAD_ARG;      // TMA: 16-byte aligned frame store
     ProfileScope prof("conv1_fwd", st);
-    Conv1Args a1{};
-    a1.obs = obs; a1.row_idx = row_idx; a1.nb = nb; a1.bpack = e->w1s; a1.bias = e->b1eff; a1.scale = kInv255;
+    CUtensorMap tm;
+    DRL_TRY(make_tmap_frame_phases(&tm, obs));
+    Conv1I8Args a1{};
+    a1.row_idx = row_idx; a1.nb = nb; a1.bpack = e->w1q; a1.cscale = e->c1scale; a1.bias = p + o[1];
     a1.out = reinterpret_cast<__nv_bfloat16*>(n->act[0]); a1.mask_bits = e->bits[0];
     static int configured[kMaxDevices] = {0};
-    DRL_TRY(ensure_dyn_smem(conv1_fwd_s2d_kernel, kS2dFwdSmem, configured));
-    conv1_fwd_s2d_kernel<<<nb < sm_count() ? nb : sm_count(), kS2dFThreads, kS2dFwdSmem, st>>>(a1);
+    DRL_TRY(ensure_dyn_smem(conv1_fwd_i8_kernel, kI8Smem, configured));
+    conv1_fwd_i8_kernel<<<nb < sm_count() ? nb : sm_count(), kI8Threads, kI8Smem, st>>>(tm, a1);
     DRL_LAUNCH_CHECK();
   }
   {

@@ -7,7 +7,7 @@ import json
 import sys
 
 # launch order of one bf16 learner step (umma_net.cu / net.cu) and a substring each kernel name must contain
-SITES = [('pack_weights', 'pack_all_kernel'), ('conv1_fwd', 'conv1_fwd_s2d_kernel'), ('conv2_fwd', 'tma_conv2_kernel<64'),
+SITES = [('pack_weights', 'pack_all_kernel'), ('conv1_fwd', 'conv1_fwd_i8_kernel'), ('conv2_fwd', 'tma_conv2_kernel<64'),
          ('conv3_fwd', 'tma_conv_kernel<64'), ('fc_fwd', 'tma_gemm2_kernel'), ('heads_loss', 'heads_mma_kernel'),
          ('fc_wgrad', 'wgrad_tma_kernel'), ('fc_wgrad_t', 'wgrad_untranspose_kernel'), ('fc_dgrad', 'tma_gemm_kernel<256'),
          ('conv3_wgrad', 'wgrad_conv_tma_kernel<64, 5'), ('conv3_wgrad_t', 'wgrad_untranspose_kernel'),

@@ -274,6 +274,78 @@ def test_forward_vs_oracle(precision):
     np.testing.assert_allclose(ent.cpu().numpy(), e_ref.numpy(), rtol=0, atol=t['loss'])
 
 
+def _bf16_round(x):
+    return tc.from_numpy(np.asarray(x, np.float32)).to(tc.bfloat16).float().numpy()
+
+
+def _bf16_ulp(x):
+    return 2.0 ** (np.floor(np.log2(np.maximum(np.abs(x), 1e-30))) - 7)          # bf16: 8 significant bits
+
+
+def test_conv1_integer_forward_exactness():
+    """conv1 of the tcgen05 engine runs on the raw bytes (u8 x s8 integer MMAs, 16-bit fixed-point weights, s32 sums;
+    umma_conv1_i8.cuh).  (1) Impulse responses: one 255 pixel per frame, channel 31 carries the code 1 + ci*64 + ky*8 + kx as
+    its weight -> every output is that code to within half a weight step (tap geometry of the overlapping-row descriptors, both
+    weight halves), zero elsewhere.
+    (2) Range extremes: all 256 weights of a channel at +-max with all pixels 255 is the largest |256 S_hi + S_lo| the s32
+    combine can meet -> equals the fp64 convolution after bf16 rounding.  (3) Random frames: act1 within HALF a bf16 ulp
+    + 2e-4 of the fp64 oracle (weight quantisation 2^-15 of the channel maximum), i.e. bf16 output rounding is the only
+    visible error.  nature_cnn.py:27-29, scale_observations.py:35."""
+    A, rk = 6, ['extrinsic']
+    eng, params = _build('bf16', A, rk, 64)
+    wname = [k for k in params if params[k].shape == (32, 4, 8, 8)][0]
+    bname = [k for k in params if params[k].shape == (32,)][0]
+    code = (1 + np.arange(256)).reshape(4, 8, 8).astype(F32)
+    w = np.stack([code * (co + 1) / 32.0 for co in range(32)]).astype(F32)
+    eng.load_named({k: tc.from_numpy({wname: w, bname: np.zeros(32, F32)}.get(k, v)) for k, v in params.items()})
+    pix = [(0, 0, 0), (0, 0, 3), (0, 5, 1), (3, 0, 2), (5, 7, 0), (40, 41, 1), (83, 83, 3), (17, 62, 2), (4, 4, 0), (7, 7, 3),
+           (83, 0, 1), (0, 83, 2), (79, 79, 0), (80, 3, 3)]
+    obs = np.zeros((len(pix), 84, 84, 4), np.uint8)
+    for i, (y, x, c) in enumerate(pix):
+        obs[i, y, x, c] = 255
+    eng.forward(cu(obs), cu(np.arange(len(pix), dtype=np.int64)))
+    got = eng.activation(1, len(pix)).float().cpu().numpy().reshape(len(pix), 20, 20, 32)
+    for i, (y, x, c) in enumerate(pix):
+        want = np.zeros((20, 20), F32)
+        for oy in range(20):
+            for ox in range(20):
+                ky, kx = y - 4 * oy, x - 4 * ox
+                if 0 <= ky < 8 and 0 <= kx < 8:
+                    want[oy, ox] = code[c, ky, kx]
+        # weight step of channel 31: 256 / 32639 (|q| <= 127 * 256 + 127) -> half a step + half a bf16 ulp; codes differ by >= 1
+        assert np.all(np.abs(got[i, :, :, 31] - want) <= 0.5 * 256 / 32639 + 0.5 * _bf16_ulp(want)), f'impulse {(y, x, c)}'
+        assert np.all((got[i, :, :, 31] != 0) == (want != 0))
+    # (2) extremes of the s32 range
+    rs = np.random.RandomState(5)
+    w = np.zeros((32, 4, 8, 8), F32)
+    w[0] = 0.75; w[1] = -0.75; w[2] = 0.75 * rs.choice([-1.0, 1.0], size=(4, 8, 8)); w[3] = rs.uniform(-0.75, 0.75, (4, 8, 8))
+    w[4:] = rs.standard_normal((28, 4, 8, 8)) * 0.05
+    bias = rs.uniform(-0.1, 0.1, 32).astype(F32)
+    bias[1] = 200.0                                           # keeps the most negative sum visible through the ReLU
+    eng.load_named({k: tc.from_numpy({wname: w, bname: bias}.get(k, v)) for k, v in params.items()})
+    obs = np.full((3, 84, 84, 4), 255, np.uint8)
+    obs[1] = rs.randint(0, 2, size=(84, 84, 4)) * 255
+    obs[2] = rs.randint(0, 256, size=(84, 84, 4))
+    eng.forward(cu(obs), cu(np.arange(3, dtype=np.int64)))
+    got = eng.activation(1, 3).float().cpu().numpy().reshape(3, 20, 20, 32)
+    x64 = tc.from_numpy(obs).permute(0, 3, 1, 2).double() * float(np.float32(1.0 / 255.0))
+    ref = tc.relu(tc.nn.functional.conv2d(x64, tc.from_numpy(w).double(), tc.from_numpy(bias).double(), stride=4)).permute(0, 2, 3, 1).numpy()
+    ulp = _bf16_ulp(ref)
+    wmax = np.abs(w).reshape(32, -1).max(1)
+    assert np.all(np.abs(got - ref) <= 0.5 * ulp + 256 * wmax * 2.0 ** -15 + 1e-6), np.abs(got - ref).max()
+    assert got[0, 0, 0, 0] == _bf16_round(0.75 * 256 + bias[0]) and got[0, 0, 0, 1] == _bf16_round(200.0 - 0.75 * 256)
+    # (3) random frames with the seeded NatureCNN weights
+    eng, params = _build('bf16', A, rk, 64)
+    obs = rs.randint(0, 256, size=(40, 84, 84, 4), dtype=np.uint8)
+    rows = rs.permutation(40)[:33].astype(np.int64)
+    eng.forward(cu(obs), cu(rows))
+    got = eng.activation(1, 33).float().cpu().numpy().reshape(33, 20, 20, 32)
+    x64 = tc.from_numpy(obs[rows]).permute(0, 3, 1, 2).double() * float(np.float32(1.0 / 255.0))
+    ref = tc.relu(tc.nn.functional.conv2d(x64, tc.from_numpy(params[wname]).double(), tc.from_numpy(params[bname]).double(),
+                                          stride=4)).permute(0, 2, 3, 1).numpy()
+    assert np.all(np.abs(got - ref) <= 0.5 * _bf16_ulp(ref) + 2e-4), np.abs(got - ref).max()
+
+
 def _ppo_case(A, rk, n_envs, T, B, seed=0):
     params = po.init_params(A, rk, seed=11)
     credit = {k: dict(gamma=0.99, lambda_=0.95, use_dones=(k == 'extrinsic')) for k in rk}
