@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) conv1_fwd_i8_kernel(const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kI8Stages; ++s) { mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, 1); }
-    for (int a = 0; a < kI8NAcc; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < kI8NAcc; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) conv1_fwd_i8_kernel(const __gri
           tmem_ld_wait();
           if (h == 1) {
             tc_fence_before();
-            mbar_arrive(tempty + acc);
+            mbar_arrive_warp(tempty + acc);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) conv1_fwd_i8_kernel(const __gri
         }
       } else {
         tc_fence_before();
-        mbar_arrive(tempty + acc);
+        mbar_arrive_warp(tempty + acc);
       }
     }
   }

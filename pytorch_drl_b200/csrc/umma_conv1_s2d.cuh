@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, NCONV);
-      mbar_init(img_full + s, NCONV); mbar_init(img_empty + s, 1);
+      mbar_init(raw_full + s, 1); mbar_init(raw_empty + s, NCONV / 32);
+      mbar_init(img_full + s, NCONV / 32); mbar_init(img_empty + s, 1);
       mbar_init(dy_full + s, 1);
     }
     mbar_init(done, 1);
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(img_full + s);
-        mbar_arrive(raw_empty + s);
+        mbar_arrive_warp(img_full + s);
+        mbar_arrive_warp(raw_empty + s);
       }
     } else if (warp == 4) {
       // ================= MMA issuer =================

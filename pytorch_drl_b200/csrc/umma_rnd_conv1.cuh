@@ -122,7 +122,7 @@ __device__ __forceinline__ void r1_converters(const RndConv1Args& args, const R1
         }
       }
     }
-    mbar_arrive(sm.raw_empty + rs);
+    mbar_arrive_warp(sm.raw_empty + rs);
     asm volatile("bar.sync 1, 256;" ::: "memory");           // both images complete
     // phase B: im2col tiles, one step = tile `tile` of both frames
 #pragma unroll 1
@@ -144,7 +144,7 @@ __device__ __forceinline__ void r1_converters(const RndConv1Args& args, const R1
         }
       }
       fence_proxy_async_smem();
-      mbar_arrive(sm.a_full + slot);
+      mbar_arrive_warp(sm.a_full + slot);
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");           // everybody is done reading the images
   }
@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(kR1FThreads, 1) rnd_conv1_fwd_kernel(const Rnd
   const int n_mine = (int)blockIdx.x < n_pairs ? (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (threadIdx.x == 0) {
-    for (int q = 0; q < kR1RawStages; ++q) { mbar_init(sm.raw_full + q, 1); mbar_init(sm.raw_empty + q, 256); }
-    for (int s = 0; s < kR1Steps; ++s) { mbar_init(sm.a_full + s, 256); mbar_init(sm.a_empty + s, 1); }
-    for (int a = 0; a < kR1NAcc; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 128); }
+    for (int q = 0; q < kR1RawStages; ++q) { mbar_init(sm.raw_full + q, 1); mbar_init(sm.raw_empty + q, 8); }
+    for (int s = 0; s < kR1Steps; ++s) { mbar_init(sm.a_full + s, 8); mbar_init(sm.a_empty + s, 1); }
+    for (int a = 0; a < kR1NAcc; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kR1FThreads, 1) rnd_conv1_fwd_kernel(const Rnd
       tmem_ld_32x32b_x32(ta + 32, r1);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(acc_empty + acc);
+      mbar_arrive_warp(acc_empty + acc);
       if (pos < 400) {
         auto act = [&](uint32_t raw_acc, int i) {
           const float v = __uint_as_float(raw_acc) + bias[i];
@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(kR1Threads, 1) rnd_conv1_wgrad_kernel(const __
   const int n_mine = (int)blockIdx.x < n_pairs ? (n_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (threadIdx.x == 0) {
-    for (int q = 0; q < kR1RawStages; ++q) { mbar_init(sm.raw_full + q, 1); mbar_init(sm.raw_empty + q, 256); }
-    for (int s = 0; s < kR1Steps; ++s) { mbar_init(sm.a_full + s, 256); mbar_init(sm.a_empty + s, 1); mbar_init(dy_full + s, 1); }
+    for (int q = 0; q < kR1RawStages; ++q) { mbar_init(sm.raw_full + q, 1); mbar_init(sm.raw_empty + q, 8); }
+    for (int s = 0; s < kR1Steps; ++s) { mbar_init(sm.a_full + s, 8); mbar_init(sm.a_empty + s, 1); mbar_init(dy_full + s, 1); }
     mbar_init(done, 1);
     fence_barrier_init();
   }

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
   if (!epi_is_mask(EPI) && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int a = 0; a < NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, 1); }
-    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_conv_kernel(const 
         if (NEPI > 1 && (int)(it % NEPI) != wg) continue;
         const uint32_t acc = it % NACC;
         tma_conv_epilogue_tile<N, EPI, BG>(args, b, mt * 128 + trow, true, tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * N,
-                                           sBias, cs, tfull + acc, (it / NACC) & 1, [&]() { mbar_arrive(tempty + acc); });
+                                           sBias, cs, tfull + acc, (it / NACC) & 1, [&]() { mbar_arrive_warp(tempty + acc); });
       }
     }
     if (epi_is_mask(EPI) && args.bias_grad) {

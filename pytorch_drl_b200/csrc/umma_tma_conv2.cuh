@@ -13,7 +13,7 @@
 //   raw_full[s]   leader only: 1 arrival (expect_tx of both boxes) + the loads of the pair
 //   raw_empty[s]  both CTAs: tcgen05.commit multicast after the MMAs that read slot s
 //   tfull[a]      both CTAs: tcgen05.commit multicast after the last MMA of a tile
-//   tempty[a]     leader only: 256 arrivals = one epilogue warpgroup of each CTA (remote arrive from the peer)
+//   tempty[a]     leader only: 8 arrivals = the 4 warps of one epilogue warpgroup of each CTA (one remote arrive per warp)
 // Pair p processes sample pairs q = p, p + pairs, ...: rank r owns sample 2q + r (the last pair of an odd batch
 // re-loads sample nb - 1 in rank 1 and discards it).
 #pragma once
@@ -68,7 +68,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NEPI + 2),
   if (EPI != EPI_MASK_BF16 && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int a = 0; a < NR; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, 1); }
-    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -176,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NEPI + 2),
       const uint32_t acc = (uint32_t)j % NACC;
       const int b = sample_of(j);
       tma_conv_epilogue_tile<N, EPI, BG>(args, b, trow, b < args.nb, tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * N, sBias, cs,
-                                         tfull + acc, ((uint32_t)j / NACC) & 1, [&]() { mbar_arrive_leader(tempty + acc); });
+                                         tfull + acc, ((uint32_t)j / NACC) & 1, [&]() { mbar_arrive_leader_warp(tempty + acc); });
     }
     if (EPI == EPI_MASK_BF16 && args.bias_grad) {
 #pragma unroll
@@ -265,7 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NEPI + 2),
   if (EPI != EPI_MASK_BF16 && threadIdx.x < N) sBias[threadIdx.x] = args.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int a = 0; a < NRG; ++a) { mbar_init(raw_full + a, 1); mbar_init(raw_empty + a, 1); }
-    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 256); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 8); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -361,7 +361,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NEPI + 2),
         const int r = t * 128 + trow;
         const int sidx = r / SROWS, rem = r - sidx * SROWS;
         tma_conv_epilogue_tile<N, EPI, BG>(args, b0 + sidx, rem, sidx < nv, tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + t * N, sBias,
-                                           cs, tfull + t, (uint32_t)j & 1, [&]() { mbar_arrive_leader(tempty + t); });
+                                           cs, tfull + t, (uint32_t)j & 1, [&]() { mbar_arrive_leader_warp(tempty + t); });
       }
     }
     if (EPI == EPI_MASK_BF16 && args.bias_grad) {

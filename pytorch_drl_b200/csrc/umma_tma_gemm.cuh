@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 128 * NEPI); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4 * NEPI); }
     fence_barrier_init();
   }
   constexpr int W_MMA = 4 * NEPI, W_TMA = 4 * NEPI + 1;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(32 * (4 * NEPI + 2), 1) tma_gemm_kernel(const 
         tmem_ld_wait();
         if (c2 == CPW - 1) {
           tc_fence_before();
-          mbar_arrive(tempty + acc);
+          mbar_arrive_warp(tempty + acc);
         }
         const int n = n0 + ch * 32;
         if (m < args.M && n < args.N_total) {

@@ -84,6 +84,13 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
       : "memory");
 }
 
+// The same for a whole converged warp with ONE remote arrival: 128 remote arrivals per accumulator tile serialise on the
+// leader's barrier (the CTA-pair conv kernels sat on a 0.20 ms floor of these handshakes); barrier counts are per warp.
+__device__ __forceinline__ void mbar_arrive_leader_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive_leader(bar);
+}
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
     tma_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -108,7 +115,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 512); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 16);      // 2 CTAs x 2 epilogue warpgroups x 4 warps (mbar_arrive_leader_warp) }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc2(tmem_slot, 512);
@@ -193,7 +200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
         tmem_ld_wait();
         if (c2 == BN / 64 - 1) {
           tc_fence_before();
-          mbar_arrive_leader(tempty + acc);
+          mbar_arrive_leader_warp(tempty + acc);
         }
         const int n = n0 + ch * 32;
         if (m < args.M && n < args.N_total) {
