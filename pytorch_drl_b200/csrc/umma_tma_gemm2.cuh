@@ -115,7 +115,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 16);      // 2 CTAs x 2 epilogue warpgroups x 4 warps (mbar_arrive_leader_warp) }
+    // tempty: 16 arrivals = 2 CTAs x 2 epilogue warpgroups x 4 warps (mbar_arrive_leader_warp)
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 16); }
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc2(tmem_slot, 512);
