@@ -758,7 +758,56 @@ def run_extras(algo, agent, rollout, st, n_envs, dev, ms_per_step, pk, hyper, ba
     out['actor'] = run_actor_extras(agent, n_envs, dev)
     # ---- PER sum-tree (config 4): 2^20 leaves, batch 512 — dependent-access latency bound; parity unpinned (no reference code) ----
     out['sumtree'] = run_sumtree_extras(dev, g)
+    # ---- config 3 of BASELINE.json: double / dueling DQN learner step on a 2^20-transition prioritized replay buffer, batch 512 ----
+    out['dqn'] = run_dqn_extras(rollout, dev, g)
     return out
+
+
+def run_dqn_extras(rollout, dev, g):
+    """One DQN learner step = prioritized sample of 512 of 2^20 transitions (fused stratified draw + importance weights), Q(s') of the
+    online and the target network and Q(s) on the frame ring by row index (no gather copy), double-Q Bellman targets + SmoothL1 TD
+    loss + gradients (dueling head, trunk), Adam on both, |td| priorities back into the sum-tree.  The ring holds 2^20 uint8 stacks
+    (29.6 GB): its first 131 072 slots are the benchmark's random frames, the rest zeros (kernel times do not depend on the data)."""
+    from pytorch_drl_b200 import agents
+    from pytorch_drl_b200.algos.dqn import DQN
+    from pytorch_drl_b200.replay import PrioritizedReplayBuffer
+    A, nb, cap = 6, 512, 1 << 20
+    try:
+        replay = PrioritizedReplayBuffer(cap, 0.6, 1e-6, device=dev)
+    except tc.OutOfMemoryError:
+        return {'skipped': 'no room for the 29.6 GB frame ring next to the rollout'}
+    obs = rollout['observations']
+    n_real = min(obs.shape[0] * obs.shape[1], cap)
+    replay.frames.view(cap, -1)[:n_real] = obs.reshape(-1, obs[0, 0].numel())[:n_real]
+    replay.actions.random_(0, A, generator=g)
+    replay.rewards.copy_(tc.randint(-1, 2, (cap,), device=dev, generator=g).float())
+    replay.dones.copy_((tc.rand(cap, device=dev, generator=g) < 0.01).float())
+    replay.count, replay.index.size = cap, cap
+    replay.index.tree.set_leaves(tc.rand(cap, device=dev, generator=g) + 0.01)
+    qas = []
+    for _ in range(2):
+        head = agents.SimpleDiscreteActionValueHead(512, A, agents.DuelingArchitecture, {'widening': 1},
+                                                    w_init=lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5), b_init=tc.nn.init.zeros_)
+        qa = agents.QAgent([agents.ToChannelMajor()], agents.NatureCNN(4, lambda w: tc.nn.init.orthogonal_(w, gain=2 ** 0.5), tc.nn.init.zeros_),
+                           {'action_value_extrinsic': head})
+        qas.append(qa.fuse(max_batch=nb, precision='bf16', device=dev))
+    dqn = DQN(qas[0], qas[1], replay, batch_size=nb, gamma=0.99, double_q=True, loss='SmoothL1Loss', lr=1e-4, target_update_interval=1000)
+    ms = timed(dqn.learner_step, iters=50, warm=5)
+    tc.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        dqn.learner_step()
+    host_ms = (time.perf_counter() - t0) / 50 * 1e3
+    tc.cuda.synchronize()
+    loss = float(dqn.loss.item())
+    del dqn, qas, replay
+    tc.cuda.empty_cache()
+    return {'workload': 'double / dueling DQN (NatureCNN trunk + DuelingArchitecture head), 2^20-transition prioritized replay, batch 512',
+            'ms_per_step': ms, 'samples_per_s': nb / (ms * 1e-3), 'host_enqueue_ms_per_step': host_ms, 'final_loss': loss,
+            'trunk_passes_per_step': '3 forward (online s, online s\', target s\') + 1 recomputed forward + 1 backward at 512 samples',
+            'bound': 'launch latency: ~45 launches of 4-148 CTAs per step; the host enqueue time is the floor when larger',
+            'parity': 'network blocks + Bellman operator pinned to the reference (tests/golden/dqn.npz); the algorithm itself has no reference '
+                      'counterpart (the reference ships no DQN learner and its dueling head cannot be differentiated as written: dueling.py:53)'}
 
 
 def graph_timed(fn, iters=50):

@@ -225,6 +225,21 @@ int drl_dueling_forward_f32(const float* feat, int nb, int in_dim, int num_actio
                             const float* b0, const float* wa1, const float* ba1, const float* wa2, const float* ba2,
                             const float* wv1, const float* bv1, const float* wv2, const float* bv2, float* q_out,
                             void* stream);
+/* DQN learner step on that head (BASELINE config "Double/Dueling DQN with prioritized replay").  The reference ships the head
+ * (dueling.py:9-57, action_value_heads.py:85-140) and the double-Q Bellman operator (credit_assignment.py:252-305) but no DQN
+ * algorithm; this entry is the loss a learner puts on them and its gradient, for a batch of sampled transitions:
+ *   y_i = rewards_i + (1 - dones_i) * gamma * q_next_target[i, argmax_a q_sel[i, a]]     q_sel = q_next_online if double_q else q_next_target
+ *   td_i = Q(s_i, actions_i) - y_i ;  loss = mean_i is_weights_i * crit(td_i) ;  crit = SmoothL1 (beta 1) if smooth_l1 else squared error
+ * head_params / head_grads: ONE flat fp32 buffer each in the reference module's parameters() order
+ *   [w0 50 x in_dim | b0 50 | wa1 25 x 50 | ba1 25 | wa2 A x 25 | ba2 A | wv1 25 x 50 | bv1 25 | wv2 25 | bv2 1];
+ * head_grads and loss_out[1] are ACCUMULATED into (caller zeroes them), dfeat_out [nb, in_dim] = d loss / d features is
+ * overwritten (feed it to drl_net_backward_features), q_out [nb, A] / y_out [nb] are optional, td_out [nb] feeds the priority
+ * update (drl_sumtree_update), workspace: nb * 50 floats.  is_weights may be NULL (all ones). */
+int drl_dueling_loss_backward_f32(const float* feat, int nb, int in_dim, int num_actions, int widening,
+                                  const float* head_params, const int64_t* actions, const float* rewards, const float* dones,
+                                  const float* q_next_online, const float* q_next_target, const float* is_weights, float gamma,
+                                  int use_dones, int double_q, int smooth_l1, float* q_out, float* td_out, float* y_out,
+                                  float* loss_out, float* dfeat_out, float* head_grads, float* workspace, void* stream);
 /* probs[nb, A] = (1 - eps) * one_hot(argmax_a q) + eps / A (first maximum on ties, like torch.argmax), bit-identical
  * to the reference's float32 expression; greedy_out (nullable) receives the argmax.  eps outside [0, 1] is refused. */
 int drl_epsilon_greedy_probs_f32(const float* q, int nb, int num_actions, double epsilon, float* probs_out,
@@ -386,6 +401,11 @@ int drl_comm_p2p_import(drl_comm_t* comm, const uint8_t* handles_all /* [world][
  * Activations are recomputed; `grads` is overwritten. */
 int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dlogits,
                      const float* dvalues, float* grads, void* stream);
+/* The same for a head that lives outside the handle (the DQN action-value head): trunk gradients from dfeat [nb, 512] =
+ * d loss / d(the features drl_net_features returned).  Activations are recomputed; `grads` (flat, drl_net_param_count
+ * floats) is overwritten, the slices of the handle's own policy / value heads stay zero. */
+int drl_net_backward_features(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dfeat,
+                              float* grads, void* stream);
 /* Attach (or detach, comm = NULL) a communicator to a network handle: drl_net_ppo_step then returns gradients
  * that are already SUMMED over the ranks — what DistributedDataParallel's backward hooks do in the reference
  * (drl/utils/launch.py:310, drl/algos/ppo.py:233) — and overlaps the exchange with the backward pass: the

@@ -16,6 +16,8 @@ What is pinned (all from reference code, never from the oracle):
                  drl/algos/common/credit_assignment.py:225-249, 276-305
   reward_norm.npz ReturnAcc.update/forward (the reward normaliser's accumulator)
                  drl/envs/wrappers/stateful/normalize_reward.py:20-100
+  dqn.npz        TD loss + autograd gradients through the reference's Agent(NatureCNN, SimpleDiscreteActionValueHead(Dueling)) and
+                 SimpleDiscreteBellmanOptimalityOperator targets (pins oracle/dqn_oracle.py)
   dueling.npz    DuelingArchitecture.forward through SimpleDiscreteActionValueHead, and the probabilities of
                  EpsilonGreedyCategoricalPolicyHead  (dueling.py:50-57, action_value_heads.py:124-140,
                  policy_heads.py:197-226)
@@ -476,6 +478,59 @@ def gen_actor_rollout():
     np.savez_compressed(os.path.join(GOLD, 'actor_rollout.npz'), **out)
 
 
+def gen_dqn():
+    """The DQN blocks of the reference — Agent(NatureCNN, SimpleDiscreteActionValueHead(DuelingArchitecture)) built like
+    launch.py:268-282 and SimpleDiscreteBellmanOptimalityOperator — under the TD loss of oracle/dqn_oracle.py, gradients by torch
+    autograd THROUGH THE REFERENCE MODULES.  Pins oracle/dqn_oracle.py (the restatement the GPU tests compare with)."""
+    from drl.agents.architectures.stateless.dueling import DuelingArchitecture
+    from drl.agents.architectures.stateless.nature_cnn import NatureCNN
+    from drl.agents.heads.action_value_heads import SimpleDiscreteActionValueHead
+    from drl.agents.integration.agent import Agent
+    from drl.agents.preprocessing.vision import ToChannelMajor
+    from drl.algos.common.credit_assignment import SimpleDiscreteBellmanOptimalityOperator
+    from oracle import dqn_oracle as do
+    out = {}
+    cases = [(6, 5, 0.99, True, True, 'SmoothL1Loss'), (18, 4, 0.9, True, False, 'MSELoss'), (4, 3, 0.99, False, True, 'SmoothL1Loss')]
+    for i, (A, nb, gamma, use_dones, double_q, loss) in enumerate(cases):
+        def build(seed):
+            head = SimpleDiscreteActionValueHead(num_features=512, num_actions=A, head_architecture_cls=DuelingArchitecture,
+                                                 head_architecture_cls_args={'widening': 1}, w_init=None, b_init=None)
+            agent = Agent([ToChannelMajor()], NatureCNN(4, None, None), {'action_value_extrinsic': head})
+            agent.load_state_dict({k: tc.from_numpy(v.copy()) for k, v in do.init_params(A, seed).items()}, strict=True)
+            return agent
+        online, target = build(40 + i), build(70 + i)
+        obs, nxt, actions, rewards, dones, weights = do.make_case(500 + i, nb, A)
+        x, xn = po.scale_obs(tc.from_numpy(obs)), po.scale_obs(tc.from_numpy(nxt))
+        with tc.no_grad():
+            qn_on = online(xn, predict=['action_value_extrinsic'])['action_value_extrinsic']
+            qn_tg = target(xn, predict=['action_value_extrinsic'])['action_value_extrinsic']
+        op = SimpleDiscreteBellmanOptimalityOperator(gamma=gamma, use_dones=use_dones, double_q=double_q)
+        y = tc.stack([op(rollout_len=1, extra_steps=0, rewards=tc.tensor([rewards[j]]), qpreds=tc.stack([qn_on[j], qn_on[j]]),
+                         tgt_qpreds=tc.stack([qn_tg[j], qn_tg[j]]), dones=tc.tensor([dones[j]]))[0] for j in range(nb)])
+        # DuelingArchitecture.forward subtracts the mean IN PLACE from a ReLU output (dueling.py:53), which autograd refuses
+        # ("modified by an inplace operation": the shipped head was never trained).  The differentiable pass therefore calls the
+        # reference's own sub-modules and forms `adv - mean(adv) + val` out of place; the no-grad passes above use forward() itself.
+        head = online._predictors['action_value_extrinsic']._action_value_head
+        feats = online._architecture(online._preprocessing(x))
+        proj = head._proj(feats)
+        adv = head._advantage_stream(proj)
+        q = (adv - adv.mean(dim=-1, keepdim=True)) + head._value_stream(proj)
+        with tc.no_grad():
+            assert tc.equal(q.detach(), online(x, predict=['action_value_extrinsic'])['action_value_extrinsic'])
+        q_taken = q.gather(1, tc.from_numpy(actions).unsqueeze(1)).squeeze(1)
+        crit = getattr(tc.nn, loss)(reduction='none')                                     # drl/algos/common/losses.py:6-18
+        total = (tc.from_numpy(weights) * crit(q_taken, y)).mean()
+        online.zero_grad()
+        total.backward()
+        grads = {k: v.grad.numpy() for k, v in online.named_parameters()}
+        out.update({f'c{i}_meta': np.array([A, nb, gamma, float(use_dones), float(double_q), float(loss == 'SmoothL1Loss'), 40 + i, 70 + i, 500 + i]),
+                    f'c{i}_q': q.detach().numpy(), f'c{i}_y': y.numpy(), f'c{i}_loss': np.array(float(total.detach())),
+                    f'c{i}_qn_on': qn_on.numpy(), f'c{i}_qn_tg': qn_tg.numpy()})
+        out.update({f'c{i}_{k}': v for k, v in do.summarize_grads(grads, list(grads.keys())).items()})
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(GOLD, 'dqn.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_loader.load()
@@ -488,6 +543,7 @@ def main():
     gen_reward_norm()
     gen_nstep_bellman()
     gen_dueling()
+    gen_dqn()
     gen_actor_rollout()
     gen_ppo('ppo_2rank', ['extrinsic'], {'extrinsic': 1.0}, False, 29611)
     gen_ppo('ppo_2rank_rnd', ['extrinsic', 'intrinsic_rnd'], {'extrinsic': 2.0, 'intrinsic_rnd': 1.0},

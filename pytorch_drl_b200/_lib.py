@@ -53,6 +53,7 @@ PROTOTYPES = {
     'drl_net_destroy': (c_int, [c_void_p]),
     'drl_net_set_comm': (c_int, [c_void_p, c_void_p]),
     'drl_net_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'drl_net_backward_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'drl_net_param_count': (c_int64, [c_int, c_int]),
     'drl_net_param_offsets': (c_int, [c_int, c_int, POINTER(c_int64), c_int]),
     'drl_net_set_params': (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -103,6 +104,8 @@ PROTOTYPES = {
     'drl_bellman_backups_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64,
                                         c_int64, c_int64, c_float, c_int, c_int, c_void_p, c_void_p]),
     'drl_dueling_forward_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 10 + [c_void_p, c_void_p]),
+    'drl_dueling_loss_backward_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 7 + [c_float, c_int, c_int, c_int] +
+                                      [c_void_p] * 8),
     'drl_epsilon_greedy_probs_f32': (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     'drl_return_acc_update_f32': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_float, c_int, c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

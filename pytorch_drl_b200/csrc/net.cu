@@ -80,6 +80,24 @@ static int fp32_trunk_backward(drl_net* n, const uint8_t* obs, const int64_t* ro
   return DRL_OK;
 }
 
+// d(features) of an external head (the DQN action-value head) -> d(pre-activation) of the fc layer in the engine's format,
+// masked by the fc ReLU (feat > 0); the tcgen05 engine also needs the fc bias gradient = column sums (its heads kernel
+// normally produces it).  One thread per column, 64 rows per block.
+template <typename TOut>
+__global__ void __launch_bounds__(512) dfeat_to_dpre_kernel(const float* __restrict__ feat, const float* __restrict__ dfeat, int nb,
+                                                            TOut* __restrict__ dpre, float* __restrict__ gfc_bias) {
+  const int c = threadIdx.x, r0 = blockIdx.x * 64, r1 = min(nb, r0 + 64);
+  float sum = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const size_t e = (size_t)r * 512 + c;
+    const float d = feat[e] > 0.f ? dfeat[e] : 0.f;
+    sum += d;
+    if constexpr (sizeof(TOut) == 2) dpre[e] = __float2bfloat16_rn(d);
+    else dpre[e] = d;
+  }
+  if (gfc_bias) atomicAdd(gfc_bias + c, sum);
+}
+
 static int check_call(const drl_net* net, const void* obs, int nb) {
   if (!net || !obs) return DRL_ERR_BAD_ARG;
   if (!net->params) return DRL_ERR_BAD_ARG;       // drl_net_set_params first
@@ -226,6 +244,25 @@ extern "C" int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_
   DRL_TRY(heads_loss_dispatch(3, bf16, net->feat, hpp, row_idx, nb, batch, hp, nullptr, const_cast<float*>(dlogits),
                               const_cast<float*>(dvalues), nullptr, nullptr, net->dpre, st));
   // no collective here: the caller owns `grads` (a scratch buffer of the autograd path) and decides when to exchange it
+  DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, /*overlap_comm=*/false, st)
+               : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
+  return DRL_OK;
+}
+
+extern "C" int drl_net_backward_features(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dfeat,
+                                         float* grads, void* stream) {
+  DRL_TRY(check_call(net, obs, nb));
+  if (!dfeat || !grads) return DRL_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  const bool bf16 = net->precision == DRL_PRECISION_BF16;
+  DRL_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->nparams * sizeof(float), st));
+  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, false, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
+  if (bf16)
+    dfeat_to_dpre_kernel<__nv_bfloat16><<<(nb + 63) / 64, 512, 0, st>>>(net->feat, dfeat, nb, reinterpret_cast<__nv_bfloat16*>(net->dpre),
+                                                                       grads + net->off[7]);
+  else
+    dfeat_to_dpre_kernel<float><<<(nb + 63) / 64, 512, 0, st>>>(net->feat, dfeat, nb, reinterpret_cast<float*>(net->dpre), nullptr);
+  DRL_LAUNCH_CHECK();
   DRL_TRY(bf16 ? bf16_trunk_backward(net, obs, row_idx, nb, grads, /*overlap_comm=*/false, st)
                : fp32_trunk_backward(net, obs, row_idx, nb, grads, st));
   return DRL_OK;

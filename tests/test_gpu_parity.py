@@ -1068,6 +1068,131 @@ def test_qagent_trunk_features_and_dueling_q_vs_oracle(precision, golden_dir):
     np.testing.assert_array_equal(out2['action_value'].cpu().numpy(), q)
 
 
+# ---- DQN learner step around the replay buffer (BASELINE config "Double/Dueling DQN with prioritized replay"; §8 f4) ----
+def _dqn_setup(precision, A, nb, capacity, seeds=(40, 70), **kw):
+    from oracle import dqn_oracle as do
+    from pytorch_drl_b200 import agents
+    from pytorch_drl_b200.algos.dqn import DQN
+    from pytorch_drl_b200.replay import PrioritizedReplayBuffer
+    params = [do.init_params(A, s) for s in seeds]
+    qas = []
+    for p in params:
+        head = agents.SimpleDiscreteActionValueHead(512, A, agents.DuelingArchitecture, {'widening': 1})
+        qa = agents.QAgent([agents.ToChannelMajor()], agents.NatureCNN(4), {'action_value_extrinsic': head})
+        qa.load_state_dict({k: tc.from_numpy(v) for k, v in p.items()}, strict=False)
+        qa.fuse(max_batch=nb, precision=precision, device=dev())
+        qas.append(qa)
+    replay = PrioritizedReplayBuffer(capacity, 0.6, 1e-6, device=dev())
+    dqn = DQN(qas[0], qas[1], replay, batch_size=nb, **kw)
+    # the constructor copies online -> target; the parity cases want a DIFFERENT target network
+    dqn.target.engine.load_named({**{k: tc.zeros_like(v) for k, v in dqn.target.engine.named_views().items()},
+                                  **{k: tc.from_numpy(params[1][k]) for k in po.TRUNK_KEYS}})
+    for k, v in dqn.target_head.views().items():
+        v.copy_(tc.from_numpy(params[1][do.HEAD_PREFIX + k]))
+    return dqn, params
+
+
+@pytest.mark.parametrize('precision', _precisions())
+@pytest.mark.parametrize('A,gamma,use_dones,double_q,loss', [(6, 0.99, True, True, 'SmoothL1Loss'), (18, 0.9, False, False, 'MSELoss')])
+def test_dqn_loss_and_grads_vs_oracle(precision, A, gamma, use_dones, double_q, loss):
+    """Q(s, .), double-Q Bellman targets, importance-weighted TD loss and its gradient w.r.t. EVERY parameter (dueling head through
+    drl_dueling_loss_backward_f32, trunk through drl_net_backward_features) against oracle/dqn_oracle.py, which is pinned to the
+    reference's own modules + torch autograd (tests/golden/dqn.npz).  fp32 engine: tight; tcgen05 engine: the bf16 bars of TOL."""
+    from oracle import dqn_oracle as do
+    nb = 24
+    dqn, (p_on, p_tg) = _dqn_setup(precision, A, nb, 64, gamma=gamma, use_dones=use_dones, double_q=double_q, loss=loss)
+    obs, nxt, actions, rewards, dones, weights = do.make_case(11, nb, A)
+    frames = np.concatenate([obs, nxt])                                    # ring rows: s_i = i, s'_i = nb + i
+    rows, nrows = np.arange(nb, dtype=np.int64), np.arange(nb, 2 * nb, dtype=np.int64)
+    dqn.loss_and_grads(cu(frames), cu(rows), cu(nrows), cu(actions), cu(rewards), cu(dones), cu(weights))
+    t = TOL[precision]
+    qn_on = dqn.q_values(dqn.online, dqn.head, cu(frames), cu(nrows)).cpu().numpy()
+    qn_tg = dqn.q_values(dqn.target, dqn.target_head, cu(frames), cu(nrows)).cpu().numpy()
+    assert rel_l2(qn_on, do.q_values(p_on, nxt)) < 2 * t['act'] and rel_l2(qn_tg, do.q_values(p_tg, nxt)) < 2 * t['act']
+    y_dev = dqn.y.cpu().numpy()
+    # the targets are EXACTLY the reference operator applied to the device's own Q(s', .)
+    np.testing.assert_array_equal(y_dev, do.bellman_targets(rewards, dones, qn_on, qn_tg, gamma, use_dones, double_q))
+    res, grads = do.loss_and_grads(p_on, p_tg, obs, nxt, actions, rewards, dones, weights, gamma, use_dones, double_q, loss,
+                                   y_override=None if precision == 'fp32' else y_dev)
+    assert rel_l2(dqn.q.cpu().numpy(), res['q']) < 2 * t['act']
+    np.testing.assert_allclose(y_dev, res['y'], rtol=0, atol=2 * t['act'] * max(1.0, float(np.abs(res['y']).max())))
+    np.testing.assert_allclose(dqn.td.cpu().numpy(), res['td'], rtol=0, atol=2 * t['act'] * max(1.0, float(np.abs(res['q']).max())))
+    assert abs(float(dqn.loss.item()) - res['loss']) < max(t['loss'], 20 * t['act']) * max(1.0, abs(res['loss']))
+    got = {**{k: v for k, v in dqn.online.engine.named_views(dqn.online.engine.grads).items() if k in po.TRUNK_KEYS},
+           **{do.HEAD_PREFIX + k: v for k, v in dqn.head.views(dqn.head_grads).items()}}
+
+    def check(gref_all, bar, min_cos):
+        for k, gref in gref_all.items():
+            gdev = got[k].cpu().numpy().astype(np.float64)
+            if np.linalg.norm(gref) == 0:
+                assert np.linalg.norm(gdev) == 0, k
+                continue
+            err = rel_l2(gdev, gref)
+            cos = float((gdev * gref).sum() / (np.linalg.norm(gdev) * np.linalg.norm(gref)))
+            assert err < bar and cos > min_cos, (k, err, cos)
+    if precision == 'fp32':
+        check(grads, t['grad'], 0.999999)                                   # the whole chain against the oracle
+    else:
+        # bf16 trunk: a few ReLU units of the 50 / 25-wide head flip with the rounded features and move a 24-sample head gradient
+        # by tens of percent, so the chain is checked link by link: the fp32 head kernels against the oracle AT THE DEVICE'S
+        # FEATURES (tight), then the bf16 trunk against the oracle's VJP of the device's d(features) (the bf16 bars of TOL).
+        feat_dev = dqn.online.engine.features(cu(frames), cu(rows)).cpu().numpy()
+        hres, hgrads, dfeat_ref = do.head_loss_and_grads(p_on, feat_dev, y_dev, actions, weights, loss)
+        assert rel_l2(dqn.q.cpu().numpy(), hres['q']) < 1e-5 and abs(float(dqn.loss.item()) - hres['loss']) < 1e-5 * max(1.0, hres['loss'])
+        check(hgrads, 2e-4, 0.999999)
+        assert rel_l2(dqn.dfeat.cpu().numpy(), dfeat_ref) < 2e-4
+        check(do.trunk_vjp(p_on, obs, dqn.dfeat.cpu().numpy()), 0.12, 0.99)
+    # the engine's own (unused) policy / value heads receive no gradient
+    for k, v in dqn.online.engine.named_views(dqn.online.engine.grads).items():
+        if k not in po.TRUNK_KEYS:
+            assert float(v.abs().max()) == 0.0, k
+
+
+def test_dqn_learner_step_updates_network_priorities_and_target():
+    """One whole learner step: prioritized sample of 32 of 256 stored transitions, update, |td| priorities back into the sum-tree
+    (bit-exact vs the buffer's own update path), Adam on trunk + head against torch.optim.Adam semantics, target sync."""
+    from oracle import dqn_oracle as do
+    A, nb, cap = 6, 32, 256
+    dqn, _ = _dqn_setup('fp32', A, nb, cap, gamma=0.99, lr=1e-3, target_update_interval=3, beta=0.5)
+    dqn.sync_target()
+    rs = np.random.RandomState(3)
+    obs, _, actions, rewards, dones, _ = do.make_case(12, cap, A)
+    dqn.replay.add(cu(obs), cu(actions), cu(rewards), cu(dones))
+    dqn.replay.update_priorities(cu(np.arange(cap, dtype=np.int64)), cu(rs.uniform(0.1, 2.0, cap).astype(F32)))
+    uni = cu(rs.uniform(size=nb).astype(F32))
+    p0 = dqn.online.engine.params.clone()
+    h0 = dqn.head.flat.clone()
+    tree0 = dqn.replay.index.tree.tree.clone()
+    expect = dqn.replay.sample(nb, 0.5, uni)                                # same uniform numbers -> the same batch
+    loss = dqn.learner_step(uni)
+    tc.cuda.synchronize()
+    assert np.isfinite(float(loss.item())) and dqn.steps == 1 and dqn.online.engine.adam_steps == 1
+    # first Adam step: every parameter with a non-zero gradient moves by lr * sign(g) (torch.optim.Adam, bias-corrected)
+    for params, before, grads in ((dqn.online.engine.params, p0, dqn.online.engine.grads), (dqn.head.flat, h0, dqn.head_grads)):
+        g = grads.cpu().numpy()
+        step = (params - before).cpu().numpy()
+        nzm = np.abs(g) > 1e-6
+        assert nzm.sum() > 1000 if params is dqn.online.engine.params else nzm.sum() > 100
+        np.testing.assert_allclose(step[nzm], -1e-3 * np.sign(g[nzm]), rtol=2e-2)
+        assert np.all(step[g == 0] == 0)
+    # priorities of the sampled transitions = (|td| + eps)^alpha through the buffer's own kernel; everything else untouched
+    idx = expect['idx']
+    want = tree0.clone()
+    from pytorch_drl_b200.replay import SumTree
+    ref_tree = SumTree(cap, dev())
+    ref_tree.tree.copy_(want)
+    ref_tree.update(idx, (dqn.td.abs() + 1e-6).pow(0.6).float())
+    assert tc.equal(dqn.replay.index.tree.tree, ref_tree.tree)
+    # the target network follows every 3rd step
+    assert not tc.equal(dqn.target.engine.params, dqn.online.engine.params)
+    dqn.learner_step()
+    dqn.learner_step()
+    assert dqn.steps == 3 and tc.equal(dqn.target.engine.params, dqn.online.engine.params) and tc.equal(dqn.target_head.flat, dqn.head.flat)
+    # module parameters ARE the flat buffers (state_dict sees the update)
+    sd = dqn.online.state_dict()
+    assert tc.equal(sd[do.HEAD_PREFIX + '_proj.0.bias'], dqn.head.views()['_proj.0.bias'])
+
+
 # ---- checkpoint / resume (SURVEY §8 f2, f3): complete optimizer + RND state in the reference's formats --------------------
 def _ppo_for_resume(precision, seed=0):
     from pytorch_drl_b200 import agents, algos

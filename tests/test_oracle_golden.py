@@ -287,3 +287,26 @@ def test_actor_rollout_oracle_vs_reference_rollout_manager_golden(golden_dir):
     fs = ao.HostFrameStack(ao.SingleFrameEnv(9, A, False))
     stacks = [fs.reset()] + [fs.step(k % A)[0] for k in range(5)] + [fs.reset()] + [fs.step(k % A)[0] for k in range(3)]
     np.testing.assert_array_equal(ao.frame_checksums(np.stack(stacks)), g['framestack_sums'])
+
+
+def test_dqn_oracle_vs_reference_modules_golden(golden_dir):
+    """oracle/dqn_oracle.py (NatureCNN + dueling head + double-Q Bellman targets + TD loss, torch autograd) against
+    tests/golden/dqn.npz = the same loss through the reference's OWN Agent / SimpleDiscreteActionValueHead(DuelingArchitecture) /
+    SimpleDiscreteBellmanOptimalityOperator (oracle/make_golden.py::gen_dqn): Q values, targets, loss and every gradient tensor."""
+    from oracle import dqn_oracle as do
+    g = np.load(os.path.join(golden_dir, 'dqn.npz'))
+    for i in range(int(g['ncases'])):
+        A, nb, gamma, ud, dq, sl1, s_on, s_tg, s_case = g[f'c{i}_meta']
+        A, nb = int(A), int(nb)
+        p, pt = do.init_params(A, int(s_on)), do.init_params(A, int(s_tg))
+        obs, nxt, actions, rewards, dones, weights = do.make_case(int(s_case), nb, A)
+        res, grads = do.loss_and_grads(p, pt, obs, nxt, actions, rewards, dones, weights, float(gamma), bool(ud), bool(dq),
+                                       'SmoothL1Loss' if sl1 else 'MSELoss')
+        np.testing.assert_allclose(res['q'], g[f'c{i}_q'], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(res['y'], g[f'c{i}_y'], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(res['loss'], float(g[f'c{i}_loss']), rtol=1e-5)
+        summ = do.summarize_grads(grads, list(grads.keys()))
+        assert sum(float(g[f'c{i}_n_{k}']) > 0 for k in grads) >= 14            # the case exercises (nearly) every tensor
+        for k, v in summ.items():
+            ref = g[f'c{i}_{k}']
+            np.testing.assert_allclose(v, ref, rtol=1e-4, atol=1e-6 * max(float(np.abs(ref).max()), 1e-6), err_msg=f'case {i} {k}')
