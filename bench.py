@@ -804,8 +804,8 @@ def run_dqn_extras(rollout, dev, g):
     tc.cuda.empty_cache()
     return {'workload': 'double / dueling DQN (NatureCNN trunk + DuelingArchitecture head), 2^20-transition prioritized replay, batch 512',
             'ms_per_step': ms, 'samples_per_s': nb / (ms * 1e-3), 'host_enqueue_ms_per_step': host_ms, 'final_loss': loss,
-            'trunk_passes_per_step': '3 forward (online s, online s\', target s\') + 1 recomputed forward + 1 backward at 512 samples',
-            'bound': 'launch latency: ~45 launches of 4-148 CTAs per step; the host enqueue time is the floor when larger',
+            'trunk_passes_per_step': '3 forward (target s\', online s\', online s) + 1 backward on the live activations of the last one, at 512 samples',
+            'bound': 'launch latency: ~40 launches of 4-148 CTAs per step; the host enqueue time is the floor when larger',
             'parity': 'network blocks + Bellman operator pinned to the reference (tests/golden/dqn.npz); the algorithm itself has no reference '
                       'counterpart (the reference ships no DQN learner and its dueling head cannot be differentiated as written: dueling.py:53)'}
 

@@ -402,10 +402,11 @@ int drl_comm_p2p_import(drl_comm_t* comm, const uint8_t* handles_all /* [world][
 int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dlogits,
                      const float* dvalues, float* grads, void* stream);
 /* The same for a head that lives outside the handle (the DQN action-value head): trunk gradients from dfeat [nb, 512] =
- * d loss / d(the features drl_net_features returned).  Activations are recomputed; `grads` (flat, drl_net_param_count
- * floats) is overwritten, the slices of the handle's own policy / value heads stay zero. */
+ * d loss / d(the features drl_net_features returned).  Activations are recomputed unless reuse_forward != 0, which asserts that
+ * the LAST call on this handle was drl_net_features on exactly (obs, row_idx, nb); `grads` (flat, drl_net_param_count floats)
+ * is overwritten, the slices of the handle's own policy / value heads stay zero. */
 int drl_net_backward_features(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dfeat,
-                              float* grads, void* stream);
+                              float* grads, int reuse_forward, void* stream);
 /* Attach (or detach, comm = NULL) a communicator to a network handle: drl_net_ppo_step then returns gradients
  * that are already SUMMED over the ranks — what DistributedDataParallel's backward hooks do in the reference
  * (drl/utils/launch.py:310, drl/algos/ppo.py:233) — and overlaps the exchange with the backward pass: the

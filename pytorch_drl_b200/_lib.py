@@ -53,7 +53,7 @@ PROTOTYPES = {
     'drl_net_destroy': (c_int, [c_void_p]),
     'drl_net_set_comm': (c_int, [c_void_p, c_void_p]),
     'drl_net_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'drl_net_backward_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'drl_net_backward_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'drl_net_param_count': (c_int64, [c_int, c_int]),
     'drl_net_param_offsets': (c_int, [c_int, c_int, POINTER(c_int64), c_int]),
     'drl_net_set_params': (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -141,7 +141,8 @@ class DQN:
             ptr(q_next_on) if q_next_on is not None else None, ptr(q_next_tgt), ptr(w) if w is not None else None,
             float(self.gamma), int(self.use_dones), int(self.double_q), int(self.smooth_l1), ptr(self.q), ptr(self.td), ptr(self.y),
             ptr(self.loss), ptr(self.dfeat), ptr(self.head_grads), ptr(self._ws), current_stream()), 'dueling_loss_backward')
-        check(self._L.drl_net_backward_features(eng._h, ptr(frames), ptr(rows), nb, ptr(self.dfeat), ptr(eng.grads),
+        # the online engine's last pass was features(frames, rows) just above (one chunk: nb <= max_batch): its activations are live
+        check(self._L.drl_net_backward_features(eng._h, ptr(frames), ptr(rows), nb, ptr(self.dfeat), ptr(eng.grads), 1,
                                                 current_stream()), 'net_backward_features')
         return self.loss
 

@@ -250,13 +250,14 @@ extern "C" int drl_net_backward(drl_net_t* net, const uint8_t* obs, const int64_
 }
 
 extern "C" int drl_net_backward_features(drl_net_t* net, const uint8_t* obs, const int64_t* row_idx, int nb, const float* dfeat,
-                                         float* grads, void* stream) {
+                                         float* grads, int reuse_forward, void* stream) {
   DRL_TRY(check_call(net, obs, nb));
   if (!dfeat || !grads) return DRL_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
   const bool bf16 = net->precision == DRL_PRECISION_BF16;
   DRL_CUDA(cudaMemsetAsync(grads, 0, (size_t)net->nparams * sizeof(float), st));
-  DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, false, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
+  // reuse_forward: the caller's LAST call on this handle was drl_net_features on exactly (obs, row_idx, nb): the activations are live
+  if (!reuse_forward) DRL_TRY(bf16 ? bf16_trunk_forward(net, obs, row_idx, nb, false, st) : fp32_trunk_forward(net, obs, row_idx, nb, st));
   if (bf16)
     dfeat_to_dpre_kernel<__nv_bfloat16><<<(nb + 63) / 64, 512, 0, st>>>(net->feat, dfeat, nb, reinterpret_cast<__nv_bfloat16*>(net->dpre),
                                                                        grads + net->off[7]);
