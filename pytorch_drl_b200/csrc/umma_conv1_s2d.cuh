@@ -9,15 +9,17 @@
 //                (64B swizzle; the x = 20 column is the TMA unit's out-of-bounds zero fill)
 //   8 converter  raw frame -> bf16 "block image": row q = by*21 + bx holds the block's 64 values (128 B,
 //   warps        128B swizzle), element e = dy*16 + px*4 + ci.  Every pixel is converted ONCE.
-//   MMA warp     dW^T[tap-pair block ty][128 = (tx, e)][32 co] += sum over rows r of image[r + ty*21 + tx][e] * dY[r][co]
-//                Both operands are MN-major; the A operand of tap (ty, tx) is the block image shifted by
-//                ty*21 + tx rows, read in place through a descriptor whose start address is advanced by the
-//                shift; the two taps of a block are its two 64-wide atoms (leading-dimension offset = 128 B).
-//                27 k-steps of 16 rows cover r < 432; rows with x = 20 or r >= 420 meet zero dY rows.
-//   epilogue     after the last sample: TMEM -> red.global.add.f32 into the OIHW gradient, scaled by 1/255.
+//   MMA warp     dW^T[(tap, co)][e] += sum over image rows q of dY[q - off_tap][co] * image[q][e],  off_tap = ty*21 + tx.
+//                Both operands are MN-major and read in place: A = the dY tile (64B swizzle), one 32-channel atom per tap, a PAIR
+//                of taps per MMA (M = 64; atom 0 = the tap with the larger offset, leading-dimension offset = one dY row; the
+//                window of a tap starts `off` rows BEFORE the tile: 22 zero rows lead each tile, 28 follow it), B = the block
+//                image (N = 64 elements of a block).  28 k-steps of 16 rows cover q < 448; dY rows with x = 20 or r >= 420 are
+//                zeros.  4 KB of operands per MMA; the image-as-A form (M = 128 = two taps x 64 elements, N = 32 channels: 5 KB)
+//                it replaces took 0.355 instead of 0.333 ms.
+//   epilogue     after the last sample: TMEM (M = 64: rows in lanes 0-15 of each quarter) -> atomicAdd into the OIHW gradient,
+//                scaled by 1/255.
 //
-// Per sample the shared-memory traffic is 28 KB (raw) + 2 x 55 KB (image write + 2 x 2 taps x ... read by the
-// MMAs as 54 x 5 KB) instead of ~3.1 tiles x 176 KB for the im2col kernel (umma_conv1.cuh).
+// Per sample the shared-memory traffic is 28 KB (raw) + 56 KB (image write) + 28 KB raw read + 56 MMAs x 4 KB of operand fetch.
 #pragma once
 #include <cuda.h>
 #include <type_traits>
@@ -29,12 +31,16 @@
 namespace drl {
 
 constexpr int kS2dRawBytes = 28672;                  // 28 224 B frame, padded to 1 KB
-constexpr int kS2dImgRows = 456;                     // 441 block rows + the shift of the last k-step (432 + 22), zero tail
-constexpr int kS2dImgBytes = kS2dImgRows * 128;      // 58 368 B = 57 KB
-constexpr int kS2dDyRows = 432;                      // 27 k-steps x 16 rows; TMA writes rows < 420
-constexpr int kS2dDyBytes = kS2dDyRows * 64;         // 27 648 B = 27 KB
-constexpr int kS2dKSteps = 27;
-constexpr int kS2dWgradSmem = 2 * (kS2dRawBytes + kS2dImgBytes + kS2dDyBytes) + 256 + 1024;
+constexpr int kS2dKSteps = 28;                       // 28 x 16 = 448 block-image rows q cover 441 blocks + the largest dY shift
+constexpr int kS2dImgRows = 448;                     // 441 block rows, zero tail
+constexpr int kS2dImgBytes = kS2dImgRows * 128;      // 57 344 B = 56 KB
+// dY region: [22 zero rows][tile 0: 420 rows][28 zero rows][tile 1: 420 rows][28 zero rows] of 64 B.  A tap window reads dY rows
+// q - off, off in {0, 1, 21, 22}, q < 448: up to 22 rows before and 28 rows behind a tile, which are zeros (the gap is shared).
+constexpr int kS2dDyLead = 22, kS2dDyPitchRows = 448;
+constexpr int kS2dDyPitch = kS2dDyPitchRows * 64;    // 28 672 B between the two tiles
+constexpr int kS2dDyRegion = (kS2dDyLead + 2 * kS2dDyPitchRows) * 64;   // 58 752 B
+constexpr int kS2dWgradSmem = 2 * (kS2dRawBytes + kS2dImgBytes) + kS2dDyRegion + 256 + 1024;
+static_assert(kS2dWgradSmem <= 227 * 1024, "conv1 weight-gradient shared-memory plan");
 constexpr int kS2dThreads = 32 * (4 + 1 + 8 + 1);    // epilogue, MMA, converters, TMA
 
 struct Conv1S2dArgs {
@@ -61,8 +67,8 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sImg = smem;                                    // 2 block images
-  uint8_t* sDy = smem + 2 * kS2dImgBytes;                  // 2 dY tiles
-  uint8_t* sRaw = sDy + 2 * kS2dDyBytes;                   // 2 raw frames
+  uint8_t* sDy = smem + 2 * kS2dImgBytes + kS2dDyLead * 64;   // 2 dY tiles (kS2dDyPitch apart) inside the zero-padded dY region
+  uint8_t* sRaw = smem + 2 * kS2dImgBytes + kS2dDyRegion;  // 2 raw frames
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + 2 * kS2dRawBytes);
   uint64_t* raw_full = bars;          // [2]
   uint64_t* raw_empty = bars + 2;     // [2]
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
 
   // rows the producers never write must read as finite zeros: image rows >= 441 (they only ever meet zero dY
   // rows, but 0 * NaN would poison the sum) and dY rows >= 420
-  for (int i = threadIdx.x * 16; i < 2 * (kS2dImgBytes + kS2dDyBytes); i += blockDim.x * 16)
+  for (int i = threadIdx.x * 16; i < 2 * kS2dImgBytes + kS2dDyRegion; i += blockDim.x * 16)
     st_shared_v4(smem_u32(smem + i), make_uint4(0u, 0u, 0u, 0u));
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 64);
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
   if (warp == 13 && lane == 0) tma_prefetch_desc(&tmap_dy);
   tc_fence_before();
   __syncthreads();
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
           tma_bulk_g2s(sRaw + s * kS2dRawBytes, args.obs + srow * kC1FrameBytes, kC1FrameBytes, raw_full + s);
           mbar_wait(img_empty + s, ph ^ 1);                 // the MMAs of sample j-2 are done with this dY tile
           mbar_arrive_expect_tx(dy_full + s, 420 * 64);
-          tma_load_4d_s2d(sDy + s * kS2dDyBytes, &tmap_dy, 0, 0, 0, b, dy_full + s);
+          tma_load_4d_s2d(sDy + s * kS2dDyPitch, &tmap_dy, 0, 0, 0, b, dy_full + s);
         }
       }
       __syncwarp();
@@ -144,22 +150,27 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
       }
     } else if (warp == 4) {
       // ================= MMA issuer =================
-      constexpr uint32_t idesc = make_idesc_f16(1u, 128, 32, 1, 1);     // bf16, MN-major A and B
-      constexpr uint32_t a_hi = desc_hi(1024, LAYOUT_SW128), b_hi = desc_hi(512, LAYOUT_SW64);
-      // block ty: atoms (ty, tx = 0 / 1) are the image shifted by ty*21 and ty*21 + 1 rows -> LBO = 128 B
-      const uint32_t a_base0 = desc_lo(smem_u32(sImg), 128), a_base1 = desc_lo(smem_u32(sImg) + 21 * 128, 128);
-      const uint32_t b_base = desc_lo(smem_u32(sDy), 0);
+      // dW^T[(tap, co)][e] += sum_q dY[q - off_tap][co] * image[q][e]: the A operand is the dY tile (MN-major, 64B swizzle; one
+      // 32-channel atom per tap), a PAIR of taps per MMA (M = 64: atom 0 = the tap with the larger offset, leading-dimension offset =
+      // one dY row), the B operand the block image itself (MN-major, N = 64 elements of a block).  Two accumulators (pairs
+      // {(0,1), (0,0)} and {(1,1), (1,0)}) are issued interleaved.  2 KB + 2 KB of operands per MMA instead of 4 KB + 1 KB for the
+      // image-as-A form (M = 128 = two taps x 64 elements, N = 32): 20 % less shared-memory operand traffic.
+      constexpr uint32_t idesc = make_idesc_f16(1u, 64, 64, 1, 1);      // bf16, MN-major A and B
+      constexpr uint32_t a_hi = desc_hi(512, LAYOUT_SW64), b_hi = desc_hi(1024, LAYOUT_SW128);
+      const uint32_t a_base0 = desc_lo(smem_u32(sDy) - 1 * 64, 64), a_base1 = desc_lo(smem_u32(sDy) - 22 * 64, 64);
+      const uint32_t b_base = desc_lo(smem_u32(sImg), 0);
       auto issue = [&](uint32_t a_off, uint32_t b_off, auto first) {
         constexpr bool FIRST = decltype(first)::value;
 #pragma unroll
         for (int k = 0; k < kS2dKSteps; ++k) {
-          const uint32_t bl = b_base + b_off + k * ((16 * 64) >> 4);
+          const uint32_t bl = b_base + b_off + k * ((16 * 128) >> 4);
+          const uint32_t ak = a_off + k * ((16 * 64) >> 4);
           if (FIRST && k == 0) {
-            mma_f16_lohi<false>(tmem_base, a_base0 + a_off, a_hi, bl, b_hi, idesc);
-            mma_f16_lohi<false>(tmem_base + 32, a_base1 + a_off, a_hi, bl, b_hi, idesc);
+            mma_f16_lohi<false>(tmem_base, a_base0 + ak, a_hi, bl, b_hi, idesc);
+            mma_f16_lohi<false>(tmem_base + 64, a_base1 + ak, a_hi, bl, b_hi, idesc);
           } else {
-            mma_f16_lohi<true>(tmem_base, a_base0 + a_off + k * ((16 * 128) >> 4), a_hi, bl, b_hi, idesc);
-            mma_f16_lohi<true>(tmem_base + 32, a_base1 + a_off + k * ((16 * 128) >> 4), a_hi, bl, b_hi, idesc);
+            mma_f16_lohi<true>(tmem_base, a_base0 + ak, a_hi, bl, b_hi, idesc);
+            mma_f16_lohi<true>(tmem_base + 64, a_base1 + ak, a_hi, bl, b_hi, idesc);
           }
         }
       };
@@ -169,8 +180,8 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
         mbar_wait(dy_full + s, ph);
         tc_fence_after();
         if (elect_one()) {
-          if (j == 0) issue(s * (kS2dImgBytes >> 4), s * (kS2dDyBytes >> 4), std::true_type{});
-          else issue(s * (kS2dImgBytes >> 4), s * (kS2dDyBytes >> 4), std::false_type{});
+          if (j == 0) issue(s * (kS2dDyPitch >> 4), s * (kS2dImgBytes >> 4), std::true_type{});
+          else issue(s * (kS2dDyPitch >> 4), s * (kS2dImgBytes >> 4), std::false_type{});
           mma_commit(img_empty + s);
         }
         __syncwarp();
@@ -179,19 +190,27 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
       __syncwarp();
     } else {
       // ================= epilogue (once): TMEM -> OIHW gradient =================
+      // M = 64 accumulators keep their rows in lanes 0-15 of every 32-lane quarter: row m = 16 * quarter + lane = (tap of the pair, co)
       mbar_wait(done, 0);
       tc_fence_after();
 #pragma unroll
-      for (int ty = 0; ty < 2; ++ty) {
-        const int i = threadIdx.x;                          // row of the block: (tx, e)
-        const int tx = i >> 6, e = i & 63;
-        const int ky = 4 * ty + (e >> 4), kx = 4 * tx + ((e >> 2) & 3), ci = e & 3;
-        float* g0 = args.gw + (ci * 8 + ky) * 8 + kx;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + ty * 32, r);
-        tmem_ld_wait();
+      for (int pr = 0; pr < 2; ++pr) {
 #pragma unroll
-        for (int co = 0; co < 32; ++co) atomicAdd(g0 + co * 256, __uint_as_float(r[co]) * args.scale);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + pr * 64 + half * 32, r);
+          tmem_ld_wait();
+          if (lane < 16) {
+            const int m = 16 * warp + lane, tp = m >> 5, co = m & 31;
+            const int ty = pr, tx = 1 - tp;                  // pair pr: atom 0 = tap (ty, 1), atom 1 = tap (ty, 0)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int e = half * 32 + c;
+              const int ky = 4 * ty + (e >> 4), kx = 4 * tx + ((e >> 2) & 3), ci = e & 3;
+              atomicAdd(args.gw + ((co * 4 + ci) * 8 + ky) * 8 + kx, __uint_as_float(r[c]) * args.scale);
+            }
+          }
+        }
       }
     }
   }
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(kS2dThreads, 1) conv1_wgrad_s2d_kernel(const _
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
