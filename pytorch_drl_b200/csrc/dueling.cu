@@ -15,7 +15,7 @@
 namespace drl {
 
 constexpr int kDuelWarps = 8;
-constexpr int kDuelMaxIn = 512, kDuelMaxP = 64, kDuelMaxH = 32;
+constexpr int kDuelMaxIn = 512;
 
 struct DuelingParams {
   const float *w0, *b0, *wa1, *ba1, *wa2, *ba2, *wv1, *bv1, *wv2, *bv2;
@@ -310,6 +310,19 @@ __global__ void __launch_bounds__(256) dueling_proj_dgrad_kernel(const float* __
   dfeat[(size_t)i * in_dim + k] = acc;
 }
 
+constexpr int kDuelMaxDevices = 64;
+template <typename Kern>
+static int duel_ensure_smem(Kern kern, size_t smem, size_t (&configured)[kDuelMaxDevices]) {
+  int dev = 0;
+  DRL_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kDuelMaxDevices) return DRL_ERR_BAD_ARG;
+  if (configured[dev] < smem) {
+    DRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = smem;
+  }
+  return DRL_OK;
+}
+
 }  // namespace drl
 
 using namespace drl;
@@ -324,11 +337,8 @@ extern "C" int drl_dueling_forward_f32(const float* feat, int nb, int in_dim, in
   const int P = 50 * widening, H = 25 * widening, A = num_actions;
   const size_t smem = sizeof(float) * ((size_t)in_dim * P + 2 * P * H + A * H + H + (P + 2 * H + A + 1) +
                                        (size_t)kDuelWarps * (in_dim + P + 2 * H));
-  static size_t configured = 0;
-  if (configured < smem) {
-    DRL_CUDA(cudaFuncSetAttribute(dueling_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static size_t configured[kDuelMaxDevices] = {0};       // the attribute is a per-device setting
+  DRL_TRY(duel_ensure_smem(dueling_forward_kernel, smem, configured));
   int blocks = (nb + kDuelWarps - 1) / kDuelWarps;
   if (blocks > sm_count()) blocks = sm_count();
   DuelingParams p{w0, b0, wa1, ba1, wa2, ba2, wv1, bv1, wv2, bv2};
@@ -378,11 +388,8 @@ extern "C" int drl_dueling_loss_backward_f32(const float* feat, int nb, int in_d
   const int n_gacc = 2 * H * P + A * H + H + H + A + H + 1;
   const size_t smem = sizeof(float) * ((size_t)in_dim * P + 2 * P * H + A * H + H + (P + 2 * H + A + 1) + n_gacc +
                                        (size_t)kDuelWarps * (in_dim + 2 * P + 4 * H + 32));
-  static size_t configured = 0;
-  if (configured < smem) {
-    DRL_CUDA(cudaFuncSetAttribute(dueling_loss_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static size_t configured[kDuelMaxDevices] = {0};
+  DRL_TRY(duel_ensure_smem(dueling_loss_backward_kernel, smem, configured));
   int blocks = (nb + kDuelWarps - 1) / kDuelWarps;
   if (blocks > sm_count()) blocks = sm_count();
   dueling_loss_backward_kernel<<<blocks, kDuelWarps * 32, smem, st>>>(

@@ -115,6 +115,8 @@ class PrioritizedReplayBuffer:
 
     Transition i = (observation stack frames[i] uint8 [84, 84, 4], action, reward, done); its successor stack is frames[i + 1]
     (consecutive writes of one environment stream; at 28 224 B per stack a 2^20-entry ring is 29.6 GB of the B200's 180 GB).
+    The NEWEST transition has no successor yet (frames[cursor] still holds the oldest stack, or nothing): it keeps priority 0
+    until the next `add` delivers its successor, so it can never be sampled with a wrong s'.
     `sample` returns the batch's indices, importance weights and scalars, the frame ring itself (the fused NatureCNN trunk
     gathers rows by index: no copy is needed to run `QAgent` on the batch) and, on request, gathered copies of the
     observation / successor stacks (`drl_ring_gather`)."""
@@ -129,10 +131,12 @@ class PrioritizedReplayBuffer:
         self.rewards = tc.zeros(capacity, dtype=tc.float32, device=dev)
         self.dones = tc.zeros(capacity, dtype=tc.float32, device=dev)
         self.cursor, self.count = 0, 0
+        self._open = None              # slot of the newest transition (priority 0 until its successor is written)
         self._L = _lib.lib()
 
-    def add(self, frames: tc.Tensor, actions: tc.Tensor, rewards: tc.Tensor, dones: tc.Tensor) -> tc.Tensor:
-        """Append n transitions at the ring cursor (wrapping); they get the maximal priority.  Returns their slots."""
+    def add(self, frames: tc.Tensor, actions: tc.Tensor, rewards: tc.Tensor, dones: tc.Tensor, max_priority: float = 1.0) -> tc.Tensor:
+        """Append n transitions at the ring cursor (wrapping); they get the maximal priority (Schaul et al. 2015, Algorithm 1
+        line 6) except the newest one, which waits for its successor.  Returns their slots."""
         n = frames.shape[0]
         if n > self.capacity:
             raise ValueError('more transitions than the ring holds')
@@ -146,7 +150,13 @@ class PrioritizedReplayBuffer:
                 dst[:n - first] = src[first:]
         self.cursor = (self.cursor + n) % self.capacity
         self.count = min(self.capacity, self.count + n)
-        self.index.add(slots, count=self.count)
+        # max priority for the new transitions and for the one that was waiting for its successor; 0 for the newest one
+        upd = slots if self._open is None else tc.cat([tc.tensor([self._open], device=dev, dtype=tc.int64), slots])
+        pr = tc.full((upd.numel(),), max_priority, dtype=tc.float32, device=dev)
+        pr[-1] = 0.0
+        self.index.tree.update(upd, pr)
+        self.index.size = self.count
+        self._open = int((self.cursor - 1) % self.capacity)
         return slots
 
     def gather_frames(self, idx: tc.Tensor, shift: int = 0) -> tc.Tensor:

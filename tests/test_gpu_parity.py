@@ -1330,7 +1330,7 @@ def test_prioritized_replay_buffer_vs_oracle():
     # empty buffer: weights 0, no NaN
     e = buf.sample(16, beta, cu(np.full(16, 0.5, F32)))
     assert tc.isfinite(e['weights']).all() and float(e['weights'].abs().sum()) == 0.0
-    cursor = 0
+    cursor, open_slot = 0, None
     for n in (700, 500):                                           # the second add wraps around
         fr = rs.randint(0, 256, size=(n, 8, 8, 4)).astype(np.uint8)
         ac, rw, dn = rs.randint(0, 6, size=n).astype(np.int64), rs.standard_normal(n).astype(F32), (rs.uniform(size=n) < 0.1).astype(F32)
@@ -1338,9 +1338,15 @@ def test_prioritized_replay_buffer_vs_oracle():
         want = (np.arange(n) + cursor) % cap
         assert np.array_equal(slots, want)
         frames_ref[want], act_ref[want], rew_ref[want] = fr, ac, rw
-        ref.update(want, np.ones(n, F32))
+        # max priority for the new transitions and for the one that was waiting for its successor; the newest one stays at 0
+        upd = want if open_slot is None else np.concatenate([[open_slot], want])
+        pr = np.ones(len(upd), F32)
+        pr[-1] = 0.0
+        ref.update(upd, pr)
         cursor = (cursor + n) % cap
+        open_slot = (cursor - 1) % cap
     assert buf.count == cap and buf.cursor == 1200 % cap
+    assert float(buf.index.tree.leaves[open_slot]) == 0.0        # the newest transition waits for its successor: never sampled
     assert np.array_equal(buf.index.tree.tree.cpu().numpy().view(np.uint32), ref.tree.view(np.uint32))
     # TD-error priorities for a batch, then a sampled batch
     upd = rs.permutation(cap)[:300].astype(np.int64)
