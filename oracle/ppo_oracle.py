@@ -146,13 +146,17 @@ def scale_obs(obs_u8: tc.Tensor) -> tc.Tensor:
     return obs_u8.to(tc.float32) * tc.tensor(float(SCALE_1_255), dtype=tc.float32)
 
 
-def trunk_forward(p: Dict[str, tc.Tensor], obs_f32_nhwc: tc.Tensor, keep: Optional[dict] = None) -> tc.Tensor:
-    """ToChannelMajor (vision.py:8-9) + NatureCNN (nature_cnn.py:27-36)."""
+def trunk_forward(p: Dict[str, tc.Tensor], obs_f32_nhwc: tc.Tensor, keep: Optional[dict] = None,
+                  masks: Optional[dict] = None) -> tc.Tensor:
+    """ToChannelMajor (vision.py:8-9) + NatureCNN (nature_cnn.py:27-36).  `masks` (tests only): 0/1 tensors act1 / act2 / act3
+    (NCHW) / feat that REPLACE the ReLU decisions (`z * mask` instead of `relu(z)`) — the gradient of the network with another
+    forward's ReLU pattern, used to separate the tensor-core engine's arithmetic error from its ReLU-mask flips."""
+    relu = (lambda z, name: F.relu(z)) if masks is None else (lambda z, name: z * masks[name])
     x = obs_f32_nhwc.permute(0, 3, 1, 2)
-    a1 = F.relu(F.conv2d(x, p[TRUNK_KEYS[0]], p[TRUNK_KEYS[1]], stride=4))
-    a2 = F.relu(F.conv2d(a1, p[TRUNK_KEYS[2]], p[TRUNK_KEYS[3]], stride=2))
-    a3 = F.relu(F.conv2d(a2, p[TRUNK_KEYS[4]], p[TRUNK_KEYS[5]], stride=1))
-    feat = F.relu(F.linear(a3.flatten(1), p[TRUNK_KEYS[6]], p[TRUNK_KEYS[7]]))
+    a1 = relu(F.conv2d(x, p[TRUNK_KEYS[0]], p[TRUNK_KEYS[1]], stride=4), 'act1')
+    a2 = relu(F.conv2d(a1, p[TRUNK_KEYS[2]], p[TRUNK_KEYS[3]], stride=2), 'act2')
+    a3 = relu(F.conv2d(a2, p[TRUNK_KEYS[4]], p[TRUNK_KEYS[5]], stride=1), 'act3')
+    feat = relu(F.linear(a3.flatten(1), p[TRUNK_KEYS[6]], p[TRUNK_KEYS[7]]), 'feat')
     if keep is not None:
         keep.update(act1=a1, act2=a2, act3=a3, feat=feat)
     return feat
@@ -255,7 +259,7 @@ def annotate(params: Dict[str, np.ndarray], obs_u8: np.ndarray, actions: np.ndar
 
 
 def minibatch_losses_and_grads(params: Dict[str, np.ndarray], envs: List[dict], hp: Hyper,
-                               want_grads: bool = True, keep: Optional[dict] = None):
+                               want_grads: bool = True, keep: Optional[dict] = None, masks: Optional[List[dict]] = None):
     """One learner step over `len(envs)` ranks.  `envs[n]` holds the minibatch of rank/env n:
     obs uint8[B,84,84,4], actions[B], logprobs[B], advantages{k}[B], vpreds{k}[B], vtargs{k}[B].
     Loss per rank = ppo.py:172-207; gradients = mean over ranks (DDP, launch.py:310 / ppo.py:233);
@@ -263,9 +267,9 @@ def minibatch_losses_and_grads(params: Dict[str, np.ndarray], envs: List[dict], 
     rk = list(hp.reward_weights.keys())
     p = {k: tc.from_numpy(v.copy()).requires_grad_(want_grads) for k, v in params.items()}
     per_rank = []
-    for e in envs:
+    for n, e in enumerate(envs):
         k2 = {} if keep is not None else None
-        feat = trunk_forward(p, scale_obs(tc.from_numpy(e['observations'])), k2)
+        feat = trunk_forward(p, scale_obs(tc.from_numpy(e['observations'])), k2, None if masks is None else masks[n])
         logits, values = heads_forward(p, feat, rk)
         logp, ent = categorical_logprob_entropy(logits, tc.from_numpy(e['actions']))
         if keep is not None:

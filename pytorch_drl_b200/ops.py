@@ -87,6 +87,9 @@ def make_batch(actions: tc.Tensor, logp_old: tc.Tensor, adv: Sequence[tc.Tensor]
         b.adv[k] = ptr(_cuda(adv[k], tc.float32, 'advantages'))
         b.vtarg[k] = ptr(_cuda(vtarg[k], tc.float32, 'vtargs'))
         b.v_old[k] = ptr(v_old[k]) if v_old[k] is not None else None
+    # the struct carries raw device pointers: keep the tensors alive as long as the struct (a caller that passes temporaries
+    # would otherwise hand the kernels freed memory)
+    b._keepalive = (actions, logp_old, tuple(adv), tuple(v_old), tuple(vtarg))
     return b
 
 
