@@ -20,8 +20,8 @@
 // sample: s32 -> fp32 scale + bias, ReLU folded into the bf16 conversion, ReLU mask word), 1 MMA warp (one election per
 // sample, the tiles issued as interleaved pairs into the 8 accumulators = all 512 TMEM columns), 1 TMA warp (6-frame ring).
 // Measured at 32 768 samples: 0.29 ms = 6.0 TB/s of frame reads + act1 writes (0.92 of the measured HBM peak); the fp16
-// converter kernel it replaces took 0.41 ms.  MMAs alone: 0.25 ms (67 cycles per MMA: the 16-byte row pitch makes 3 of 4
-// core-matrix fetches straddle two 128-byte lines).
+// converter kernel it replaces took 0.41 ms.  MMAs alone: 0.25 ms (67 cycles per MMA, the same ~1.4x over the micro-benchmark's
+// 48 cycles that the bf16 conv kernels show; forcing their tap shifts to 0 does not change it, so it is not an alignment effect).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
