@@ -1168,7 +1168,9 @@ def test_dqn_loss_and_grads_vs_oracle(precision, A, gamma, use_dones, double_q, 
                 continue
             err = rel_l2(gdev, gref)
             cos = float((gdev * gref).sum() / (np.linalg.norm(gdev) * np.linalg.norm(gref)))
+            worst[0] = max(worst[0], err / bar)
             assert err < bar and cos > min_cos, (k, err, cos)
+    worst = [0.0]
     if precision == 'fp32':
         check(grads, t['grad'], 0.999999)                                   # the whole chain against the oracle
     else:
@@ -1181,6 +1183,7 @@ def test_dqn_loss_and_grads_vs_oracle(precision, A, gamma, use_dones, double_q, 
         check(hgrads, 2e-4, 0.999999)
         assert rel_l2(dqn.dfeat.cpu().numpy(), dfeat_ref) < 2e-4
         check(do.trunk_vjp(p_on, obs, dqn.dfeat.cpu().numpy()), 0.12, 0.99)
+    print(f'dqn gradients [{precision}, A={A}]: worst error / bar = {worst[0]:.3f}')
     # the engine's own (unused) policy / value heads receive no gradient
     for k, v in dqn.online.engine.named_views(dqn.online.engine.grads).items():
         if k not in po.TRUNK_KEYS:
